@@ -1,0 +1,113 @@
+"""Generate golden vectors by running the UNMODIFIED reference (`/root/reference`) on the CPU.
+
+Run in the authoring container only (the reference tree does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Inputs and weights come from `lft_b200.synth` (counter-based, reproducible anywhere), so only
+the reference OUTPUTS need to be committed. The reference is imported, never copied:
+  * model/LFT.py   -> get_model(args).forward, plus forward hooks on conv_init / altblock.i.*
+  * utils/utils.py -> LFdivide / LFintegrate (needs a stub `skimage` and a clean sys.argv,
+                      because utils.py:3,7 import skimage and parse argv at import time)
+"""
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from lft_b200 import synth  # noqa: E402
+
+REF = "/root/reference"
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    argv, sys.argv = sys.argv, ["x"]
+    sk = types.ModuleType("skimage")
+    sk.metrics = types.ModuleType("skimage.metrics")
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.metrics", sk.metrics)
+    import model.LFT as ref_model          # noqa
+    import utils.utils as ref_utils        # noqa
+    sys.argv = argv
+    return ref_model, ref_utils
+
+
+def run_case(ref_model, name, A, s, h, B, seed, want_stages):
+    args = types.SimpleNamespace(channels=64, angRes=A, scale_factor=s)
+    net = ref_model.get_model(args)
+    sd = synth.synth_state_dict(A, s, seed)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    lr = torch.from_numpy(synth.synth_lr_mosaic(B, A, h, h, seed))
+    stages = {}
+
+    def cl(t):  # [B,C,N,h,w] -> channels-last [B,N,h,w,C]
+        return t.permute(0, 2, 3, 4, 1).contiguous().numpy()
+
+    hooks = []
+    if want_stages:
+        first = {}
+        hooks.append(net.conv_init.register_forward_hook(
+            lambda m, i, o: first.__setitem__("conv_init_in", i[0]) or first.__setitem__("conv_init_out", o)))
+        for i in (0, 3):
+            hooks.append(net.altblock[i].ang_trans.register_forward_hook(
+                lambda m, inp, o, i=i: stages.__setitem__(f"ang{i}", cl(o.detach()))))
+            hooks.append(net.altblock[i].spa_trans.register_forward_hook(
+                lambda m, inp, o, i=i: stages.__setitem__(f"spa{i}", cl(o.detach()))))
+    with torch.no_grad():
+        out = net(lr)
+    for hk in hooks:
+        hk.remove()
+    if want_stages:
+        stages["conv_init"] = cl((first["conv_init_out"] + first["conv_init_in"]).detach())  # LFT.py:66
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez(path, out=out.numpy(), meta=np.array([A, s, h, B, seed]), **stages)
+    print(name, "out", tuple(out.shape), "absmax", float(out.abs().max()), "->", os.path.getsize(path) // 1024, "KiB")
+
+
+def run_tiler(ref_utils, name, A, h0, w0, s, seed, store_full):
+    lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, seed))
+    sub = ref_utils.LFdivide(lf, A, 32, 16)
+    numU, numV = sub.shape[:2]
+    # stand-in SR patches: integer-valued so that integrate is checked exactly, independent of a net
+    g = torch.arange(numU * numV * (A * 32 * s) ** 2, dtype=torch.float32).remainder(65521.0)
+    fake_sr = g.view(numU, numV, A * 32 * s, A * 32 * s)
+    integ = ref_utils.LFintegrate(fake_sr, A, 32 * s, 16 * s, h0 * s, w0 * s)
+    rec = {
+        "meta": np.array([A, h0, w0, s, seed, numU, numV]),
+        "divide_sha256": np.frombuffer(hashlib.sha256(sub.numpy().tobytes()).digest(), dtype=np.uint8),
+        "integrate_sha256": np.frombuffer(hashlib.sha256(integ.numpy().tobytes()).digest(), dtype=np.uint8),
+    }
+    if store_full:
+        rec["divide"] = sub.numpy()
+        rec["integrate"] = integ.numpy()
+    # identity property noted in SURVEY section 4: integrate(divide(x)) == x at scale 1
+    ident = ref_utils.LFintegrate(sub, A, 32, 16, h0, w0)
+    rec["identity_ok"] = np.array([bool(torch.equal(ident.permute(0, 2, 1, 3).reshape(A * h0, A * w0), lf))])
+    np.savez(os.path.join(HERE, f"{name}.npz"), **rec)
+    print(name, "numU,numV", numU, numV, "identity", rec["identity_ok"][0])
+
+
+def main():
+    torch.manual_seed(0)
+    ref_model, ref_utils = import_reference()
+    # name, A, s, h(=w), B, seed, stages
+    run_case(ref_model, "fwd_A5_s4_h8_B1", 5, 4, 8, 1, 10, True)
+    run_case(ref_model, "fwd_A5_s2_h8_B2", 5, 2, 8, 2, 11, False)
+    run_case(ref_model, "fwd_A3_s2_h12_B1", 3, 2, 12, 1, 12, False)
+    run_case(ref_model, "fwd_A5_s2_h32_B1", 5, 2, 32, 1, 1, False)
+    run_case(ref_model, "fwd_A5_s4_h32_B1", 5, 4, 32, 1, 0, False)
+    run_tiler(ref_utils, "tiler_A3_40x56_s2", 3, 40, 56, 2, 5, True)
+    run_tiler(ref_utils, "tiler_A5_108x156_s4", 5, 108, 156, 4, 3, False)
+    run_tiler(ref_utils, "tiler_A5_128x128_s4", 5, 128, 128, 4, 2, False)
+
+
+if __name__ == "__main__":
+    main()

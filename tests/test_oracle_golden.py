@@ -1,0 +1,85 @@
+"""Pin the oracle (oracle/lft_oracle.py) against outputs of the reference itself
+(tests/golden/*.npz, produced by tests/golden/make_golden.py from /root/reference)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lft_b200 import synth
+from oracle import lft_oracle as O
+
+FWD_CASES = ["fwd_A5_s4_h8_B1", "fwd_A5_s2_h8_B2", "fwd_A3_s2_h12_B1", "fwd_A5_s2_h32_B1"]
+TOL = 2e-5  # fp32 op-order noise between the restatement and the reference modules
+
+
+def _load(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    A, s, h, B, seed = (int(x) for x in g["meta"])
+    sd = synth.synth_state_dict(A, s, seed)
+    lr = torch.from_numpy(synth.synth_lr_mosaic(B, A, h, h, seed))
+    return g, A, s, sd, lr
+
+
+@pytest.mark.parametrize("name", FWD_CASES)
+@pytest.mark.parametrize("mode", ["window", "dense"])
+def test_forward_matches_reference(golden_dir, name, mode):
+    if mode == "dense" and "h32" in name:
+        pytest.skip("dense 1024x1024 path covered by the h8/h12 cases; keeps the CPU suite short")
+    g, A, s, sd, lr = _load(golden_dir, name)
+    stages = {}
+    out = O.forward(sd, lr, A, s, mode=mode, stages=stages).numpy()
+    assert out.shape == g["out"].shape
+    assert np.abs(out - g["out"]).max() <= TOL
+    for k in g.files:
+        if k in ("out", "meta"):
+            continue
+        assert np.abs(stages[k].numpy() - g[k]).max() <= TOL, k
+
+
+def test_forward_fp64_spec_agrees(golden_dir):
+    g, A, s, sd, lr = _load(golden_dir, "fwd_A5_s4_h8_B1")
+    out = O.forward(sd, lr, A, s, mode="window", dtype=torch.float64).numpy()
+    assert np.abs(out - g["out"]).max() <= TOL
+
+
+def test_mask_equals_window():
+    for h in (5, 8, 12):
+        m = O.gen_mask_loop(h, h, 5)
+        idx, valid = O.window_index(h, h, 5)
+        dense = torch.full((h * h, h * h), float("-inf"))
+        rows = torch.arange(h * h)[:, None].expand_as(idx)
+        dense[rows[valid], idx[valid]] = 0.0
+        assert torch.equal(m, dense)
+        assert int(valid.sum(1).min()) == 9 and int(valid.sum(1).max()) == 25
+
+
+@pytest.mark.parametrize("name", ["tiler_A3_40x56_s2", "tiler_A5_108x156_s4", "tiler_A5_128x128_s4"])
+def test_tiler_matches_reference(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    A, h0, w0, s, seed, numU, numV = (int(x) for x in g["meta"])
+    lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, seed))
+    sub = O.lf_divide(lf, A, 32, 16)
+    assert tuple(sub.shape[:2]) == (numU, numV)
+    assert hashlib.sha256(sub.numpy().tobytes()).digest() == bytes(g["divide_sha256"])
+    fake = torch.arange(numU * numV * (A * 32 * s) ** 2, dtype=torch.float32).remainder(65521.0)
+    fake = fake.view(numU, numV, A * 32 * s, A * 32 * s)
+    integ = O.lf_integrate(fake, A, 32 * s, 16 * s, h0 * s, w0 * s)
+    assert hashlib.sha256(integ.numpy().tobytes()).digest() == bytes(g["integrate_sha256"])
+    if "divide" in g.files:
+        assert np.array_equal(sub.numpy(), g["divide"])
+        assert np.array_equal(integ.numpy(), g["integrate"])
+    assert bool(g["identity_ok"][0])
+    ident = O.lf_integrate(sub, A, 32, 16, h0, w0).permute(0, 2, 1, 3).reshape(A * h0, A * w0)
+    assert torch.equal(ident, lf)
+
+
+def test_synth_checkpoint_format(tmp_path):
+    sd = synth.synth_state_dict(5, 4, 0)
+    assert len(sd) == 78 and sum(v.numel() for v in sd.values()) == 1163392
+    assert sum(v.numel() for v in synth.synth_state_dict(5, 2, 0).values()) == 1114240
+    p = tmp_path / "LFT_5x5_4x_epoch_50_model.pth"
+    synth.save_checkpoint(str(p), sd)
+    ck = torch.load(str(p), map_location="cpu")
+    assert ck["epoch"] == 50 and list(ck["state_dict"].keys()) == list(sd.keys())
