@@ -1,0 +1,339 @@
+// Host side of the C ABI (include/lft_b200.h): handle, strict state_dict intake, weight packing into
+// bf16 hi/lo operand slabs, constant position-encoding tables, launch sequences, per-kernel profiling.
+#include "../../include/lft_b200.h"
+#include "host.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace lft {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+// ------------------------------------------------------------------ bf16 helpers (host, RNE like the device)
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// Pack W[N][K] (accessor) into k-slabs: for ks in K/64: hi slab then lo slab, each [kc=8][n=Npad][8] bf16.
+std::vector<uint16_t> pack_weight(int N, int Npad, int K, const std::function<float(int, int)>& w) {
+  const int ks_n = K / 64;
+  std::vector<uint16_t> out((size_t)ks_n * 2 * Npad * 64, 0);
+  for (int ks = 0; ks < ks_n; ++ks)
+    for (int kc = 0; kc < 8; ++kc)
+      for (int n = 0; n < N; ++n)
+        for (int e = 0; e < 8; ++e) {
+          const float x = w(n, ks * 64 + kc * 8 + e);
+          const uint16_t hi = f2bf(x);
+          const uint16_t lo = f2bf(x - bf2f(hi));
+          const size_t base = (size_t)ks * 2 * Npad * 64;
+          out[base + ((size_t)kc * Npad + n) * 8 + e] = hi;
+          out[base + (size_t)Npad * 64 + ((size_t)kc * Npad + n) * 8 + e] = lo;
+        }
+  return out;
+}
+
+// ------------------------------------------------------------------ spec of the reference state_dict
+static void build_spec(Handle* h) {
+  const int C = 64, S = 128, s2 = h->cfg.scale * h->cfg.scale;
+  auto add = [&](const std::string& k, std::vector<int64_t> shp) { h->spec[k] = shp; };
+  add("conv_init0.0.weight", {C, 1, 1, 3, 3});
+  for (int i : {0, 2, 4}) add("conv_init." + std::to_string(i) + ".weight", {C, C, 1, 3, 3});
+  for (int i = 0; i < kLayers; ++i) {
+    std::string p = "altblock." + std::to_string(i) + ".spa_trans.";
+    add(p + "MLP.weight", {S, 9 * C});
+    add(p + "norm.weight", {S});
+    add(p + "norm.bias", {S});
+    add(p + "attention.in_proj_weight", {3 * S, S});
+    add(p + "attention.out_proj.weight", {S, S});
+    add(p + "feed_forward.0.weight", {S});
+    add(p + "feed_forward.0.bias", {S});
+    add(p + "feed_forward.1.weight", {2 * S, S});
+    add(p + "feed_forward.4.weight", {S, 2 * S});
+    add(p + "linear.0.weight", {C, S, 1, 1, 1});
+    p = "altblock." + std::to_string(i) + ".ang_trans.";
+    add(p + "norm.weight", {C});
+    add(p + "norm.bias", {C});
+    add(p + "attention.in_proj_weight", {3 * C, C});
+    add(p + "attention.out_proj.weight", {C, C});
+    add(p + "feed_forward.0.weight", {C});
+    add(p + "feed_forward.0.bias", {C});
+    add(p + "feed_forward.1.weight", {2 * C, C});
+    add(p + "feed_forward.4.weight", {C, 2 * C});
+  }
+  add("upsampling.0.weight", {C * s2, C, 1, 1});
+  add("upsampling.3.weight", {1, C, 3, 3});
+}
+
+int upload(Handle* h, const void* src, size_t bytes, void** dst) {
+  void* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  h->allocs.push_back(d);
+  CUDA_TRY(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+  *dst = d;
+  return 0;
+}
+
+static int upload_packed(Handle* h, int N, int Npad, int K, const std::function<float(int, int)>& w,
+                         const uint8_t** dst) {
+  std::vector<uint16_t> p = pack_weight(N, Npad, K, w);
+  void* d;
+  int rc = upload(h, p.data(), p.size() * 2, &d);
+  *dst = (const uint8_t*)d;
+  return rc;
+}
+static int upload_f32(Handle* h, const std::vector<float>& v, const float** dst) {
+  void* d;
+  int rc = upload(h, v.data(), v.size() * 4, &d);
+  *dst = (const float*)d;
+  return rc;
+}
+
+// One axis of PositionEncoding.forward (LFT.py:94-104) in fp32, as the reference computes it.
+static std::vector<float> pos_axis(int length, int C) {
+  std::vector<float> t((size_t)length * C);
+  std::vector<float> grid(C);
+  for (int i = 0; i < C; ++i) grid[i] = powf(10000.f, 2.f * (float)(i / 2) / (float)C);
+  for (int p = 0; p < length; ++p)
+    for (int j = 0; j < C / 2; ++j) {
+      t[(size_t)p * C + j] = sinf((float)p / grid[2 * j]);
+      t[(size_t)p * C + C / 2 + j] = cosf((float)p / grid[2 * j + 1]);
+    }
+  return t;
+}
+
+static int finalize(Handle* h) {
+  const int C = 64, S = 128, A = h->cfg.ang_res, s = h->cfg.scale, s2 = s * s;
+  for (auto& kv : h->spec)
+    if (!h->host_w.count(kv.first)) return fail(LFT_ERR_STATE, "missing state_dict key '%s'", kv.first.c_str());
+  auto W = [&](const std::string& k) -> const float* { return h->host_w[k].data(); };
+  int rc;
+  // conv_init0: fp32 [64][9]
+  {
+    const float* w = W("conv_init0.0.weight");
+    std::vector<float> v(w, w + 576);
+    if ((rc = upload_f32(h, v, &h->w_conv0))) return rc;
+  }
+  // conv weights [N][C][ky][kx] -> tap-major K: k = tap*64 + c
+  auto conv_pack = [&](const float* w, int N, const uint8_t** dst) {
+    return upload_packed(h, N, N, 576, [=](int n, int k) { return w[((size_t)n * 64 + (k % 64)) * 9 + (k / 64)]; }, dst);
+  };
+  for (int i = 0; i < 3; ++i)
+    if ((rc = conv_pack(W("conv_init." + std::to_string(2 * i) + ".weight"), 64, &h->w_conv[i]))) return rc;
+  auto lin_pack = [&](const float* w, int row0, int N, int ldk, int col0, int K, const uint8_t** dst) {
+    return upload_packed(h, N, N, K, [=](int n, int k) { return w[(size_t)(row0 + n) * ldk + col0 + k]; }, dst);
+  };
+  for (int i = 0; i < kLayers; ++i) {
+    Layer& L = h->layer[i];
+    std::string p = "altblock." + std::to_string(i) + ".ang_trans.";
+    const float* in_w = W(p + "attention.in_proj_weight");
+    if ((rc = lin_pack(in_w, 0, 128, C, 0, C, &L.a_wqk))) return rc;
+    if ((rc = lin_pack(in_w, 128, 64, C, 0, C, &L.a_wv))) return rc;
+    if ((rc = lin_pack(W(p + "attention.out_proj.weight"), 0, 64, C, 0, C, &L.a_wo))) return rc;
+    if ((rc = lin_pack(W(p + "feed_forward.1.weight"), 0, 128, C, 0, C, &L.a_w1))) return rc;
+    if ((rc = lin_pack(W(p + "feed_forward.4.weight"), 0, 64, 2 * C, 0, 2 * C, &L.a_w2))) return rc;
+    {
+      std::vector<float> ln(4 * C);
+      memcpy(&ln[0], W(p + "norm.weight"), C * 4);
+      memcpy(&ln[C], W(p + "norm.bias"), C * 4);
+      memcpy(&ln[2 * C], W(p + "feed_forward.0.weight"), C * 4);
+      memcpy(&ln[3 * C], W(p + "feed_forward.0.bias"), C * 4);
+      if ((rc = upload_f32(h, ln, &L.a_ln))) return rc;
+    }
+    p = "altblock." + std::to_string(i) + ".spa_trans.";
+    if ((rc = conv_pack(W(p + "MLP.weight"), 128, &L.s_wmlp))) return rc;  // [128][64*9]: c*9+tap (LFT.py:167)
+    in_w = W(p + "attention.in_proj_weight");
+    if ((rc = lin_pack(in_w, 0, 128, S, 0, S, &L.s_wq))) return rc;
+    if ((rc = lin_pack(in_w, 128, 128, S, 0, S, &L.s_wk))) return rc;
+    if ((rc = lin_pack(in_w, 256, 128, S, 0, S, &L.s_wv))) return rc;
+    if ((rc = lin_pack(W(p + "attention.out_proj.weight"), 0, 128, S, 0, S, &L.s_wo))) return rc;
+    if ((rc = lin_pack(W(p + "feed_forward.1.weight"), 0, 128, S, 0, S, &L.s_w1a))) return rc;
+    if ((rc = lin_pack(W(p + "feed_forward.1.weight"), 128, 128, S, 0, S, &L.s_w1b))) return rc;
+    if ((rc = lin_pack(W(p + "feed_forward.4.weight"), 0, 128, 2 * S, 0, S, &L.s_w2a))) return rc;
+    if ((rc = lin_pack(W(p + "feed_forward.4.weight"), 0, 128, 2 * S, S, S, &L.s_w2b))) return rc;
+    if ((rc = lin_pack(W(p + "linear.0.weight"), 0, 64, S, 0, S, &L.s_wlin))) return rc;
+    {
+      std::vector<float> ln(4 * S);
+      memcpy(&ln[0], W(p + "norm.weight"), S * 4);
+      memcpy(&ln[S], W(p + "norm.bias"), S * 4);
+      memcpy(&ln[2 * S], W(p + "feed_forward.0.weight"), S * 4);
+      memcpy(&ln[3 * S], W(p + "feed_forward.0.bias"), S * 4);
+      if ((rc = upload_f32(h, ln, &L.s_ln))) return rc;
+    }
+  }
+  // upsampling 1x1: rows permuted to n' = ij*64 + c  (PixelShuffle: in channel c*s^2 + i*s + j, LFT.py:41)
+  {
+    const float* w = W("upsampling.0.weight");
+    if ((rc = upload_packed(h, 64 * s2, 64 * s2, 64,
+                            [=](int n, int k) { return w[(size_t)((n % 64) * s2 + n / 64) * 64 + k]; }, &h->w_up)))
+      return rc;
+    const float* w3 = W("upsampling.3.weight");  // [1][64][3][3] -> rows = taps (9 of 16), k = c
+    if ((rc = upload_packed(h, 9, 16, 64, [=](int n, int k) { return w3[(size_t)k * 9 + n]; }, &h->w_up3))) return rc;
+  }
+  // angular position table [A*A][64]
+  if ((rc = upload_f32(h, pos_axis(A * A, C), &h->pe_ang))) return rc;
+  h->finalized = true;
+  return 0;
+}
+
+// spatial PE token table per layer: SAI2Token(spa_position) (LFT.py:180) = conv3x3(PE_hw, MLP.weight), [P*P][128]
+int ensure_spa_pe(Handle* h, int P) {
+  if (h->pe_P == P) return 0;
+  const int C = 64, S = 128;
+  std::vector<float> ax = pos_axis(P, C);
+  std::vector<float> pe((size_t)P * P * C);
+  for (int y = 0; y < P; ++y)
+    for (int x = 0; x < P; ++x)
+      for (int c = 0; c < C; ++c) pe[((size_t)y * P + x) * C + c] = (ax[(size_t)y * C + c] + ax[(size_t)x * C + c]) / 2.f;
+  for (int i = 0; i < kLayers; ++i) {
+    const float* w = h->host_w["altblock." + std::to_string(i) + ".spa_trans.MLP.weight"].data();
+    std::vector<float> tab((size_t)P * P * S);
+    for (int y = 0; y < P; ++y)
+      for (int x = 0; x < P; ++x)
+        for (int n = 0; n < S; ++n) {
+          double acc = 0.0;
+          for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            if (yy < 0 || yy >= P) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+              const int xx = x + kx - 1;
+              if (xx < 0 || xx >= P) continue;
+              const float* pv = &pe[((size_t)yy * P + xx) * C];
+              const float* wv = w + (size_t)n * 576 + ky * 3 + kx;
+              for (int c = 0; c < C; ++c) acc += (double)pv[c] * (double)wv[(size_t)c * 9];
+            }
+          }
+          tab[((size_t)y * P + x) * S + n] = (float)acc;
+        }
+    int rc = upload_f32(h, tab, &h->layer[i].s_pe);
+    if (rc) return rc;
+  }
+  h->pe_P = P;
+  return 0;
+}
+
+}  // namespace lft
+
+using namespace lft;
+
+extern "C" {
+
+const char* lft_last_error(void) { return g_err.c_str(); }
+int lft_version(void) { return 100; }
+
+int lft_create(const lft_config* cfg, lft_handle** out) {
+  if (!cfg || !out) return fail(LFT_ERR_ARG, "null argument");
+  if (cfg->channels != 64) return fail(LFT_ERR_ARG, "channels must be 64 (got %d)", cfg->channels);
+  if (cfg->ang_res < 2 || cfg->ang_res > 9) return fail(LFT_ERR_ARG, "angRes %d unsupported (2..9)", cfg->ang_res);
+  if (cfg->scale != 2 && cfg->scale != 4) return fail(LFT_ERR_ARG, "scale_factor must be 2 or 4");
+  if (cfg->precision != LFT_PREC_FP32 && cfg->precision != LFT_PREC_BF16) return fail(LFT_ERR_ARG, "bad precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(LFT_ERR_CUDA, "no CUDA device: lft_b200 has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(LFT_ERR_CUDA, "device is sm_%d%d; this library is sm_100a only", prop.major, prop.minor);
+  Handle* h = new Handle();
+  h->cfg = *cfg;
+  build_spec(h);
+  int rc = configure_kernels();
+  if (rc) { delete h; return rc; }
+  *out = reinterpret_cast<lft_handle*>(h);
+  return 0;
+}
+
+int lft_destroy(lft_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  for (void* p : h->allocs) cudaFree(p);
+  for (auto& e : h->events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+  delete h;
+  return 0;
+}
+
+int lft_set_weight(lft_handle* hh, const char* key, const float* host_data, const int64_t* shape, int32_t ndim) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !key || !host_data || !shape) return fail(LFT_ERR_ARG, "null argument");
+  auto it = h->spec.find(key);
+  if (it == h->spec.end()) return fail(LFT_ERR_KEY, "unexpected state_dict key '%s'", key);
+  const std::vector<int64_t>& want = it->second;
+  bool ok = (int)want.size() == ndim;
+  size_t n = 1;
+  for (int i = 0; ok && i < ndim; ++i) { ok = want[i] == shape[i]; n *= (size_t)shape[i]; }
+  if (!ok) return fail(LFT_ERR_KEY, "shape mismatch for '%s'", key);
+  h->host_w[key].assign(host_data, host_data + n);
+  h->finalized = false;
+  return 0;
+}
+
+int lft_finalize_weights(lft_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(LFT_ERR_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  h->pe_P = -1;
+  return finalize(h);
+}
+
+int lft_set_precision(lft_handle* hh, int32_t precision) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || (precision != LFT_PREC_FP32 && precision != LFT_PREC_BF16)) return fail(LFT_ERR_ARG, "bad precision");
+  h->cfg.precision = precision;
+  return 0;
+}
+
+int lft_profile_enable(lft_handle* hh, int32_t on) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(LFT_ERR_ARG, "null handle");
+  h->profiling = on != 0;
+  if (on) {
+    for (auto& e : h->events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+    h->events.clear();
+  }
+  return 0;
+}
+
+int lft_profile_read(lft_handle* hh, int32_t* n_kinds, const char** names, int64_t* launches, double* total_ms) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !n_kinds || !names || !launches || !total_ms) return fail(LFT_ERR_ARG, "null argument");
+  for (int k = 0; k < K_COUNT; ++k) { names[k] = kKindNames[k]; launches[k] = 0; total_ms[k] = 0.0; }
+  for (auto& e : h->events) {
+    CUDA_TRY(cudaEventSynchronize(e.stop));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e.start, e.stop));
+    launches[e.kind] += 1;
+    total_ms[e.kind] += ms;
+  }
+  *n_kinds = K_COUNT;
+  return 0;
+}
+
+int64_t lft_launch_count(lft_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  return h ? h->launches : -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+// Blackwell (sm_100a) device primitives shared by the LFT kernels: mbarrier, bulk async copy
+// (TMA engine, 1-D), tcgen05 MMA / TMEM alloc / ld / st, UMMA descriptors, bf16 hi/lo splitting.
+//
+// Operand layout used everywhere ("chunk-major, no swizzle"):
+//   element (row r, k) of a K-major bf16 operand lives at  base + (k/8)*LBO + r*16 + (k%8)*2
+//   i.e. 8-row x 16-byte core matrices are contiguous (128 B), consecutive rows are 16 B apart,
+//   SBO (8-row group stride) = 128 B and LBO (k-chunk stride) = ROWS*16 B.  Because the row stride
+//   is uniform, a descriptor whose start address is moved by d*16 B addresses the same tile shifted
+//   by d rows - which is how the 3x3 convolutions read their nine taps without an im2col copy.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace lft {
+
+#define LFT_DEVINL __device__ __forceinline__
+
+LFT_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------- mbarrier
+LFT_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+LFT_DEVINL void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+LFT_DEVINL void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+LFT_DEVINL void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+LFT_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+LFT_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+// ---------------------------------------------------------------- proxies / fences
+LFT_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+LFT_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+LFT_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+LFT_DEVINL void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------- bulk async copy global -> smem
+LFT_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- TMEM
+LFT_DEVINL void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+LFT_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+LFT_DEVINL void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+LFT_DEVINL void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (lane_base+i), columns c..c+15
+LFT_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+LFT_DEVINL void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+      "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+
+// ---------------------------------------------------------------- UMMA descriptors + MMA
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE, sm_100 version field = 1.
+// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor; LBO = k-chunk stride, SBO = 8-row stride)
+LFT_DEVINL uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// Instruction descriptor: kind::f16, A=B=bf16, D=f32, both K-major, M=128, N (multiple of 16).
+LFT_DEVINL uint32_t umma_idesc_bf16(uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+}
+LFT_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
+LFT_DEVINL void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------- bf16 split
+// x = hi + lo (+ O(2^-17 |x|)); hi = bf16(x), lo = bf16(x - hi).  3 MMAs (hi*hi, lo*hi, hi*lo)
+// reproduce an fp32 product to ~2^-16 relative.
+struct bf16x8 { uint4 v; };
+LFT_DEVINL uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+LFT_DEVINL void split8(const float* x, uint4& hi, uint4& lo) {
+  float r[8];
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat16 b = __float2bfloat16_rn(x[i]);
+    r[i] = x[i] - __bfloat162float(b);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+    l[i] = pack_bf16(r[2 * i], r[2 * i + 1]);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+LFT_DEVINL void st_shared_v4(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------- weight-stream ring (B operand)
+// Weights are pre-packed on the host into "slabs": one slab = [N rows x 64 k] bf16 in the chunk-major
+// layout above (N*128 bytes), hi slab followed by lo slab for every 64-wide k block.  A producer thread
+// streams slabs through an NST-deep ring with bulk copies; the MMA thread consumes them in order and
+// frees each stage with tcgen05.commit.
+template <int NST>
+struct RingState {
+  int stage = 0;
+  uint32_t phase = 0;
+  LFT_DEVINL void advance() {
+    if (++stage == NST) { stage = 0; phase ^= 1; }
+  }
+};
+
+struct GemmPhase {
+  const uint8_t* w;   // packed weights for this GEMM: k-slab ks at w + ks*2*N*128 (hi then lo)
+  uint32_t N;         // output columns (multiple of 16, <= 256)
+  uint32_t kslabs;    // K / 64
+};
+
+// Producer side of one GEMM phase. `passes` = 3 (fp32 via hi/lo) or 1 (bf16: hi slabs only).
+template <int NST>
+LFT_DEVINL void ring_produce(RingState<NST>& rs, uint32_t ring_base, uint32_t stage_bytes, uint32_t full0,
+                             uint32_t empty0, const GemmPhase& g, int passes) {
+  const uint32_t slab = g.N * 128u;
+  for (uint32_t ks = 0; ks < g.kslabs; ++ks) {
+    const int nparts = passes == 3 ? 2 : 1;
+    for (int part = 0; part < nparts; ++part) {
+      mbar_wait(empty0 + 8u * rs.stage, rs.phase ^ 1u);
+      mbar_arrive_expect_tx(full0 + 8u * rs.stage, slab);
+      bulk_g2s(ring_base + rs.stage * stage_bytes, g.w + (size_t)(ks * 2 + part) * slab, slab, full0 + 8u * rs.stage);
+      rs.advance();
+    }
+  }
+}
+
+// MMA side of one GEMM phase: D[128 x N] (+)= A[128 x K] * W[N x K]^T.
+//   a_hi/a_lo : smem byte addresses of the A operand (row 0, k 0), a_lbo its k-chunk stride in bytes.
+//   a_kslab_stride: byte distance between consecutive 64-wide k slabs of A (= 8*a_lbo for a plain
+//   operand; 0 together with per-slab `row_shift` for the conv taps).
+//   row_shift(ks): rows to shift A by for slab ks (conv taps), else 0.
+template <int NST, typename ShiftFn>
+LFT_DEVINL void ring_consume_mma(RingState<NST>& rs, uint32_t ring_base, uint32_t stage_bytes, uint32_t full0,
+                                 uint32_t empty0, const GemmPhase& g, int passes, uint32_t a_hi, uint32_t a_lo,
+                                 uint32_t a_lbo, uint32_t a_kslab_stride, ShiftFn row_shift, uint32_t d_tmem,
+                                 bool fresh) {
+  const uint32_t idesc = umma_idesc_bf16(g.N);
+  const uint32_t b_lbo = g.N * 16u;
+  uint32_t acc = fresh ? 0u : 1u;
+  for (uint32_t ks = 0; ks < g.kslabs; ++ks) {
+    const int sh = row_shift(ks);
+    const uint32_t a_off = ks * a_kslab_stride + (uint32_t)(sh * 16);
+    // hi weights: A_hi*W_hi (+ A_lo*W_hi)
+    mbar_wait(full0 + 8u * rs.stage, rs.phase);
+    tc_fence_after();
+    uint32_t b = ring_base + rs.stage * stage_bytes;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      umma_bf16(d_tmem, umma_desc(a_hi + a_off + j * 2 * a_lbo, a_lbo, 128), umma_desc(b + j * 2 * b_lbo, b_lbo, 128),
+                idesc, acc);
+      acc = 1u;
+    }
+    if (passes == 3) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        umma_bf16(d_tmem, umma_desc(a_lo + a_off + j * 2 * a_lbo, a_lbo, 128),
+                  umma_desc(b + j * 2 * b_lbo, b_lbo, 128), idesc, 1u);
+    }
+    umma_commit(empty0 + 8u * rs.stage);
+    rs.advance();
+    if (passes == 3) {  // lo weights: A_hi*W_lo
+      mbar_wait(full0 + 8u * rs.stage, rs.phase);
+      tc_fence_after();
+      b = ring_base + rs.stage * stage_bytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        umma_bf16(d_tmem, umma_desc(a_hi + a_off + j * 2 * a_lbo, a_lbo, 128),
+                  umma_desc(b + j * 2 * b_lbo, b_lbo, 128), idesc, 1u);
+      umma_commit(empty0 + 8u * rs.stage);
+      rs.advance();
+    }
+  }
+}
+
+struct NoShift {
+  LFT_DEVINL int operator()(uint32_t) const { return 0; }
+};
+
+// LayerNorm statistics helpers operate on register chunks; see kernels.
+LFT_DEVINL float lrelu02(float x) { return x >= 0.f ? x : 0.2f * x; }
+
+}  // namespace lft

@@ -1,0 +1,301 @@
+// conv_init0 (CUDA cores), the 3x3 implicit-GEMM convolution (tcgen05) and the GEMM self-test kernel.
+// Reference semantics: model/LFT.py:23-33,65-66 (conv stack) and LFT.py:164-169 (SpaTrans.SAI2Token:
+// unfold 3x3 + Linear == zero-padded 3x3 conv 64->128).
+#include "host.h"
+#include "kernels.cuh"
+
+namespace lft {
+
+// ------------------------------------------------------------------------------------------------
+// conv_init0: Conv3d(1->64,(1,3,3),pad(0,1,1)) on the LR SAI mosaic, zero padded PER VIEW.
+// in : lr [B,1,A*P,A*P] fp32 (view (u,v) at rows u*P.., cols v*P..)   out: feat [T,64] fp32
+// One thread = one token x 4 channels (16 threads/token -> 256 B coalesced rows).
+__global__ void __launch_bounds__(256) k_conv0(const float* __restrict__ lr, const float* __restrict__ w0,
+                                              float* __restrict__ out, int B, int A, int P) {
+  __shared__ float sw[64 * 9];
+  for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i] = w0[i];
+  __syncthreads();
+  const long long T = (long long)B * A * A * P * P;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tok = gid >> 4;
+  const int cg = (int)(gid & 15);
+  if (tok >= T) return;
+  const int x = (int)(tok % P);
+  const int y = (int)((tok / P) % P);
+  const int a = (int)((tok / ((long long)P * P)) % (A * A));
+  const int b = (int)(tok / ((long long)P * P * A * A));
+  const int u = a / A, v = a % A;
+  const int W = A * P;
+  const float* img = lr + (long long)b * W * W + (long long)(u * P) * W + v * P;
+  float t[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      t[ky * 3 + kx] = (yy >= 0 && yy < P && xx >= 0 && xx < P) ? __ldg(img + (long long)yy * W + xx) : 0.f;
+    }
+  float4 o;
+  float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* w = sw + (cg * 4 + j) * 9;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s = fmaf(w[k], t[k], s);
+    op[j] = s;
+  }
+  reinterpret_cast<float4*>(out + tok * 64)[cg] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 conv, 64 -> N channels, as an implicit GEMM on tcgen05.
+//
+// Positions: every view is laid out as P rows of (P+1) positions (the extra one is a zero pad that
+// serves as right pad of row y and left pad of row y+1) followed by one zero pad row; view stride
+// VS=(P+1)^2.  In this linear space every tap (dy,dx) is the constant row shift dy*(P+1)+dx, so the
+// nine taps are nine descriptor offsets into ONE staged copy of the inputs (no im2col).
+// A CTA computes 128 consecutive positions; pad positions are computed and discarded (6% at P=32).
+template <int N>
+__global__ void __launch_bounds__(kThreads, 2)
+k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* __restrict__ out,
+          const float* __restrict__ res, int V, int P, int passes, int epi) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NST = 3;
+  constexpr uint32_t STAGE = N * 128;
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem);
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t a_hi = s_base + kCtlBytes;
+  const uint32_t a_lo = a_hi + kConvRows * 128;
+  const uint32_t ring = a_lo + kConvRows * 128;
+  const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
+  const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P1 = P + 1;
+  const long long VS = (long long)P1 * P1;
+  const long long G = (long long)V * VS;
+  const long long g0 = (long long)blockIdx.x * 128;
+
+  cta_setup<NST>(ctl, warp, lane, 128, N <= 64 ? 64 : 128);
+  const uint32_t tmem = ctl->tmem;
+
+  GemmPhase ph{wp, (uint32_t)N, 9};
+  if (warp == kWarpProducer) {
+    if (lane == 0) {
+      RingState<NST> rs;
+      ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
+    }
+  } else if (warp == kWarpMma) {
+    if (lane == 0) {
+      RingState<NST> rs;
+      mbar_wait(a_ready, 0);
+      tc_fence_after();
+      auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
+      ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi + kConvOff * 16, a_lo + kConvOff * 16,
+                            kConvRows * 16, 0, shift, tmem, true);
+      umma_commit(mma_done);
+    }
+  } else {
+    // ---- stage the input window: rows r <-> positions g0 - kConvOff + r, lanes <-> rows
+    for (int r = tid; r < kConvRows; r += 128) {
+      const long long g = g0 - kConvOff + r;
+      const float* src = nullptr;
+      if (g >= 0 && g < G) {
+        const long long v = g / VS;
+        const int q = (int)(g - v * VS);
+        const int y = q / P1, x = q - y * P1;
+        if (y < P && x < P) src = in + ((v * P + y) * P + x) * 64;
+      }
+      float4 f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        f[i] = src ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        uint4 hi, lo;
+        split8(reinterpret_cast<const float*>(&f[2 * kc]), hi, lo);
+        st_shared_v4(a_hi + kc * (kConvRows * 16) + r * 16, hi);
+        st_shared_v4(a_lo + kc * (kConvRows * 16) + r * 16, lo);
+      }
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(a_ready);
+
+    // ---- epilogue: lane <-> position
+    mbar_wait(mma_done, 0);
+    tc_fence_after();
+    const long long g = g0 + tid;
+    long long tok = -1;
+    if (g < G) {
+      const long long v = g / VS;
+      const int q = (int)(g - v * VS);
+      const int y = q / P1, x = q - y * P1;
+      if (y < P && x < P) tok = (v * P + y) * P + x;
+    }
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + c0, v);
+      if (tok >= 0) {
+        if (epi & 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
+        }
+        if (epi & 2) {
+          const float4* rp = reinterpret_cast<const float4*>(res + tok * N + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 r4 = __ldg(rp + i);
+            v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+          }
+        }
+        float4* op = reinterpret_cast<float4*>(out + tok * N + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+    tc_fence_before();
+  }
+  cta_teardown(ctl, warp, N <= 64 ? 64 : 128);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Self-test: D[128 x N] = A[128 x K] * W[N x K]^T through exactly the machinery the real kernels use
+// (chunk-major operands, weight ring, hi/lo passes, TMEM ld/st).  `variant` 1 swaps the LBO/SBO
+// descriptor fields (bring-up aid).  aux[128 x 16] returns a tcgen05.st -> tcgen05.ld round trip.
+__global__ void __launch_bounds__(kThreads, 1)
+k_gemm_selftest(const float* __restrict__ A, int K, const uint8_t* __restrict__ wp, int N, float* __restrict__ D,
+                float* __restrict__ aux, int passes, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NST = 3;
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem);
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t a_lbo = 128 * 16;
+  const uint32_t a_hi = s_base + kCtlBytes;
+  const uint32_t a_lo = a_hi + (K / 8) * a_lbo;
+  const uint32_t ring = a_lo + (K / 8) * a_lbo;
+  const uint32_t STAGE = N * 128;
+  const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
+  const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  cta_setup<NST>(ctl, warp, lane, 128, 512);
+  const uint32_t tmem = ctl->tmem;
+  A += (size_t)blockIdx.x * 128 * K;
+  D += (size_t)blockIdx.x * 128 * N;
+  aux += (size_t)blockIdx.x * 128 * 16;
+  GemmPhase ph{wp, (uint32_t)N, (uint32_t)(K / 64)};
+  if (warp == kWarpProducer) {
+    if (lane == 0) {
+      RingState<NST> rs;
+      ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
+    }
+  } else if (warp == kWarpMma) {
+    if (lane == 0) {
+      RingState<NST> rs;
+      mbar_wait(a_ready, 0);
+      tc_fence_after();
+      if (variant == 0) {
+        ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi, a_lo, a_lbo, 8 * a_lbo, NoShift{}, tmem,
+                              true);
+      } else {  // swapped LBO/SBO interpretation
+        const uint32_t idesc = umma_idesc_bf16(N);
+        uint32_t acc = 0;
+        for (uint32_t ks = 0; ks < ph.kslabs; ++ks) {
+          for (int part = 0; part < (passes == 3 ? 2 : 1); ++part) {
+            mbar_wait(full0 + 8u * rs.stage, rs.phase);
+            tc_fence_after();
+            const uint32_t b = ring + rs.stage * STAGE;
+            for (int rep = 0; rep < ((passes == 3 && part == 0) ? 2 : 1); ++rep) {
+              const uint32_t ab = (part == 0 && rep == 1) ? a_lo : a_hi;
+              for (int j = 0; j < 4; ++j) {
+                umma_bf16(tmem, umma_desc(ab + ks * 8 * a_lbo + j * 2 * a_lbo, 128, a_lbo),
+                          umma_desc(b + j * 2 * N * 16, 128, N * 16), idesc, acc);
+                acc = 1;
+              }
+            }
+            umma_commit(empty0 + 8u * rs.stage);
+            rs.advance();
+          }
+        }
+      }
+      umma_commit(mma_done);
+    }
+  } else {
+    const int m = tid;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    float st[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st[i] = 2.f * A[(size_t)m * K + i] + 1.f;
+    tmem_st16(trow + 256, st);
+    tmem_wait_st();
+    for (int kc = 0; kc < K / 8; ++kc) {
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = A[(size_t)m * K + kc * 8 + i];
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      st_shared_v4(a_hi + kc * a_lbo + m * 16, hi);
+      st_shared_v4(a_lo + kc * a_lbo + m * 16, lo);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(a_ready);
+    mbar_wait(mma_done, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) D[(size_t)m * N + c0 + i] = v[i];
+    }
+    float v[16];
+    tmem_ld16(trow + 256, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) aux[m * 16 + i] = v[i];
+    tc_fence_before();
+  }
+  cta_teardown(ctl, warp, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+constexpr size_t kSmemConv64 = kCtlBytes + 2 * kConvRows * 128 + 3 * 64 * 128;
+constexpr size_t kSmemConv128 = kCtlBytes + 2 * kConvRows * 128 + 3 * 128 * 128;
+
+int configure_conv() {
+  CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemConv64));
+  CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemConv128));
+  CUDA_TRY(cudaFuncSetAttribute(k_gemm_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return 0;
+}
+
+int launch_conv0(Handle* h, const float* lr, float* out, int B, int P, cudaStream_t st) {
+  const int A = h->cfg.ang_res;
+  const long long T = (long long)B * A * A * P * P;
+  Scope sc(h, K_CONV0, st);
+  k_conv0<<<(unsigned)((T * 16 + 255) / 256), 256, 0, st>>>(lr, h->w_conv0, out, B, A, P);
+  return sc.finish();
+}
+
+int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* out, const float* res, int V, int P,
+                   int epi, cudaStream_t st) {
+  const long long G = (long long)V * (P + 1) * (P + 1);
+  const unsigned grid = (unsigned)((G + 127) / 128);
+  Scope sc(h, N == 64 ? K_CONV64 : K_CONV128, st);
+  if (N == 64)
+    k_conv3x3<64><<<grid, kThreads, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi);
+  else
+    k_conv3x3<128><<<grid, kThreads, kSmemConv128, st>>>(in, wp, out, res, V, P, h->passes(), epi);
+  return sc.finish();
+}
+
+int launch_selftest(const float* dA, int K, const uint8_t* dW, int N, float* dD, float* dX, int M, int passes,
+                    int variant) {
+  const size_t smem = kCtlBytes + 2 * (size_t)(K / 8) * 128 * 16 + 3 * (size_t)N * 128;
+  k_gemm_selftest<<<M / 128, kThreads, smem>>>(dA, K, dW, N, dD, dX, passes, variant);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace lft

@@ -1,0 +1,187 @@
+"""Thin Python owner of one `lft_handle` (include/lft_b200.h). PyTorch supplies device memory and the
+current CUDA stream; all arithmetic happens in liblft_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional
+
+import torch
+
+from . import capi
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    def __init__(self, angRes: int, scale: int, channels: int = 64, precision: str = "fp32",
+                 device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise capi.LftError("lft_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = capi.load()
+        self.A, self.s, self.C = int(angRes), int(scale), int(channels)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        cfg = capi.LftConfig(self.A, self.s, self.C, self._prec(precision), self.device)
+        self._h = C.c_void_p()
+        capi.check(self.lib.lft_create(C.byref(cfg), C.byref(self._h)))
+        self._ws: Optional[torch.Tensor] = None
+        self.ready = False
+
+    @staticmethod
+    def _prec(p: str) -> int:
+        if p in ("fp32", "float32"):
+            return capi.PREC_FP32
+        if p in ("bf16", "bfloat16"):
+            return capi.PREC_BF16
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {p!r}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.lft_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- weights
+    def load_state_dict(self, sd: Mapping[str, torch.Tensor]) -> None:
+        """Strict intake of the reference state_dict (78 fp32 tensors; a 'module.' prefix is stripped)."""
+        for k, v in sd.items():
+            key = k[7:] if k.startswith("module.") else k
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            capi.check(self.lib.lft_set_weight(self._h, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
+        capi.check(self.lib.lft_finalize_weights(self._h))
+        self.ready = True
+
+    def set_precision(self, precision: str) -> None:
+        capi.check(self.lib.lft_set_precision(self._h, self._prec(precision)))
+
+    # ---------------------------------------------------------------- workspace
+    def workspace_bytes(self, B: int, P: int) -> int:
+        n = C.c_size_t()
+        capi.check(self.lib.lft_workspace_bytes(self._h, B, P, C.byref(n)))
+        return int(n.value)
+
+    def _workspace(self, B: int, P: int, max_bytes: Optional[int] = None) -> torch.Tensor:
+        need = self.workspace_bytes(B, P)
+        if max_bytes is not None:
+            need = min(need, max(max_bytes, self.workspace_bytes(1, P)))
+        if self._ws is None or self._ws.numel() < need or self._ws.device.index != self.device:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+    def _check_in(self, t: torch.Tensor, name: str) -> None:
+        if not t.is_cuda:
+            raise capi.LftError(f"{name} must be a CUDA tensor (no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise capi.LftError(f"{name} must be float32, got {t.dtype}")
+        if not t.is_contiguous():
+            raise capi.LftError(f"{name} must be contiguous")
+
+    # ---------------------------------------------------------------- compute
+    def forward(self, lr: torch.Tensor, max_ws_bytes: Optional[int] = None) -> torch.Tensor:
+        """get_model.forward: lr [B,1,A*P,A*P] -> [B,1,A*P*s,A*P*s] (LFT.py:52-83)."""
+        self._check_in(lr, "lr")
+        B, c, H, W = lr.shape
+        if c != 1 or H != W or H % self.A:
+            raise capi.LftError(f"lr must be [B,1,A*P,A*P] with square patches, got {tuple(lr.shape)}")
+        P = H // self.A
+        ws = self._workspace(B, P, max_ws_bytes)
+        out = torch.empty(B, 1, H * self.s, W * self.s, dtype=torch.float32, device=lr.device)
+        capi.check(self.lib.lft_forward(self._h, _ptr(lr), _ptr(out), B, P, _ptr(ws), ws.numel(), _stream()))
+        return out
+
+    def stage_conv_init(self, lr: torch.Tensor) -> torch.Tensor:
+        self._check_in(lr, "lr")
+        B, _, H, W = lr.shape
+        P = H // self.A
+        ws = self._workspace(B, P)
+        out = torch.empty(B, self.A * self.A, P, P, 64, dtype=torch.float32, device=lr.device)
+        capi.check(self.lib.lft_stage_conv_init(self._h, _ptr(lr), _ptr(out), B, P, _ptr(ws), ws.numel(), _stream()))
+        return out
+
+    def _stage_tok(self, fn, layer: int, x: torch.Tensor) -> torch.Tensor:
+        self._check_in(x, "feat")
+        B, N, P, P2, Cc = x.shape
+        assert N == self.A * self.A and P == P2 and Cc == 64
+        ws = self._workspace(B, P)
+        out = torch.empty_like(x)
+        capi.check(fn(self._h, layer, _ptr(x), _ptr(out), B, P, _ptr(ws), ws.numel(), _stream()))
+        return out
+
+    def stage_ang(self, layer: int, x: torch.Tensor) -> torch.Tensor:
+        return self._stage_tok(self.lib.lft_stage_ang, layer, x)
+
+    def stage_spa(self, layer: int, x: torch.Tensor) -> torch.Tensor:
+        return self._stage_tok(self.lib.lft_stage_spa, layer, x)
+
+    def stage_upsample(self, feat: torch.Tensor, lr: torch.Tensor) -> torch.Tensor:
+        self._check_in(feat, "feat")
+        self._check_in(lr, "lr")
+        B, N, P, _, _ = feat.shape
+        ws = self._workspace(B, P)
+        H = self.A * P * self.s
+        out = torch.empty(B, 1, H, H, dtype=torch.float32, device=lr.device)
+        capi.check(self.lib.lft_stage_upsample(self._h, _ptr(feat), _ptr(lr), _ptr(out), B, P, _ptr(ws), ws.numel(),
+                                               _stream()))
+        return out
+
+    # ---------------------------------------------------------------- light-field path
+    def num_patches(self, h0: int, w0: int):
+        nu, nv = C.c_int32(), C.c_int32()
+        capi.check(self.lib.lft_lf_num_patches(h0, w0, C.byref(nu), C.byref(nv)))
+        return int(nu.value), int(nv.value)
+
+    def divide(self, lr_lf: torch.Tensor, p0: int, p1: int) -> torch.Tensor:
+        self._check_in(lr_lf, "lr_lf")
+        h0, w0 = lr_lf.shape[0] // self.A, lr_lf.shape[1] // self.A
+        out = torch.empty(p1 - p0, 1, self.A * 32, self.A * 32, dtype=torch.float32, device=lr_lf.device)
+        capi.check(self.lib.lft_divide(self._h, _ptr(lr_lf), h0, w0, p0, p1, _ptr(out), _stream()))
+        return out
+
+    def forward_lf_crops(self, lr_lf: torch.Tensor, p0: int, p1: int, out: Optional[torch.Tensor] = None,
+                         max_ws_bytes: Optional[int] = None) -> torch.Tensor:
+        """LFdivide + forward for patches [p0,p1) -> kept crops [p1-p0, A, A, 16s, 16s]."""
+        self._check_in(lr_lf, "lr_lf")
+        h0, w0 = lr_lf.shape[0] // self.A, lr_lf.shape[1] // self.A
+        n = p1 - p0
+        c = 16 * self.s
+        if out is None:
+            out = torch.empty(n, self.A, self.A, c, c, dtype=torch.float32, device=lr_lf.device)
+        if n > 0:
+            ws = self._workspace(n, 32, max_ws_bytes)
+            capi.check(self.lib.lft_forward_lf(self._h, _ptr(lr_lf), h0, w0, p0, p1, _ptr(out), _ptr(ws), ws.numel(),
+                                               _stream()))
+        return out
+
+    def integrate(self, crops: torch.Tensor, h0: int, w0: int, p0: int, p1: int, sr_lf: torch.Tensor) -> torch.Tensor:
+        self._check_in(crops, "crops")
+        self._check_in(sr_lf, "sr_lf")
+        if p1 > p0:
+            capi.check(self.lib.lft_integrate(self._h, _ptr(crops), h0, w0, p0, p1, _ptr(sr_lf), _stream()))
+        return sr_lf
+
+    # ---------------------------------------------------------------- profiling
+    def profile_enable(self, on: bool = True) -> None:
+        capi.check(self.lib.lft_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        n = C.c_int32()
+        names = (C.c_char_p * capi.PROFILE_MAX_KINDS)()
+        launches = (C.c_int64 * capi.PROFILE_MAX_KINDS)()
+        ms = (C.c_double * capi.PROFILE_MAX_KINDS)()
+        capi.check(self.lib.lft_profile_read(self._h, C.byref(n), names, launches, ms))
+        return {names[i].decode(): {"launches": int(launches[i]), "ms": float(ms[i])} for i in range(n.value)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.lft_launch_count(self._h))
