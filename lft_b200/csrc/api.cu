@@ -186,9 +186,14 @@ static int finalize(Handle* h) {
   // upsampling 1x1: rows permuted to n' = ij*64 + c  (PixelShuffle: in channel c*s^2 + i*s + j, LFT.py:41)
   {
     const float* w = W("upsampling.0.weight");
-    if ((rc = upload_packed(h, 64 * s2, 64 * s2, 64,
-                            [=](int n, int k) { return w[(size_t)((n % 64) * s2 + n / 64) * 64 + k]; }, &h->w_up)))
-      return rc;
+    std::vector<uint16_t> all;
+    for (int ij = 0; ij < s2; ++ij) {  // one [64 x 64] GEMM per sub-pixel ij: rows c -> original row c*s^2 + ij
+      std::vector<uint16_t> p1 = pack_weight(64, 64, 64, [=](int n, int k) { return w[(size_t)(n * s2 + ij) * 64 + k]; });
+      all.insert(all.end(), p1.begin(), p1.end());
+    }
+    void* d;
+    if ((rc = upload(h, all.data(), all.size() * 2, &d))) return rc;
+    h->w_up = (const uint8_t*)d;
     const float* w3 = W("upsampling.3.weight");  // [1][64][3][3] -> rows = taps (9 of 16), k = c
     if ((rc = upload_packed(h, 9, 16, 64, [=](int n, int k) { return w3[(size_t)k * 9 + n]; }, &h->w_up3))) return rc;
   }

@@ -116,7 +116,7 @@ int launch_selftest(const float* dA, int K, const uint8_t* dW, int N, float* dD,
 
 // Workspace carve-up for a chunk of Bc patches (floats): see launch.cu
 struct Workspace {
-  float *f0, *f1, *f2, *fres, *tok, *q, *k, *v, *o, *pp;
+  float *f0, *f1, *f2, *fres, *tok, *q, *k, *v, *o, *pp, *lrp;
 };
 size_t ws_floats_per_token(int scale);
 Workspace carve(void* ws, long long T, int scale);
@@ -126,6 +126,9 @@ int run_conv_init(Handle* h, const float* lr, float* out, float* tmp0, float* tm
 int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cudaStream_t st);
 int run_spa(Handle* h, int layer, const float* in, float* out, const float* final_res, Workspace& w, int B, int P,
             cudaStream_t st);
+int launch_divide(Handle* h, const float* lf, float* patches, int h0, int w0, int numV, int p0, int n, cudaStream_t st);
+int launch_integrate(Handle* h, const float* crops, float* sr, int h0, int w0, int numV, int p0, int n,
+                     cudaStream_t st);
 int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float* pp, int B, int P, int crop_mode,
                  cudaStream_t st);
 

@@ -1,0 +1,302 @@
+// Up-sampling tail (model/LFT.py:39-44,79-81,255-266) and the patch tiler (utils/utils.py:91-157).
+//   k_up_gemm   : per LR token, H = W_up x (1x1 conv 64 -> 64 s^2) in PixelShuffle order, LeakyReLU, and the
+//                 per-tap partial sums of the final 3x3 conv  Pp[tap][Y][X] = sum_c w3[c,tap] lrelu(H[c,Y,X])
+//                 -- two chained tcgen05 GEMMs; the 64-channel HR tensor (105 MB/patch at 4x) never exists.
+//   k_up_gather : out[Y,X] = sum_taps Pp[tap][Y+dy][X+dx] (zero outside the MOSAIC, so interior view
+//                 borders read the neighbouring view, as the reference's conv on the mosaic does)
+//                 + per-view bicubic(lr) (A=-0.75, align_corners=False, clamped taps).  Optionally writes
+//                 only the central crop LFintegrate keeps.
+//   k_lf_divide / k_lf_integrate : LFdivide (mirror-extend by 8, zero-fill, stride 16) / LFintegrate.
+#include "host.h"
+#include "kernels.cuh"
+
+namespace lft {
+
+constexpr int kUpNST = 3;
+constexpr uint32_t kUpStage = 64 * 128;
+constexpr size_t kSmemUp = kCtlBytes + 65536 + kUpNST * kUpStage;
+constexpr uint32_t kLbo64 = 128 * 16;
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const uint8_t* __restrict__ w3,
+          float* __restrict__ Pp, long long T, int A, int P, int s, int passes) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem);
+  const uint32_t A1 = smem_u32(smem) + kCtlBytes;
+  const uint32_t A2 = A1 + 32768;
+  const uint32_t ring = A2 + 32768;
+  const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
+  const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  cta_setup<kUpNST>(ctl, warp, lane, 128, 128);
+  const uint32_t tmem = ctl->tmem;
+  const int s2 = s * s;
+  const GemmPhase g3{w3, 16, 1};
+
+  if (warp == kWarpProducer) {
+    if (lane == 0) {
+      RingState<kUpNST> rs;
+      for (int ij = 0; ij < s2; ++ij) {
+        const GemmPhase g1{wup + (size_t)ij * 2 * 64 * 128, 64, 1};
+        ring_produce<kUpNST>(rs, ring, kUpStage, full0, empty0, g1, passes);
+        ring_produce<kUpNST>(rs, ring, kUpStage, full0, empty0, g3, passes);
+      }
+    }
+  } else if (warp == kWarpMma) {
+    if (lane == 0) {
+      RingState<kUpNST> rs;
+      uint32_t par = 0;
+      mbar_wait(a_ready, par);
+      par ^= 1;
+      tc_fence_after();
+      for (int ij = 0; ij < s2; ++ij) {
+        const GemmPhase g1{wup + (size_t)ij * 2 * 64 * 128, 64, 1};
+        ring_consume_mma<kUpNST>(rs, ring, kUpStage, full0, empty0, g1, passes, A1, A1 + 16384, kLbo64, 0, NoShift{},
+                                 tmem + 0, true);
+        umma_commit(mma_done);
+        mbar_wait(a_ready, par);
+        par ^= 1;
+        tc_fence_after();
+        ring_consume_mma<kUpNST>(rs, ring, kUpStage, full0, empty0, g3, passes, A2, A2 + 16384, kLbo64, 0, NoShift{},
+                                 tmem + 64 + 16 * (ij % s), true);
+        umma_commit(mma_done);
+      }
+    }
+  } else {
+    const int m = tid;
+    const long long t = (long long)blockIdx.x * 128 + m;
+    const bool ok = t < T;
+    const long long tt = ok ? t : 0;
+    const int PP = P * P, N = A * A;
+    const int x = (int)(tt % P), y = (int)((tt / P) % P);
+    const int a = (int)((tt / PP) % N);
+    const long long b = tt / ((long long)PP * N);
+    const int u = a / A, v = a - u * A;
+    const int H = A * P * s;
+    const long long Y0 = (long long)(u * P + y) * s, X0 = (long long)(v * P + x) * s;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t par = 0;
+    {
+      const float4* src = reinterpret_cast<const float4*>(feat + tt * 64);
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        float z[8];
+        const float4 f0 = ok ? __ldg(src + 2 * kc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 f1 = ok ? __ldg(src + 2 * kc + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        z[0] = f0.x; z[1] = f0.y; z[2] = f0.z; z[3] = f0.w; z[4] = f1.x; z[5] = f1.y; z[6] = f1.z; z[7] = f1.w;
+        uint4 hi, lo;
+        split8(z, hi, lo);
+        st_shared_v4(A1 + kc * kLbo64 + m * 16, hi);
+        st_shared_v4(A1 + 16384 + kc * kLbo64 + m * 16, lo);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+    }
+    for (int ij = 0; ij < s2; ++ij) {
+      mbar_wait(mma_done, par);
+      par ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float d[16];
+        tmem_ld16(trow + 16 * c, d);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d[i] = lrelu02(d[i]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint4 hi, lo;
+          split8(d + 8 * j, hi, lo);
+          st_shared_v4(A2 + (2 * c + j) * kLbo64 + m * 16, hi);
+          st_shared_v4(A2 + 16384 + (2 * c + j) * kLbo64 + m * 16, lo);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+      mbar_wait(mma_done, par);
+      par ^= 1;
+      tc_fence_after();
+      if ((ij % s) == s - 1) {  // one HR row i = ij / s of this LR pixel is complete: taps x s sub-pixels
+        const int i = ij / s;
+        float pj[4][16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < s) tmem_ld16(trow + 64 + 16 * j, pj[j]);
+        if (ok) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            float* dst = Pp + ((b * 9 + tap) * H + (Y0 + i)) * H + X0;
+            if (s == 4)
+              *reinterpret_cast<float4*>(dst) = make_float4(pj[0][tap], pj[1][tap], pj[2][tap], pj[3][tap]);
+            else
+              *reinterpret_cast<float2*>(dst) = make_float2(pj[0][tap], pj[1][tap]);
+          }
+        }
+        tc_fence_before();
+      }
+    }
+    tc_fence_before();
+  }
+  cta_teardown(ctl, warp, 128);
+}
+
+// PyTorch upsample_bicubic2d coefficients (A = -0.75)
+LFT_DEVINL void cubic_coeffs(float t, float* c) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  c[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+// crop == 0: out = sr [B,1,H,H];   crop == 1: out = crops [B][A][A][16s][16s] (P must be 32)
+__global__ void __launch_bounds__(256)
+k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* __restrict__ out, int B, int A, int P,
+            int s, int crop) {
+  const int H = A * P * s;
+  const int Ps = P * s;
+  const int cs = crop ? 16 * s : Ps;     // side of the per-view output block
+  const int c0 = crop ? 8 * s : 0;       // offset of the block inside the SR view
+  const long long total = (long long)B * A * A * cs * cs;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  int b, u, v, yy, xx;
+  if (crop) {  // [b][u][v][cy][cx]
+    xx = (int)(gid % cs) + c0;
+    yy = (int)((gid / cs) % cs) + c0;
+    v = (int)((gid / ((long long)cs * cs)) % A);
+    u = (int)((gid / ((long long)cs * cs * A)) % A);
+    b = (int)(gid / ((long long)cs * cs * A * A));
+  } else {     // mosaic order [b][Y][X]
+    const int X = (int)(gid % H), Y = (int)((gid / H) % H);
+    b = (int)(gid / ((long long)H * H));
+    u = Y / Ps; yy = Y - u * Ps;
+    v = X / Ps; xx = X - v * Ps;
+  }
+  const int Y = u * Ps + yy, X = v * Ps + xx;
+  float acc = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int Yn = Y + ky - 1;
+    if (Yn < 0 || Yn >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int Xn = X + kx - 1;
+      if (Xn < 0 || Xn >= H) continue;
+      acc += __ldg(Pp + (((long long)b * 9 + ky * 3 + kx) * H + Yn) * H + Xn);
+    }
+  }
+  // bicubic residual (LFT.py:54,81,255-266)
+  const float inv = 1.f / (float)s;
+  const float sy = inv * ((float)yy + 0.5f) - 0.5f, sx = inv * ((float)xx + 0.5f) - 0.5f;
+  const float fy = floorf(sy), fx = floorf(sx);
+  float wy[4], wx[4];
+  cubic_coeffs(sy - fy, wy);
+  cubic_coeffs(sx - fx, wx);
+  const int iy = (int)fy, ix = (int)fx;
+  const int W = A * P;
+  const float* img = lr + (long long)b * W * W + (long long)(u * P) * W + v * P;
+  float bic = 0.f;
+  float rowv[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int cy = min(max(iy - 1 + r, 0), P - 1);
+    float e[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int cx = min(max(ix - 1 + c, 0), P - 1);
+      e[c] = __ldg(img + (long long)cy * W + cx);
+    }
+    rowv[r] = e[0] * wx[0] + e[1] * wx[1] + e[2] * wx[2] + e[3] * wx[3];
+  }
+  bic = rowv[0] * wy[0] + rowv[1] * wy[1] + rowv[2] * wy[2] + rowv[3] * wy[3];
+  out[crop ? gid : ((long long)b * H + Y) * H + X] = acc + bic;
+}
+
+// LFdivide (utils.py:91-138), patch size 32, stride 16, bdr 8. One thread per output element.
+__global__ void __launch_bounds__(256)
+k_lf_divide(const float* __restrict__ lf, float* __restrict__ patches, int A, int h0, int w0, int numV, int p0, int n) {
+  const int W = A * 32;
+  const long long total = (long long)n * W * W;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int col = (int)(gid % W), row = (int)((gid / W) % W);
+  const int pi = p0 + (int)(gid / ((long long)W * W));
+  const int kh = pi / numV, kw = pi - kh * numV;
+  const int u = row >> 5, y = row & 31, v = col >> 5, x = col & 31;
+  const int ey = kh * 16 + y, ex = kw * 16 + x;  // coordinates in the mirror-extended view
+  float val = 0.f;
+  if (ey < h0 + 16 && ex < w0 + 16) {
+    int jy = ey - 8, jx = ex - 8;
+    jy = jy < 0 ? -jy - 1 : (jy >= h0 ? 2 * h0 - 1 - jy : jy);
+    jx = jx < 0 ? -jx - 1 : (jx >= w0 ? 2 * w0 - 1 - jx : jx);
+    val = __ldg(lf + (long long)(u * h0 + jy) * (A * w0) + v * w0 + jx);
+  }
+  patches[gid] = val;
+}
+
+// LFintegrate (utils.py:141-157) + test.py:100-101: crops [n][A][A][16s][16s] -> sr_lf [A*h0*s, A*w0*s]
+__global__ void __launch_bounds__(256)
+k_lf_integrate(const float* __restrict__ crops, float* __restrict__ sr, int A, int h0, int w0, int s, int numV, int p0,
+               int n) {
+  const int cs = 16 * s;
+  const long long total = (long long)n * A * A * cs * cs;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cx = (int)(gid % cs), cy = (int)((gid / cs) % cs);
+  const int v = (int)((gid / ((long long)cs * cs)) % A);
+  const int u = (int)((gid / ((long long)cs * cs * A)) % A);
+  const int pi = p0 + (int)(gid / ((long long)cs * cs * A * A));
+  const int kh = pi / numV, kw = pi - kh * numV;
+  const int Yd = kh * cs + cy, Xd = kw * cs + cx;
+  if (Yd < h0 * s && Xd < w0 * s) sr[((long long)u * h0 * s + Yd) * ((long long)A * w0 * s) + (long long)v * w0 * s + Xd] = crops[gid];
+}
+
+int configure_up() {
+  CUDA_TRY(cudaFuncSetAttribute(k_up_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUp));
+  return 0;
+}
+
+// upsampling(mosaic(feat)) + bicubic(lr).  crop_mode: write only the kept central crops.
+int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float* pp, int B, int P, int crop_mode,
+                 cudaStream_t st) {
+  const int A = h->cfg.ang_res, s = h->cfg.scale;
+  const long long T = (long long)B * A * A * P * P;
+  int rc;
+  {
+    Scope sc(h, K_UP_GEMM, st);
+    k_up_gemm<<<(unsigned)((T + 127) / 128), kThreads, kSmemUp, st>>>(feat, h->w_up, h->w_up3, pp, T, A, P, s,
+                                                                      h->passes());
+    if ((rc = sc.finish())) return rc;
+  }
+  {
+    if (crop_mode && P != 32) return fail(LFT_ERR_ARG, "crop mode needs 32x32 patches");
+    const int cs = crop_mode ? 16 * s : P * s;
+    const long long total = (long long)B * A * A * cs * cs;
+    Scope sc(h, K_UP_GATHER, st);
+    k_up_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pp, lr, sr, B, A, P, s, crop_mode);
+    if ((rc = sc.finish())) return rc;
+  }
+  return 0;
+}
+
+int launch_divide(Handle* h, const float* lf, float* patches, int h0, int w0, int numV, int p0, int n, cudaStream_t st) {
+  const int A = h->cfg.ang_res;
+  const long long total = (long long)n * A * 32 * A * 32;
+  Scope sc(h, K_DIVIDE, st);
+  k_lf_divide<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lf, patches, A, h0, w0, numV, p0, n);
+  return sc.finish();
+}
+
+int launch_integrate(Handle* h, const float* crops, float* sr, int h0, int w0, int numV, int p0, int n,
+                     cudaStream_t st) {
+  const int A = h->cfg.ang_res, s = h->cfg.scale;
+  const long long total = (long long)n * A * A * 16 * s * 16 * s;
+  Scope sc(h, K_INTEGRATE, st);
+  k_lf_integrate<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(crops, sr, A, h0, w0, s, numV, p0, n);
+  return sc.finish();
+}
+
+}  // namespace lft

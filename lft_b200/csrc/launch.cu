@@ -18,7 +18,7 @@ int configure_kernels() {
   return 0;
 }
 
-size_t ws_floats_per_token(int scale) { return 4 * 64 + 5 * 128 + 9 * (size_t)scale * scale; }
+size_t ws_floats_per_token(int scale) { return 4 * 64 + 5 * 128 + 9 * (size_t)scale * scale + 1; }
 
 Workspace carve(void* ws, long long T, int scale) {
   Workspace w;
@@ -32,7 +32,8 @@ Workspace carve(void* ws, long long T, int scale) {
   w.k = p; p += T * 128;
   w.v = p; p += T * 128;
   w.o = p; p += T * 128;
-  w.pp = p;
+  w.pp = p; p += T * 9 * scale * scale;
+  w.lrp = p;
   return w;
 }
 
@@ -48,6 +49,27 @@ int run_conv_init(Handle* h, const float* lr, float* out, float* tmp0, float* tm
   if ((rc = launch_conv3x3(h, 64, tmp1, h->w_conv[1], tmp2, nullptr, V, P, 1, st))) return rc;
   if ((rc = launch_conv3x3(h, 64, tmp2, h->w_conv[2], out, tmp0, V, P, 3, st))) return rc;
   return 0;
+}
+
+// get_model.forward for one chunk of B patches (LFT.py:52-83).  crop_mode: `out` receives only the central
+// crops [B][A][A][16s][16s] that LFintegrate keeps.
+int run_forward_chunk(Handle* h, const float* lr, float* out, Workspace& w, int B, int P, int crop_mode,
+                      cudaStream_t st) {
+  int rc;
+  if ((rc = run_conv_init(h, lr, w.fres, w.f0, w.f1, w.f2, B, P, st))) return rc;
+  const float* x = w.fres;
+  for (int i = 0; i < kLayers; ++i) {  // AltFilter: ang_trans then spa_trans (LFT.py:248-252)
+    if ((rc = run_ang(h, i, x, w.f1, B, P, st))) return rc;
+    if ((rc = run_spa(h, i, w.f1, w.f2, i == kLayers - 1 ? w.fres : nullptr, w, B, P, st))) return rc;
+    x = w.f2;
+  }
+  return run_upsample(h, w.f2, lr, out, w.pp, B, P, crop_mode, st);
+}
+
+static void num_patches(int h0, int w0, int* numU, int* numV) {  // utils.py:95-104 with patch 32, stride 16
+  const int h = h0 + 16, w = w0 + 16;
+  *numU = (h - 32) / 16 + (((h - 32) % 16) ? 2 : 1);
+  *numV = (w - 32) / 16 + (((w - 32) % 16) ? 2 : 1);
 }
 
 }  // namespace lft
@@ -108,6 +130,103 @@ int lft_stage_spa(lft_handle* hh, int32_t layer, const float* in, float* out, in
   const long long T = (long long)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
   Workspace w = carve(ws, T, h->cfg.scale);
   return run_spa(h, layer, in, out, nullptr, w, B, P, (cudaStream_t)stream);
+}
+
+int lft_stage_upsample(lft_handle* hh, const float* feat, const float* lr, float* sr, int32_t B, int32_t P, void* ws,
+                       size_t ws_bytes, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  int rc = check_ready(h, B, P);
+  if (rc) return rc;
+  size_t need;
+  lft_workspace_bytes(hh, B, P, &need);
+  if (ws_bytes < need) return fail(LFT_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
+  const long long T = (long long)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
+  Workspace w = carve(ws, T, h->cfg.scale);
+  return run_upsample(h, feat, lr, sr, w.pp, B, P, 0, (cudaStream_t)stream);
+}
+
+int lft_forward(lft_handle* hh, const float* lr, float* sr, int32_t B, int32_t P, void* ws, size_t ws_bytes,
+                void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  int rc = check_ready(h, B, P);
+  if (rc) return rc;
+  if (!lr || !sr || !ws) return fail(LFT_ERR_ARG, "null pointer");
+  size_t per;
+  lft_workspace_bytes(hh, 1, P, &per);
+  per -= 1024;
+  if (ws_bytes < per + 1024) return fail(LFT_ERR_WORKSPACE, "workspace too small for one patch: %zu < %zu", ws_bytes, per + 1024);
+  const int A = h->cfg.ang_res, s = h->cfg.scale;
+  const long long chunk = (long long)((ws_bytes - 1024) / per);
+  const size_t lr_stride = (size_t)A * P * A * P, sr_stride = lr_stride * s * s;
+  for (long long b0 = 0; b0 < B; b0 += chunk) {
+    const int Bc = (int)((B - b0) < chunk ? (B - b0) : chunk);
+    const long long T = (long long)Bc * A * A * P * P;
+    Workspace w = carve(ws, T, s);
+    if ((rc = run_forward_chunk(h, lr + b0 * lr_stride, sr + b0 * sr_stride, w, Bc, P, 0, (cudaStream_t)stream)))
+      return rc;
+  }
+  return 0;
+}
+
+int lft_lf_num_patches(int32_t h0, int32_t w0, int32_t* numU, int32_t* numV) {
+  if (!numU || !numV || h0 < 16 || w0 < 16) return fail(LFT_ERR_ARG, "bad light-field size");
+  int a, b;
+  num_patches(h0, w0, &a, &b);
+  *numU = a;
+  *numV = b;
+  return 0;
+}
+
+int lft_divide(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t p0, int32_t p1, float* patches,
+               void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !lr_lf || !patches || h0 < 16 || w0 < 16) return fail(LFT_ERR_ARG, "bad argument");
+  int nu, nv;
+  num_patches(h0, w0, &nu, &nv);
+  if (p0 < 0 || p1 > nu * nv || p0 > p1) return fail(LFT_ERR_ARG, "patch range [%d,%d) outside [0,%d)", p0, p1, nu * nv);
+  if (p0 == p1) return 0;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  return launch_divide(h, lr_lf, patches, h0, w0, nv, p0, p1 - p0, (cudaStream_t)stream);
+}
+
+int lft_integrate(lft_handle* hh, const float* sr_crops, int32_t h0, int32_t w0, int32_t p0, int32_t p1, float* sr_lf,
+                  void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !sr_crops || !sr_lf || h0 < 16 || w0 < 16) return fail(LFT_ERR_ARG, "bad argument");
+  int nu, nv;
+  num_patches(h0, w0, &nu, &nv);
+  if (p0 < 0 || p1 > nu * nv || p0 > p1) return fail(LFT_ERR_ARG, "patch range [%d,%d) outside [0,%d)", p0, p1, nu * nv);
+  if (p0 == p1) return 0;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  return launch_integrate(h, sr_crops, sr_lf, h0, w0, nv, p0, p1 - p0, (cudaStream_t)stream);
+}
+
+int lft_forward_lf(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t p0, int32_t p1, float* sr_crops,
+                   void* ws, size_t ws_bytes, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  const int P = 32;
+  int rc = check_ready(h, 1, P);
+  if (rc) return rc;
+  if (!lr_lf || !sr_crops || !ws || h0 < 16 || w0 < 16) return fail(LFT_ERR_ARG, "bad argument");
+  int nu, nv;
+  num_patches(h0, w0, &nu, &nv);
+  if (p0 < 0 || p1 > nu * nv || p0 > p1) return fail(LFT_ERR_ARG, "patch range [%d,%d) outside [0,%d)", p0, p1, nu * nv);
+  size_t per;
+  lft_workspace_bytes(hh, 1, P, &per);
+  per -= 1024;
+  if (ws_bytes < per + 1024) return fail(LFT_ERR_WORKSPACE, "workspace too small for one patch: %zu < %zu", ws_bytes, per + 1024);
+  const int A = h->cfg.ang_res, s = h->cfg.scale;
+  const long long chunk = (long long)((ws_bytes - 1024) / per);
+  const size_t crop_stride = (size_t)A * A * 16 * s * 16 * s;
+  for (long long q0 = p0; q0 < p1; q0 += chunk) {
+    const int Bc = (int)((p1 - q0) < chunk ? (p1 - q0) : chunk);
+    const long long T = (long long)Bc * A * A * P * P;
+    Workspace w = carve(ws, T, s);
+    if ((rc = launch_divide(h, lr_lf, w.lrp, h0, w0, nv, (int)q0, Bc, (cudaStream_t)stream))) return rc;
+    if ((rc = run_forward_chunk(h, w.lrp, sr_crops + (q0 - p0) * crop_stride, w, Bc, P, 1, (cudaStream_t)stream)))
+      return rc;
+  }
+  return 0;
 }
 
 int lft_gemm_selftest(const float* A, const float* W, float* D, float* aux, int32_t M, int32_t N, int32_t K,
