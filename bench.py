@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Headline benchmark: SR output megapixels/s for 5x5, 4x full light-field inference (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|bf16] [--impl reference]
+  (N > 1: launched by torchrun, one rank per GPU, NCCL)
+
+A step = one pass of the hot path over one batch of synthetic input: N light fields of HCInew shape
+(5x5 views of 128x128 LR -> 512x512 SR, 64 overlapping 32x32 patches each; BASELINE.json configs[2]),
+one per rank, patches sharded rank-wise with no data-path collective; the kept SR crops are gathered to
+rank 0 (NCCL) which assembles all N SR light fields ("weak" scaling: per-GPU work fixed).
+`value` counts INTEGRATED output pixels (after LFintegrate) of all ranks / max-over-ranks device time,
+inputs resident in HBM.  `e2e` is the same metric through the public API (LightFieldSR) from pinned
+host memory to pinned host memory, copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+A, S, H0, W0 = 5, 4, 128, 128
+PATCHES = 64
+MP_PER_LF = A * A * H0 * S * W0 * S / 1e6          # 6.5536
+TOKENS_PER_LF = PATCHES * A * A * 32 * 32          # 1,638,400
+# algorithmic FLOP per LR token and launch (window attention at its mean 23.16 keys)
+FLOP_PER_TOKEN = {
+    "conv0": 1152, "conv3x3_64": 73728, "conv3x3_128": 147456, "ang_fused": 71936, "spa_qkv": 98304,
+    "spa_attn": 11858, "spa_ffn": 180224, "up_gemm": 131072 + 18432, "up_gather": 32 * S * S,
+}
+FLOP_PER_LF = 2411464 * TOKENS_PER_LF              # 3.951 TFLOP
+# algorithmic HBM bytes per token for the bandwidth-bound kernels (fp32 in/out, once each)
+BYTES_PER_TOKEN = {"spa_attn": 4 * 128 * 4, "up_gather": (9 * 16 + 16) * 4, "conv0": 4 + 256}
+TENSOR_KINDS = {"conv3x3_64", "conv3x3_128", "ang_fused", "spa_qkv", "spa_ffn", "up_gemm"}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor": d["bf16_tflops_sustained"], "src": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(sd, lf, n_patches, threads=None):
+    """The reference's CPU path (test.py:83-99 semantics, one net() call per patch, dense masked
+    attention with the mask rebuilt per call) restated by oracle/lft_oracle.py, on a bounded sample."""
+    import torch
+    from oracle import lft_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        _, n = O.infer_light_field(sd, lf, A, S, mode="dense", batch=1, max_patches=n_patches)
+    dt = time.perf_counter() - t0
+    mp = n * A * A * (16 * S) ** 2 / 1e6
+    return mp / dt, dt, n, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference
+    is pure Python and cannot travel to the GPU box), all host threads, one patch per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from lft_b200 import synth
+    sd = synth.synth_state_dict(A, S, 0)
+    lf = torch.from_numpy(synth.synth_light_field(A, H0, W0, 2))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(sd, lf, 1)
+    times = []
+    for _ in range(args.steps):
+        v, dt, n, th = cpu_baseline(sd, lf, 1)
+        times.append(dt)
+    mp_per_step = A * A * (16 * S) ** 2 / 1e6
+    val = mp_per_step * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": "SR output megapixels/sec (5x5 4x full LF)", "value": val, "unit": "MP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "LFT 5x5 4x full-LF inference, HCInew-shape 5x5x128x128 LR -> 512x512 SR, 64 patches of 32x32",
+                   "sample": "one 32x32-per-view patch per step (1/64 of a light field), B=1 per net() call"},
+        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} steps x 1 patch (test.py:88-95 semantics, dense masked attention, mask rebuilt per call)"},
+        "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--impl", default="lft_b200", choices=["lft_b200", "reference"])
+    ap.add_argument("--cpu-patches", type=int, default=3, help="patches in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from lft_b200 import synth
+    from lft_b200.engine import Engine
+    from lft_b200.lightfield import LightFieldSR, gather_crops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sd = synth.synth_state_dict(A, S, 0)
+    eng = Engine(A, S, precision=args.precision, device=local)
+    eng.load_state_dict(sd)
+    lf_host = torch.from_numpy(synth.synth_light_field(A, H0, W0, 2 + rank)).pin_memory()
+    lf = lf_host.to(dev)
+    sr_all = torch.empty(world, A * H0 * S, A * W0 * S, dtype=torch.float32, device=dev) if rank == 0 else None
+    crops = torch.empty(PATCHES, A, A, 16 * S, 16 * S, dtype=torch.float32, device=dev)
+    ranges = [(i * PATCHES, (i + 1) * PATCHES) for i in range(world)]
+
+    def step():
+        eng.forward_lf_crops(lf, 0, PATCHES, out=crops)
+        allc = gather_crops(crops, ranges, rank, world)
+        if rank == 0:
+            for r in range(world):
+                eng.integrate(allc[r * PATCHES:(r + 1) * PATCHES], H0, W0, 0, PATCHES, sr_all[r])
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = eng.launch_count()
+    eng.profile_enable(True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    sync()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    sync()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    launches = eng.launch_count() - n0
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * MP_PER_LF * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: public API, pinned host -> device -> SR -> pinned host, every step
+    sr_host = torch.empty(A * H0 * S, A * W0 * S, dtype=torch.float32).pin_memory()
+    pipe = LightFieldSR(eng)
+    def e2e_step():
+        x = lf_host.to(dev, non_blocking=True)
+        if world == 1:
+            sr = pipe(x)
+            sr_host.copy_(sr, non_blocking=True)
+        else:
+            eng.forward_lf_crops(x, 0, PATCHES, out=crops)
+            allc = gather_crops(crops, ranges, rank, world)
+            if rank == 0:
+                for r in range(world):
+                    eng.integrate(allc[r * PATCHES:(r + 1) * PATCHES], H0, W0, 0, PATCHES, sr_all[r])
+                sr_host.copy_(sr_all[0], non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * MP_PER_LF * n_e2e / (float(t.item()) / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        kinds = {k: v for k, v in prof.items() if v["launches"] > 0}
+        step_kernel_ms = sum(v["ms"] for v in kinds.values()) / args.steps
+        top = max(kinds, key=lambda k: kinds[k]["ms"])
+        avg_ms = kinds[top]["ms"] / kinds[top]["launches"]
+        if top in TENSOR_KINDS:
+            ach = FLOP_PER_TOKEN[top] * TOKENS_PER_LF / (avg_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"]}
+        else:
+            ach = BYTES_PER_TOKEN.get(top, 0) * TOKENS_PER_LF / (avg_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
+        roof.update({"kernel": top, "avg_launch_ms": avg_ms, "share_of_step": kinds[top]["ms"] / args.steps / step_kernel_ms,
+                     "traffic": None, "peak_source": pk["src"],
+                     "note": ("fp32 path issues 3 bf16 MMAs per product (hi*hi+lo*hi+hi*lo): attainable frac <= 1/3"
+                              if args.precision == "fp32" else "single bf16 MMA per product")})
+        whole = FLOP_PER_LF * world * args.steps / (total_ms * 1e-3) / 1e12
+        line = {
+            "metric": "SR output megapixels/sec (5x5 4x full LF)", "value": value, "unit": "MP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.precision == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "LFT 5x5 4x full-LF inference, HCInew-shape 5x5x128x128 LR -> 512x512 SR, 64 patches of 32x32 per light field, one light field per GPU per step",
+                       "weights": "seeded synthetic checkpoint in the reference format (shipped pth absent)",
+                       "l2": "working set ~6.8 GB per step >> 126 MB L2 (no flush needed)", "parallelism": f"patch-sharded dp{world}"},
+            "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(lf_host.numel() * 4),
+                    "d2h_bytes_per_step": int(sr_host.numel() * 4), "steps": n_e2e},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "whole_step": {"algorithmic_tflops": whole, "frac_of_bf16_peak": whole / pk["tensor"]},
+            "kernels": {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
+                            "tflops": (FLOP_PER_TOKEN.get(k, 0) * TOKENS_PER_LF * v["launches"] / max(v["ms"], 1e-9) / 1e9)}
+                        for k, v in kinds.items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, n, th = cpu_baseline(sd, lf_host.clone(), args.cpu_patches)
+            line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": th, "kind": "port",
+                                    "sample": f"{n} of 64 patches of the same light field, B=1 per call, {dt:.1f} s (oracle port of test.py:83-99, dense masked attention)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,92 @@
+"""Full light-field inference = the reference's test loop (test.py:83-101): LFdivide -> net() per
+patch -> LFintegrate, re-designed for B200:
+
+  * all patches of a light field run as ONE batch (the forward is batch-independent),
+  * LFdivide / LFintegrate are index arithmetic inside CUDA kernels (lft_divide / lft_integrate),
+    and only the central 16s x 16s crop of every SR patch view is ever written,
+  * multi-GPU: patches are independent units -> contiguous blocks of ceil(P/G) patches per rank, no
+    data-path collective; the only collective is the gather of the kept crops to rank 0
+    (`torch.distributed.gather`, NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .engine import Engine
+
+PATCH = 32    # option.py:16  patch_size_for_test
+STRIDE = 16   # option.py:17  stride_for_test
+
+
+def num_patches(h0: int, w0: int, patch: int = PATCH, stride: int = STRIDE) -> Tuple[int, int]:
+    """numU, numV of LFdivide (utils/utils.py:95-104)."""
+    bdr = (patch - stride) // 2
+    h, w = h0 + 2 * bdr, w0 + 2 * bdr
+    nu = (h - patch) // stride + (2 if (h - patch) % stride else 1)
+    nv = (w - patch) // stride + (2 if (w - patch) % stride else 1)
+    return nu, nv
+
+
+def patch_ranges(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced blocks: the first n % world ranks get one extra patch
+    (70 patches on 8 ranks -> 9,9,9,9,9,9,8,8)."""
+    base, extra = divmod(n, world)
+    out, p = [], 0
+    for r in range(world):
+        c = base + (1 if r < extra else 0)
+        out.append((p, p + c))
+        p += c
+    return out
+
+
+def gather_crops(local: torch.Tensor, ranges: List[Tuple[int, int]], rank: int, world: int,
+                 group=None, dst: int = 0) -> Optional[torch.Tensor]:
+    """Gather per-rank crop slabs [n_r, A, A, c, c] to `dst` in patch order. Slabs are padded to the
+    largest block so one fixed-size gather suffices (ragged blocks differ by at most one patch)."""
+    if world == 1:
+        return local
+    nmax = max(b - a for a, b in ranges)
+    shape = (nmax,) + tuple(local.shape[1:])
+    send = local
+    if local.shape[0] != nmax:
+        send = torch.zeros(shape, dtype=local.dtype, device=local.device)
+        send[:local.shape[0]] = local
+    send = send.contiguous()
+    bufs = [torch.empty(shape, dtype=local.dtype, device=local.device) for _ in range(world)] if rank == dst else None
+    dist.gather(send, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([bufs[r][: ranges[r][1] - ranges[r][0]] for r in range(world)], dim=0)
+
+
+class LightFieldSR:
+    """`sr = LightFieldSR(net_or_engine)(lr_sai)` with lr_sai [A*h0, A*w0] on the GPU ->
+    sr_sai [A*h0*s, A*w0*s] (the `Sr_SAI_y` of test.py:100-101)."""
+
+    def __init__(self, net_or_engine, max_ws_bytes: Optional[int] = None):
+        self._src = net_or_engine
+        self.max_ws_bytes = max_ws_bytes
+
+    def _engine(self, device) -> Engine:
+        if isinstance(self._src, Engine):
+            return self._src
+        return self._src.engine(device)
+
+    @torch.no_grad()
+    def __call__(self, lr_sai: torch.Tensor, rank: int = 0, world: int = 1, group=None) -> Optional[torch.Tensor]:
+        eng = self._engine(lr_sai.device)
+        A, s = eng.A, eng.s
+        h0, w0 = lr_sai.shape[0] // A, lr_sai.shape[1] // A
+        nu, nv = eng.num_patches(h0, w0)
+        ranges = patch_ranges(nu * nv, world)
+        p0, p1 = ranges[rank]
+        crops = eng.forward_lf_crops(lr_sai.contiguous(), p0, p1, max_ws_bytes=self.max_ws_bytes)
+        allc = gather_crops(crops, ranges, rank, world, group)
+        if allc is None:
+            return None
+        sr = torch.empty(A * h0 * s, A * w0 * s, dtype=torch.float32, device=lr_sai.device)
+        eng.integrate(allc, h0, w0, 0, nu * nv, sr)
+        return sr

@@ -1,0 +1,141 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the drop-in
+module reproduces the reference state_dict contract, the product refuses to run without a GPU, and
+the sharding/gather host logic (world_size 2, gloo)."""
+import ctypes as C
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from lft_b200 import capi, synth
+from lft_b200 import lightfield as LF
+from oracle import lft_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "lft_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lft_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lft_b200.h but not exported"
+        assert n in capi.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(capi.SIGNATURES) == set(names)
+    assert lib.lft_version() >= 100
+
+
+def test_create_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = capi.load()
+    cfg = capi.LftConfig(5, 4, 64, 0, 0)
+    h = C.c_void_p()
+    rc = lib.lft_create(C.byref(cfg), C.byref(h))
+    assert rc == -2 and b"no CPU fallback" in lib.lft_last_error()
+    from lft_b200.engine import Engine
+    with pytest.raises(capi.LftError):
+        Engine(5, 4)
+
+
+def test_bad_config_rejected():
+    lib = capi.load()
+    h = C.c_void_p()
+    for cfg in (capi.LftConfig(5, 3, 64, 0, 0), capi.LftConfig(5, 4, 32, 0, 0), capi.LftConfig(12, 4, 64, 0, 0)):
+        assert lib.lft_create(C.byref(cfg), C.byref(h)) == -1
+
+
+@pytest.mark.parametrize("A,s", [(5, 4), (5, 2), (9, 4)])
+def test_dropin_state_dict_contract(A, s, tmp_path):
+    from lft_b200.model import get_model
+    net = get_model(types.SimpleNamespace(channels=64, angRes=A, scale_factor=s))
+    sd = synth.synth_state_dict(A, s, 3)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    assert [tuple(v.shape) for v in net.state_dict().values()] == [tuple(v.shape) for v in sd.values()]
+    for prefix in (False, True):  # test.py:39-51 tries 'module.'-prefixed keys first
+        p = tmp_path / f"ck{int(prefix)}.pth"
+        synth.save_checkpoint(str(p), sd, module_prefix=prefix)
+        ck = torch.load(str(p), map_location="cpu")
+        net.load_state_dict(ck["state_dict"])  # strict
+        assert torch.equal(net.state_dict()["altblock.2.spa_trans.MLP.weight"], sd["altblock.2.spa_trans.MLP.weight"])
+    bad = dict(sd)
+    bad.pop("upsampling.3.weight")
+    with pytest.raises(RuntimeError):
+        net.load_state_dict(bad)
+
+
+def test_forward_refuses_cpu_tensor():
+    from lft_b200.model import get_model
+    net = get_model(types.SimpleNamespace(channels=64, angRes=5, scale_factor=4))
+    with pytest.raises(capi.LftError):
+        net(torch.zeros(1, 1, 40, 40))
+
+
+def test_patch_partition_and_counts():
+    assert LF.num_patches(128, 128) == (8, 8)
+    assert LF.num_patches(108, 156) == (7, 10)
+    lf = torch.zeros(5 * 44, 5 * 60)
+    assert tuple(O.lf_divide(lf, 5, 32, 16).shape[:2]) == LF.num_patches(44, 60)
+    r = LF.patch_ranges(70, 8)
+    assert [b - a for a, b in r] == [9, 9, 9, 9, 9, 9, 8, 8] and r[0][0] == 0 and r[-1][1] == 70
+    assert all(r[i][1] == r[i + 1][0] for i in range(7))
+    assert LF.patch_ranges(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        A, s, n = 3, 2, 7  # ragged: 4 + 3 patches
+        ranges = LF.patch_ranges(n, world)
+        p0, p1 = ranges[rank]
+        c = 16 * s
+        local = torch.stack([torch.full((A, A, c, c), float(p)) + torch.arange(c * c).view(c, c) / 4096.0
+                             for p in range(p0, p1)]) if p1 > p0 else torch.zeros(0, A, A, c, c)
+        got = LF.gather_crops(local, ranges, rank, world)
+        if rank == 0:
+            want = torch.stack([torch.full((A, A, c, c), float(p)) + torch.arange(c * c).view(c, c) / 4096.0
+                                for p in range(n)])
+            q.put(bool(torch.equal(got, want)))
+        else:
+            q.put(got is None)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_crops_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(res)
+
+
+def test_crop_slab_integrates_like_reference_tiler():
+    """The [n,A,A,16s,16s] crop slab + patch-order placement equals LFintegrate on whole SR patches."""
+    A, s, h0, w0 = 3, 2, 40, 56
+    nu, nv = LF.num_patches(h0, w0)
+    g = torch.Generator().manual_seed(0)
+    sr_patches = torch.rand(nu, nv, A * 32 * s, A * 32 * s, generator=g)
+    want = O.lf_integrate(sr_patches, A, 32 * s, 16 * s, h0 * s, w0 * s)
+    c, b = 16 * s, 8 * s
+    crops = sr_patches.view(nu * nv, A, 32 * s, A, 32 * s)[:, :, b:b + c, :, b:b + c].permute(0, 1, 3, 2, 4)
+    full = crops.reshape(nu, nv, A, A, c, c).permute(2, 3, 0, 4, 1, 5).reshape(A, A, nu * c, nv * c)
+    assert torch.equal(full[:, :, :h0 * s, :w0 * s], want)
