@@ -145,14 +145,60 @@ static int finalize(Handle* h) {
   auto lin_pack = [&](const float* w, int row0, int N, int ldk, int col0, int K, const uint8_t** dst) {
     return upload_packed(h, N, N, K, [=](int n, int k) { return w[(size_t)(row0 + n) * ldk + col0 + k]; }, dst);
   };
+  // LayerNorm folded into the following linear layer: LN(z) W^T = rstd (z W'^T - mean u) + c with
+  // W' = W diag(gamma), u = W' 1 (summed over the bf16 hi+lo values the MMA really uses), c = W beta.
+  auto fold_pack = [&](const float* w, int row0, int N, int K, const float* g, const float* b, const uint8_t** dst,
+                       std::vector<float>& u, std::vector<float>& c, std::vector<float>* keep) -> int {
+    std::vector<float> wf((size_t)N * K);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) wf[(size_t)n * K + k] = w[(size_t)(row0 + n) * K + k] * g[k];
+    for (int n = 0; n < N; ++n) {
+      double su = 0.0, sc = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const float x = wf[(size_t)n * K + k];
+        const uint16_t hi = f2bf(x);
+        const uint16_t lo = f2bf(x - bf2f(hi));
+        su += (double)bf2f(hi) + (double)bf2f(lo);
+        sc += (double)w[(size_t)(row0 + n) * K + k] * (double)b[k];
+      }
+      u.push_back((float)su);
+      c.push_back((float)sc);
+    }
+    const float* wp = wf.data();
+    int r = upload_packed(h, N, N, K, [=](int n, int k) { return wp[(size_t)n * K + k]; }, dst);
+    if (keep) *keep = wf;
+    return r;
+  };
+  std::vector<float> pe_a = pos_axis(A * A, C);
   for (int i = 0; i < kLayers; ++i) {
     Layer& L = h->layer[i];
     std::string p = "altblock." + std::to_string(i) + ".ang_trans.";
     const float* in_w = W(p + "attention.in_proj_weight");
-    if ((rc = lin_pack(in_w, 0, 128, C, 0, C, &L.a_wqk))) return rc;
+    {
+      std::vector<float> uqk, cqk, u1, c1, wqk_fold;
+      if ((rc = fold_pack(in_w, 0, 128, C, W(p + "norm.weight"), W(p + "norm.bias"), &L.a_wqk, uqk, cqk, &wqk_fold)))
+        return rc;
+      if ((rc = fold_pack(W(p + "feed_forward.1.weight"), 0, 128, C, W(p + "feed_forward.0.weight"),
+                          W(p + "feed_forward.0.bias"), &L.a_w1, u1, c1, nullptr)))
+        return rc;
+      std::vector<float> tab;
+      tab.insert(tab.end(), uqk.begin(), uqk.end());
+      tab.insert(tab.end(), cqk.begin(), cqk.end());
+      tab.insert(tab.end(), u1.begin(), u1.end());
+      tab.insert(tab.end(), c1.begin(), c1.end());
+      if ((rc = upload_f32(h, tab, &L.a_tab))) return rc;
+      const int NA = A * A;
+      std::vector<float> peqk((size_t)NA * 128);  // chunk-planar [n/4][a][4]
+      for (int a = 0; a < NA; ++a)
+        for (int n = 0; n < 128; ++n) {
+          double acc = 0.0;
+          for (int k = 0; k < C; ++k) acc += (double)pe_a[(size_t)a * C + k] * (double)wqk_fold[(size_t)n * C + k];
+          peqk[((size_t)(n / 4) * NA + a) * 4 + (n % 4)] = (float)acc;
+        }
+      if ((rc = upload_f32(h, peqk, &L.a_peqk))) return rc;
+    }
     if ((rc = lin_pack(in_w, 128, 64, C, 0, C, &L.a_wv))) return rc;
     if ((rc = lin_pack(W(p + "attention.out_proj.weight"), 0, 64, C, 0, C, &L.a_wo))) return rc;
-    if ((rc = lin_pack(W(p + "feed_forward.1.weight"), 0, 128, C, 0, C, &L.a_w1))) return rc;
     if ((rc = lin_pack(W(p + "feed_forward.4.weight"), 0, 64, 2 * C, 0, 2 * C, &L.a_w2))) return rc;
     {
       std::vector<float> ln(4 * C);
@@ -165,12 +211,25 @@ static int finalize(Handle* h) {
     p = "altblock." + std::to_string(i) + ".spa_trans.";
     if ((rc = conv_pack(W(p + "MLP.weight"), 128, &L.s_wmlp))) return rc;  // [128][64*9]: c*9+tap (LFT.py:167)
     in_w = W(p + "attention.in_proj_weight");
-    if ((rc = lin_pack(in_w, 0, 128, S, 0, S, &L.s_wq))) return rc;
-    if ((rc = lin_pack(in_w, 128, 128, S, 0, S, &L.s_wk))) return rc;
+    {
+      std::vector<float> uq, cq, uk, ck, u1, c1;
+      const float *g1 = W(p + "norm.weight"), *b1 = W(p + "norm.bias");
+      const float *g2 = W(p + "feed_forward.0.weight"), *b2 = W(p + "feed_forward.0.bias");
+      if ((rc = fold_pack(in_w, 0, 128, S, g1, b1, &L.s_wq, uq, cq, &L.h_wq_fold))) return rc;
+      if ((rc = fold_pack(in_w, 128, 128, S, g1, b1, &L.s_wk, uk, ck, &L.h_wk_fold))) return rc;
+      if ((rc = fold_pack(W(p + "feed_forward.1.weight"), 0, 128, S, g2, b2, &L.s_w1a, u1, c1, nullptr))) return rc;
+      if ((rc = fold_pack(W(p + "feed_forward.1.weight"), 128, 128, S, g2, b2, &L.s_w1b, u1, c1, nullptr))) return rc;
+      std::vector<float> tab;
+      tab.insert(tab.end(), uq.begin(), uq.end());
+      tab.insert(tab.end(), uk.begin(), uk.end());
+      tab.insert(tab.end(), cq.begin(), cq.end());
+      tab.insert(tab.end(), ck.begin(), ck.end());
+      tab.insert(tab.end(), u1.begin(), u1.end());
+      tab.insert(tab.end(), c1.begin(), c1.end());
+      if ((rc = upload_f32(h, tab, &L.s_tab))) return rc;
+    }
     if ((rc = lin_pack(in_w, 256, 128, S, 0, S, &L.s_wv))) return rc;
     if ((rc = lin_pack(W(p + "attention.out_proj.weight"), 0, 128, S, 0, S, &L.s_wo))) return rc;
-    if ((rc = lin_pack(W(p + "feed_forward.1.weight"), 0, 128, S, 0, S, &L.s_w1a))) return rc;
-    if ((rc = lin_pack(W(p + "feed_forward.1.weight"), 128, 128, S, 0, S, &L.s_w1b))) return rc;
     if ((rc = lin_pack(W(p + "feed_forward.4.weight"), 0, 128, 2 * S, 0, S, &L.s_w2a))) return rc;
     if ((rc = lin_pack(W(p + "feed_forward.4.weight"), 0, 128, 2 * S, S, S, &L.s_w2b))) return rc;
     if ((rc = lin_pack(W(p + "linear.0.weight"), 0, 64, S, 0, S, &L.s_wlin))) return rc;
@@ -197,8 +256,14 @@ static int finalize(Handle* h) {
     const float* w3 = W("upsampling.3.weight");  // [1][64][3][3] -> rows = taps (9 of 16), k = c
     if ((rc = upload_packed(h, 9, 16, 64, [=](int n, int k) { return w3[(size_t)k * 9 + n]; }, &h->w_up3))) return rc;
   }
-  // angular position table [A*A][64]
-  if ((rc = upload_f32(h, pos_axis(A * A, C), &h->pe_ang))) return rc;
+  // angular position table, chunk-planar [c/4][A*A][4]
+  {
+    const int NA = A * A;
+    std::vector<float> pl((size_t)NA * C);
+    for (int a = 0; a < NA; ++a)
+      for (int c = 0; c < C; ++c) pl[((size_t)(c / 4) * NA + a) * 4 + (c % 4)] = pe_a[(size_t)a * C + c];
+    if ((rc = upload_f32(h, pl, &h->pe_ang))) return rc;
+  }
   h->finalized = true;
   return 0;
 }
@@ -232,8 +297,28 @@ int ensure_spa_pe(Handle* h, int P) {
           }
           tab[((size_t)y * P + x) * S + n] = (float)acc;
         }
-    int rc = upload_f32(h, tab, &h->layer[i].s_pe);
+    const int PPn = P * P;
+    std::vector<float> tab_pl((size_t)PPn * S);  // chunk-planar [n/4][p][4]
+    for (int t = 0; t < PPn; ++t)
+      for (int n = 0; n < S; ++n) tab_pl[((size_t)(n / 4) * PPn + t) * 4 + (n % 4)] = tab[(size_t)t * S + n];
+    int rc = upload_f32(h, tab_pl, &h->layer[i].s_pe);
     if (rc) return rc;
+    // (PE_s W'q^T | PE_s W'k^T): the position-encoding term of the LN-folded Q/K projections
+    const std::vector<float>& wq = h->layer[i].h_wq_fold;
+    const std::vector<float>& wk = h->layer[i].h_wk_fold;
+    std::vector<float> pq((size_t)P * P * 256);
+    for (int t = 0; t < P * P; ++t)
+      for (int n = 0; n < S; ++n) {
+        double aq = 0.0, ak = 0.0;
+        for (int k = 0; k < S; ++k) {
+          const double pv = tab[(size_t)t * S + k];
+          aq += pv * (double)wq[(size_t)n * S + k];
+          ak += pv * (double)wk[(size_t)n * S + k];
+        }
+        pq[((size_t)(n / 4) * PPn + t) * 4 + (n % 4)] = (float)aq;          // chunks 0..31: Q
+        pq[((size_t)(32 + n / 4) * PPn + t) * 4 + (n % 4)] = (float)ak;     // chunks 32..63: K
+      }
+    if ((rc = upload_f32(h, pq, &h->layer[i].s_peqk))) return rc;
   }
   h->pe_P = P;
   return 0;

@@ -41,12 +41,17 @@ extern const char* const kKindNames[K_COUNT];
 struct Layer {
   // AngTrans (LFT.py:194-238)
   const uint8_t *a_wqk = nullptr, *a_wv = nullptr, *a_wo = nullptr, *a_w1 = nullptr, *a_w2 = nullptr;
-  const float* a_ln = nullptr;  // [norm.w | norm.b | ff0.w | ff0.b] x 64
+  const float* a_ln = nullptr;    // [norm.w | norm.b | ff0.w | ff0.b] x 64
+  const float* a_tab = nullptr;   // LN-folded epilogue constants [u_qk 128 | c_qk 128 | u_1 128 | c_1 128]
+  const float* a_peqk = nullptr;  // [A*A][128]  PE_a W'qk^T
   // SpaTrans (LFT.py:118-191)
   const uint8_t *s_wmlp = nullptr, *s_wq = nullptr, *s_wk = nullptr, *s_wv = nullptr, *s_wo = nullptr;
   const uint8_t *s_w1a = nullptr, *s_w1b = nullptr, *s_w2a = nullptr, *s_w2b = nullptr, *s_wlin = nullptr;
   const float* s_ln = nullptr;  // [norm.w | norm.b | ff0.w | ff0.b] x 128
-  const float* s_pe = nullptr;  // [P*P][128] SAI2Token(spa_position), rebuilt when P changes
+  const float* s_pe = nullptr;    // [P*P][128] SAI2Token(spa_position), rebuilt when P changes
+  const float* s_peqk = nullptr;  // [P*P][256]  (PE_s W'q^T | PE_s W'k^T), rebuilt when P changes
+  const float* s_tab = nullptr;   // [u_q 128 | u_k 128 | c_q 128 | c_k 128 | u_1 256 | c_1 256]
+  std::vector<float> h_wq_fold, h_wk_fold;  // host copies of W'q, W'k (gamma folded) for the PE tables
 };
 
 struct ProfEvent {
@@ -111,6 +116,7 @@ int configure_up();
 int launch_conv0(Handle* h, const float* lr, float* out, int B, int P, cudaStream_t st);
 int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* out, const float* res, int V, int P,
                    int epi, cudaStream_t st);
+int launch_layout(Handle* h, const float* in, float* out, long long T, int C, int to_t32, cudaStream_t st);
 int launch_selftest(const float* dA, int K, const uint8_t* dW, int N, float* dD, float* dX, int M, int passes,
                     int variant);
 

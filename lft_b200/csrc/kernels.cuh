@@ -24,8 +24,16 @@ struct Ctl {
 };
 static_assert(sizeof(Ctl) <= kCtlBytes, "control block too large");
 
+// 2-threads-per-row layout: warps 0-7 are row owners (row m = 32*(warp&3)+lane, column half q = warp>>2;
+// warps w and w+4 share a TMEM lane quarter), warp 8 streams weights, warp 9 allocates TMEM / issues MMAs.
+constexpr int kThreads2 = 320;
+constexpr int kRowThreads2 = 256;
+constexpr int kWarpProducer2 = 8;
+constexpr int kWarpMma2 = 9;
+
 template <int NST>
-LFT_DEVINL void cta_setup(Ctl* ctl, int warp, int lane, uint32_t a_ready_count, uint32_t tmem_cols) {
+LFT_DEVINL void cta_setup(Ctl* ctl, int warp, int lane, uint32_t a_ready_count, uint32_t tmem_cols,
+                          int mma_warp = kWarpMma) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) {
       mbar_init(smem_u32(&ctl->full[i]), 1);
@@ -36,19 +44,81 @@ LFT_DEVINL void cta_setup(Ctl* ctl, int warp, int lane, uint32_t a_ready_count, 
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&ctl->aux[i]), a_ready_count);
     mbar_fence_init();
   }
-  if (warp == kWarpMma) tmem_alloc(smem_u32(&ctl->tmem), tmem_cols);
+  if (warp == mma_warp) tmem_alloc(smem_u32(&ctl->tmem), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
 }
 
-LFT_DEVINL void cta_teardown(Ctl* ctl, int warp, uint32_t tmem_cols) {
+LFT_DEVINL void cta_teardown(Ctl* ctl, int warp, uint32_t tmem_cols, int mma_warp = kWarpMma) {
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpMma) {
+  if (warp == mma_warp) {
     tc_fence_after();
     tmem_dealloc(ctl->tmem, tmem_cols);
   }
+}
+
+// "T32" activation layout for [T, C] fp32 tensors: blocks of 32 consecutive tokens, inside a block the
+// 16-byte channel chunks are the slow axis:  off(t, c) = (((t>>5)*(C/4) + c/4) * 32 + (t&31)) * 4 + c%4.
+// A warp whose lanes own 32 consecutive tokens reads/writes one chunk as 512 contiguous bytes.
+LFT_DEVINL long long t32_off(long long t, int chunk, int C4) {
+  return ((((t >> 5) * C4 + chunk) << 5) + (t & 31)) << 2;
+}
+
+// Stage the 64-channel input window of a 3x3 conv tile: smem rows r <-> padded positions g0-kConvOff+r,
+// one lane per row (T32 source: a warp reads 512 contiguous bytes per chunk), bf16 hi/lo, chunk-major.
+LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, uint32_t a_lo, long long g0, long long G,
+                                  long long VS, int P, int tid) {
+  const int P1 = P + 1;
+  for (int r = tid; r < kConvRows; r += kRowThreads2) {
+    const long long g = g0 - kConvOff + r;
+    long long tok = -1;
+    if (g >= 0 && g < G) {
+      const long long v = g / VS;
+      const int qq = (int)(g - v * VS);
+      const int y = qq / P1, x = qq - y * P1;
+      if (y < P && x < P) tok = (v * P + y) * P + x;
+    }
+    float4 f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      f[i] = tok >= 0 ? __ldg(reinterpret_cast<const float4*>(in + t32_off(tok, i, 16))) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+      uint4 hi, lo;
+      split8(reinterpret_cast<const float*>(&f[2 * kc]), hi, lo);
+      st_shared_v4(a_hi + kc * (kConvRows * 16) + r * 16, hi);
+      st_shared_v4(a_lo + kc * (kConvRows * 16) + r * 16, lo);
+    }
+  }
+}
+
+// LayerNorm statistics of a row whose two halves live in two partner threads (same lane, warps w / w+4).
+// Each thread reduces its own H values (two-pass, in registers), publishes (mean_q, M2_q) through 4 TMEM
+// columns it owns, and combines with its partner's pair (Chan's parallel variance).  eps = 1e-5.
+template <int H>
+LFT_DEVINL void pair_ln_stats(const float* y, uint32_t mbox_own, uint32_t mbox_partner, int bar_id, float& mean,
+                              float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < H; ++i) s += y[i];
+  const float mq = s * (1.f / H);
+  float m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < H; ++i) { const float d = y[i] - mq; m2 = fmaf(d, d, m2); }
+  float v[4] = {mq, m2, 0.f, 0.f};
+  tmem_st4(mbox_own, v);
+  tmem_wait_st();
+  tc_fence_before();
+  pair_bar_sync(bar_id - 1);
+  tc_fence_after();
+  float o[4];
+  tmem_ld4(mbox_partner, o);
+  mean = 0.5f * (mq + o[0]);
+  const float dm = mq - o[0];
+  const float M2 = m2 + o[1] + (0.5f * H) * dm * dm;
+  rstd = rsqrtf(M2 * (1.f / (2 * H)) + 1e-5f);
 }
 
 }  // namespace lft

@@ -1,10 +1,12 @@
 // Fused AngTrans (model/LFT.py:194-238): for every pixel, MHSA over its N=A*A angular tokens + FFN.
 //   Xn = LN(X + PE_a); Q,K = Xn Wq^T, Xn Wk^T; V = X Wv^T (raw tokens!); per head (hd=8) softmax(QK^T/sqrt 8) V;
 //   X1 = X + O Wo^T;  X2 = X1 + W2 relu(W1 LN2(X1)).
-// One CTA = 128 accumulator rows = floor(128/N) pixels x N views.  The (b c a h w) <-> (a, b h w, c)
-// permutes of the reference (LFT.py:216-223) are address arithmetic in the row loads/stores.
-// Projections/FFN run on tcgen05 (A operand built in smem by the row-owner threads, weights streamed
-// through the ring); the 25x25 (hd 8) attention core is CUDA-core work with K/V shared through smem.
+// One CTA = 128 accumulator rows = floor(128/N) pixels x N views, 2 threads per row (channel halves = heads
+// 4q..4q+3).  The (b c a h w) <-> (a, b h w, c) permutes of the reference (LFT.py:216-223) are address
+// arithmetic in the row loads/stores.  Both LayerNorms are folded into the following projection
+// (LN(z) W^T = rstd (x W'^T + PE W'^T - mean u) + c), so Q, K and V come from ONE raw operand.
+// Projections/FFN run on tcgen05; the N x N (hd 8) attention core is CUDA-core work with K/V shared
+// through shared memory (fp32, XOR-swizzled 16-byte chunks).
 #include "host.h"
 #include "kernels.cuh"
 
@@ -14,29 +16,38 @@ constexpr int kAngNST = 3;
 constexpr uint32_t kAngStage = 128 * 128;  // largest slab: N=128 rows
 constexpr size_t kSmemAng = kCtlBytes + 65536 + kAngNST * kAngStage;
 
-__global__ void __launch_bounds__(kThreads, 2)
+LFT_DEVINL float dot8(const float* q, const float4& k0, const float4& k1) {
+  float s0 = q[0] * k0.x, s1 = q[4] * k1.x;
+  s0 = fmaf(q[1], k0.y, s0); s1 = fmaf(q[5], k1.y, s1);
+  s0 = fmaf(q[2], k0.z, s0); s1 = fmaf(q[6], k1.z, s1);
+  s0 = fmaf(q[3], k0.w, s0); s1 = fmaf(q[7], k1.w, s1);
+  return s0 + s1;
+}
+
+__global__ void __launch_bounds__(kThreads2, 2)
 k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __restrict__ wqk,
       const uint8_t* __restrict__ wv, const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1,
-      const uint8_t* __restrict__ w2, const float* __restrict__ ln, const float* __restrict__ pe, int N, int PP,
-      long long npix, int passes) {
+      const uint8_t* __restrict__ w2, const float* __restrict__ tab, const float* __restrict__ peqk,
+      const float* __restrict__ pe, int N, int PP, long long npix, int passes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t s_base = smem_u32(smem);
   const uint32_t R1 = s_base + kCtlBytes;  // 32 KB
   const uint32_t R2 = R1 + 32768;          // 32 KB
   const uint32_t ring = R2 + 32768;
-  uint8_t* r2_ptr = smem + kCtlBytes + 32768;
+  uint8_t* vs_ptr = smem + kCtlBytes;          // V (fp32, all heads) reuses R1 during the attention
+  uint8_t* ks_ptr = smem + kCtlBytes + 32768;  // K (fp32, all heads) in R2
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t LBO = 128 * 16;
 
-  cta_setup<kAngNST>(ctl, warp, lane, 128, 256);
+  cta_setup<kAngNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
 
   const GemmPhase g_qk{wqk, 128, 1}, g_v{wv, 64, 1}, g_o{wo, 64, 1}, g_1{w1, 128, 1}, g_2{w2, 64, 2};
 
-  if (warp == kWarpProducer) {
+  if (warp == kWarpProducer2) {
     if (lane == 0) {
       RingState<kAngNST> rs;
       ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_qk, passes);
@@ -45,14 +56,14 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes);
       ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes);
     }
-  } else if (warp == kWarpMma) {
+  } else if (warp == kWarpMma2) {
     if (lane == 0) {
       RingState<kAngNST> rs;
       mbar_wait(a_ready, 0);
       tc_fence_after();
       ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_qk, passes, R1, R1 + 16384, LBO, 0, NoShift{},
                                 tmem + 0, true);
-      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_v, passes, R2, R2 + 16384, LBO, 0, NoShift{},
+      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_v, passes, R1, R1 + 16384, LBO, 0, NoShift{},
                                 tmem + 128, true);
       umma_commit(mma_done);
       mbar_wait(a_ready, 1);
@@ -72,8 +83,8 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       umma_commit(mma_done);
     }
   } else {
-    // ------------------------------------------------------------ row owner: m = tid
-    const int m = tid;
+    // ------------------------------------------------------------ row owner: row m, channel half q
+    const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     const int PPT = 128 / N;
     const int pl = m / N, a = m - pl * N;
     const long long gp = (long long)blockIdx.x * PPT + pl;
@@ -84,87 +95,93 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       const int p = (int)(gp - b * PP);
       tok = (b * N + a) * PP + p;
     }
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const int aa = rowok ? a : 0;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int bar_id = 1 + (warp & 3);
+    float mean, rstd;
 
-    // ---- phase 0: load X, stash, LN1(X+PE) -> R1, X -> R2
+    // ---- phase 0: load X (own 32 channels), stash in TMEM, LN1 statistics of X+PE, raw X -> R1
     {
-      float x[64];
-      const float4* src = reinterpret_cast<const float4*>(in + tok * 64);
+      float x[32];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 f = rowok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; ++i) {
+        const float4 f = rowok ? __ldg(reinterpret_cast<const float4*>(in + t32_off(tok, 8 * q + i, 16)))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
         x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
       }
+      tmem_st16(trow + 192 + 32 * q, x);
+      tmem_st16(trow + 192 + 32 * q + 16, x + 16);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_st16(trow + 192 + 16 * c, x + 16 * c);
-#pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
+      for (int c = 0; c < 4; ++c) {
         uint4 hi, lo;
-        split8(x + 8 * kc, hi, lo);
-        st_shared_v4(R2 + kc * LBO + m * 16, hi);
-        st_shared_v4(R2 + 16384 + kc * LBO + m * 16, lo);
+        split8(x + 8 * c, hi, lo);
+        st_shared_v4(R1 + (4 * q + c) * LBO + m * 16, hi);
+        st_shared_v4(R1 + 16384 + (4 * q + c) * LBO + m * 16, lo);
       }
-      const float4* pep = reinterpret_cast<const float4*>(pe + (rowok ? a : 0) * 64);
-      float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 f = __ldg(pep + i);
+      for (int i = 0; i < 8; ++i) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(pe) + (8 * q + i) * N + aa);  // [chunk 16][N][4]
         x[4 * i] += f.x; x[4 * i + 1] += f.y; x[4 * i + 2] += f.z; x[4 * i + 3] += f.w;
-        sum += (x[4 * i] + x[4 * i + 1]) + (x[4 * i + 2] + x[4 * i + 3]);
       }
-      const float mean = sum * (1.f / 64.f);
-      float var = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
-      const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-5f);
-#pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
-        float y[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = (x[8 * kc + e] - mean) * rstd * __ldg(ln + 8 * kc + e) + __ldg(ln + 64 + 8 * kc + e);
-        uint4 hi, lo;
-        split8(y, hi, lo);
-        st_shared_v4(R1 + kc * LBO + m * 16, hi);
-        st_shared_v4(R1 + 16384 + kc * LBO + m * 16, lo);
-      }
-      tmem_wait_st();
+      pair_ln_stats<32>(x, trow + 4 * q, trow + 4 * (1 - q), bar_id, mean, rstd);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(a_ready);
     }
 
-    // ---- phase 1: attention (two head-halves; K,V of 4 heads at a time in R2)
+    // ---- phase 1: attention. K (affine-corrected) -> R2, V -> R1 (fp32, all 8 heads), Q in registers
     mbar_wait(mma_done, 0);
     tc_fence_after();
-    const float scale = 0.35355339059327373f;  // 1/sqrt(8)
-    for (int half = 0; half < 2; ++half) {
-      {
-        float kv[16];
+    {
+      const float mr = mean * rstd;
+      const float4* pq4 = reinterpret_cast<const float4*>(peqk) + aa;  // [chunk 32][N][4]: Q chunks 0..15, K 16..31
+      const float4* tab4 = reinterpret_cast<const float4*>(tab);      // [u_qk 128 | c_qk 128 | u_1 128 | c_1 128]
+      float kv[16];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {  // K cols 64+32*half .. +32
-          tmem_ld16(trow + 64 + 32 * half + 16 * c, kv);
+      for (int c = 0; c < 2; ++c) {  // K columns 64 + 32q + 16c
+        const int col = 64 + 32 * q + 16 * c;
+        tmem_ld16(trow + col, kv);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ch = 4 * c + j;
-            *reinterpret_cast<float4*>(r2_ptr + m * 128 + ((ch ^ (m & 7)) * 16)) =
-                make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
-          }
+        for (int j = 0; j < 4; ++j) {
+          const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
+          const float4 uv = __ldg(tab4 + col / 4 + j), cv = __ldg(tab4 + 32 + col / 4 + j);
+          kv[4 * j] = fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
+          kv[4 * j + 1] = fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
+          kv[4 * j + 2] = fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
+          kv[4 * j + 3] = fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
         }
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {  // V cols 128+32*half .. +32
-          tmem_ld16(trow + 128 + 32 * half + 16 * c, kv);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ch = 4 * c + j;
-            *reinterpret_cast<float4*>(r2_ptr + 16384 + m * 128 + ((ch ^ (m & 7)) * 16)) =
-                make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
-          }
+        for (int j = 0; j < 4; ++j) {
+          const int ch = 8 * q + 4 * c + j;  // 16-byte chunk index within the 256-byte row
+          *reinterpret_cast<float4*>(ks_ptr + m * 256 + ((ch ^ (m & 7)) * 16)) =
+              make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
         }
       }
-      named_bar_sync(1, 128);
-      float q[32];
-      tmem_ld16(trow + 32 * half, q);
-      tmem_ld16(trow + 32 * half + 16, q + 16);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {  // V columns 128 + 32q + 16c (raw)
+        tmem_ld16(trow + 128 + 32 * q + 16 * c, kv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = 8 * q + 4 * c + j;
+          *reinterpret_cast<float4*>(vs_ptr + m * 256 + ((ch ^ (m & 7)) * 16)) =
+              make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+        }
+      }
+      float qv[32];
+      tmem_ld16_nowait(trow + 32 * q, qv);
+      tmem_ld16_nowait(trow + 32 * q + 16, qv + 16);
+      tmem_wait_ld();
+      const float scale = 0.35355339059327373f;  // 1/sqrt(8), folded into Q
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 pv = __ldg(pq4 + (8 * q + j) * N);
+        const float4 uv = __ldg(tab4 + 8 * q + j), cv = __ldg(tab4 + 32 + 8 * q + j);
+        qv[4 * j] = scale * fmaf(rstd, qv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
+        qv[4 * j + 1] = scale * fmaf(rstd, qv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
+        qv[4 * j + 2] = scale * fmaf(rstd, qv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
+        qv[4 * j + 3] = scale * fmaf(rstd, qv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+      }
+      rows_bar_sync256();
       float o[32];
 #pragma unroll
       for (int hh = 0; hh < 4; ++hh) {
@@ -174,91 +191,99 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
         float l = 1.f;
         if (pl < PPT) {
           const int r0 = pl * N;
+          const int c0 = 2 * (4 * q + hh);
           float mx = -INFINITY;
+#pragma unroll 5
           for (int t = 0; t < N; ++t) {
             const int r = r0 + t;
-            const float4 k0 = *reinterpret_cast<const float4*>(r2_ptr + r * 128 + (((2 * hh) ^ (r & 7)) * 16));
-            const float4 k1 = *reinterpret_cast<const float4*>(r2_ptr + r * 128 + (((2 * hh + 1) ^ (r & 7)) * 16));
-            float s = q[8 * hh] * k0.x;
-            s = fmaf(q[8 * hh + 1], k0.y, s); s = fmaf(q[8 * hh + 2], k0.z, s); s = fmaf(q[8 * hh + 3], k0.w, s);
-            s = fmaf(q[8 * hh + 4], k1.x, s); s = fmaf(q[8 * hh + 5], k1.y, s); s = fmaf(q[8 * hh + 6], k1.z, s);
-            s = fmaf(q[8 * hh + 7], k1.w, s);
-            mx = fmaxf(mx, s);
+            const float4 k0 = *reinterpret_cast<const float4*>(ks_ptr + r * 256 + ((c0 ^ (r & 7)) * 16));
+            const float4 k1 = *reinterpret_cast<const float4*>(ks_ptr + r * 256 + (((c0 + 1) ^ (r & 7)) * 16));
+            mx = fmaxf(mx, dot8(qv + 8 * hh, k0, k1));
           }
           l = 0.f;
+#pragma unroll 5
           for (int t = 0; t < N; ++t) {
             const int r = r0 + t;
-            const float4 k0 = *reinterpret_cast<const float4*>(r2_ptr + r * 128 + (((2 * hh) ^ (r & 7)) * 16));
-            const float4 k1 = *reinterpret_cast<const float4*>(r2_ptr + r * 128 + (((2 * hh + 1) ^ (r & 7)) * 16));
-            float s = q[8 * hh] * k0.x;
-            s = fmaf(q[8 * hh + 1], k0.y, s); s = fmaf(q[8 * hh + 2], k0.z, s); s = fmaf(q[8 * hh + 3], k0.w, s);
-            s = fmaf(q[8 * hh + 4], k1.x, s); s = fmaf(q[8 * hh + 5], k1.y, s); s = fmaf(q[8 * hh + 6], k1.z, s);
-            s = fmaf(q[8 * hh + 7], k1.w, s);
-            const float p = __expf((s - mx) * scale);
-            l += p;
-            const float4 v0 = *reinterpret_cast<const float4*>(r2_ptr + 16384 + r * 128 + (((2 * hh) ^ (r & 7)) * 16));
-            const float4 v1 =
-                *reinterpret_cast<const float4*>(r2_ptr + 16384 + r * 128 + (((2 * hh + 1) ^ (r & 7)) * 16));
-            acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]); acc[2] = fmaf(p, v0.z, acc[2]);
-            acc[3] = fmaf(p, v0.w, acc[3]); acc[4] = fmaf(p, v1.x, acc[4]); acc[5] = fmaf(p, v1.y, acc[5]);
-            acc[6] = fmaf(p, v1.z, acc[6]); acc[7] = fmaf(p, v1.w, acc[7]);
+            const float4 k0 = *reinterpret_cast<const float4*>(ks_ptr + r * 256 + ((c0 ^ (r & 7)) * 16));
+            const float4 k1 = *reinterpret_cast<const float4*>(ks_ptr + r * 256 + (((c0 + 1) ^ (r & 7)) * 16));
+            const float pw = __expf(dot8(qv + 8 * hh, k0, k1) - mx);
+            l += pw;
+            const float4 v0 = *reinterpret_cast<const float4*>(vs_ptr + r * 256 + ((c0 ^ (r & 7)) * 16));
+            const float4 v1 = *reinterpret_cast<const float4*>(vs_ptr + r * 256 + (((c0 + 1) ^ (r & 7)) * 16));
+            acc[0] = fmaf(pw, v0.x, acc[0]); acc[1] = fmaf(pw, v0.y, acc[1]); acc[2] = fmaf(pw, v0.z, acc[2]);
+            acc[3] = fmaf(pw, v0.w, acc[3]); acc[4] = fmaf(pw, v1.x, acc[4]); acc[5] = fmaf(pw, v1.y, acc[5]);
+            acc[6] = fmaf(pw, v1.z, acc[6]); acc[7] = fmaf(pw, v1.w, acc[7]);
           }
         }
         const float inv = 1.f / l;
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[8 * hh + e] = acc[e] * inv;
       }
+      rows_bar_sync256();  // everyone is done reading K/V: R1 can take the O operand
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 hi, lo;
         split8(o + 8 * c, hi, lo);
-        st_shared_v4(R1 + (4 * half + c) * LBO + m * 16, hi);
-        st_shared_v4(R1 + 16384 + (4 * half + c) * LBO + m * 16, lo);
+        st_shared_v4(R1 + (4 * q + c) * LBO + m * 16, hi);
+        st_shared_v4(R1 + 16384 + (4 * q + c) * LBO + m * 16, lo);
       }
-      named_bar_sync(1, 128);  // everyone done with this half's K/V before it is overwritten / reused
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(a_ready);
     }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(a_ready);
 
-    // ---- phase 2: X1 = X + O Wo^T (stash), LN2(X1) -> R1
+    // ---- phase 2: X1 = X + O Wo^T (own 32 channels; stash), LN2 statistics, raw X1 -> R1
     mbar_wait(mma_done, 1);
     tc_fence_after();
     {
-      float sum = 0.f;
+      float d[32], x[32];
+      tmem_ld16_nowait(trow + 32 * q, d);
+      tmem_ld16_nowait(trow + 32 * q + 16, d + 16);
+      tmem_ld16_nowait(trow + 192 + 32 * q, x);
+      tmem_ld16_nowait(trow + 192 + 32 * q + 16, x + 16);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] += d[i];
+      tmem_st16(trow + 192 + 32 * q, x);
+      tmem_st16(trow + 192 + 32 * q + 16, x + 16);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float d[16], x[16];
-        tmem_ld16(trow + 16 * c, d);
-        tmem_ld16(trow + 192 + 16 * c, x);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { x[i] += d[i]; sum += x[i]; }
-        tmem_st16(trow + 192 + 16 * c, x);
+        uint4 hi, lo;
+        split8(x + 8 * c, hi, lo);
+        st_shared_v4(R1 + (4 * q + c) * LBO + m * 16, hi);
+        st_shared_v4(R1 + 16384 + (4 * q + c) * LBO + m * 16, lo);
       }
-      tmem_wait_st();
-      const float mean = sum * (1.f / 64.f);
-      float var = 0.f;
-#pragma unroll
+      pair_ln_stats<32>(x, trow + 64 + 4 * q, trow + 64 + 4 * (1 - q), bar_id, mean, rstd);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+    }
+
+    // ---- phase 3: hidden = relu(LN2-folded D[0,128)), own 64 columns -> K=128 operand (hi in R1, lo in R2)
+    mbar_wait(mma_done, 0);
+    tc_fence_after();
+    {
+      const float mr = mean * rstd;
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        float x[16];
-        tmem_ld16(trow + 192 + 16 * c, x);
+        float d[16];
+        const int col = 64 * q + 16 * c;
+        tmem_ld16(trow + col, d);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const float dd = x[i] - mean; var = fmaf(dd, dd, var); }
-      }
-      const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-5f);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float x[16];
-        tmem_ld16(trow + 192 + 16 * c, x);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          x[i] = (x[i] - mean) * rstd * __ldg(ln + 128 + 16 * c + i) + __ldg(ln + 192 + 16 * c + i);
+        for (int j = 0; j < 4; ++j) {
+          const float4 uv = __ldg(reinterpret_cast<const float4*>(tab + 256 + col) + j);
+          const float4 cv = __ldg(reinterpret_cast<const float4*>(tab + 384 + col) + j);
+          d[4 * j] = fmaxf(fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x)), 0.f);
+          d[4 * j + 1] = fmaxf(fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y)), 0.f);
+          d[4 * j + 2] = fmaxf(fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
+          d[4 * j + 3] = fmaxf(fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w)), 0.f);
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           uint4 hi, lo;
-          split8(x + 8 * j, hi, lo);
-          st_shared_v4(R1 + (2 * c + j) * LBO + m * 16, hi);
-          st_shared_v4(R1 + 16384 + (2 * c + j) * LBO + m * 16, lo);
+          split8(d + 8 * j, hi, lo);
+          st_shared_v4(R1 + (8 * q + 2 * c + j) * LBO + m * 16, hi);
+          st_shared_v4(R2 + (8 * q + 2 * c + j) * LBO + m * 16, lo);
         }
       }
       fence_proxy_async_smem();
@@ -266,46 +291,27 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       mbar_arrive(a_ready);
     }
 
-    // ---- phase 3: hidden = relu(D[0,128)) -> K=128 operand (hi in R1, lo in R2)
-    mbar_wait(mma_done, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      float d[16];
-      tmem_ld16(trow + 16 * c, d);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) d[i] = fmaxf(d[i], 0.f);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint4 hi, lo;
-        split8(d + 8 * j, hi, lo);
-        st_shared_v4(R1 + (2 * c + j) * LBO + m * 16, hi);
-        st_shared_v4(R2 + (2 * c + j) * LBO + m * 16, lo);
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(a_ready);
-
-    // ---- phase 4: X2 = X1 + D[128,192) -> global
+    // ---- phase 4: X2 = X1 + D[128,192) -> global (own 32 channels)
     mbar_wait(mma_done, 1);
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float d[16], x[16];
-      tmem_ld16(trow + 128 + 16 * c, d);
-      tmem_ld16(trow + 192 + 16 * c, x);
+    {
+      float d[32], x[32];
+      tmem_ld16_nowait(trow + 128 + 32 * q, d);
+      tmem_ld16_nowait(trow + 128 + 32 * q + 16, d + 16);
+      tmem_ld16_nowait(trow + 192 + 32 * q, x);
+      tmem_ld16_nowait(trow + 192 + 32 * q + 16, x + 16);
+      tmem_wait_ld();
       if (rowok) {
-        float4* op = reinterpret_cast<float4*>(out + tok * 64 + 16 * c);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          op[i] = make_float4(x[4 * i] + d[4 * i], x[4 * i + 1] + d[4 * i + 1], x[4 * i + 2] + d[4 * i + 2],
-                              x[4 * i + 3] + d[4 * i + 3]);
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(out + t32_off(tok, 8 * q + i, 16)) =
+              make_float4(x[4 * i] + d[4 * i], x[4 * i + 1] + d[4 * i + 1], x[4 * i + 2] + d[4 * i + 2],
+                          x[4 * i + 3] + d[4 * i + 3]);
       }
     }
     tc_fence_before();
   }
-  cta_teardown(ctl, warp, 256);
+  cta_teardown(ctl, warp, 256, kWarpMma2);
 }
 
 int configure_ang() {
@@ -320,8 +326,8 @@ int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cud
   const unsigned grid = (unsigned)((npix + PPT - 1) / PPT);
   const Layer& L = h->layer[layer];
   Scope sc(h, K_ANG, st);
-  k_ang<<<grid, kThreads, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, L.a_ln, h->pe_ang, N, P * P,
-                                         npix, h->passes());
+  k_ang<<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, L.a_tab, L.a_peqk, h->pe_ang,
+                                          N, P * P, npix, h->passes());
   return sc.finish();
 }
 

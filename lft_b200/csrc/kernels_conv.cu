@@ -8,8 +8,8 @@ namespace lft {
 
 // ------------------------------------------------------------------------------------------------
 // conv_init0: Conv3d(1->64,(1,3,3),pad(0,1,1)) on the LR SAI mosaic, zero padded PER VIEW.
-// in : lr [B,1,A*P,A*P] fp32 (view (u,v) at rows u*P.., cols v*P..)   out: feat [T,64] fp32
-// One thread = one token x 4 channels (16 threads/token -> 256 B coalesced rows).
+// in : lr [B,1,A*P,A*P] fp32 (view (u,v) at rows u*P.., cols v*P..)   out: feat [T,64] fp32, T32 layout
+// One thread = one token x 4 channels; consecutive threads = consecutive tokens (512 B coalesced stores).
 __global__ void __launch_bounds__(256) k_conv0(const float* __restrict__ lr, const float* __restrict__ w0,
                                               float* __restrict__ out, int B, int A, int P) {
   __shared__ float sw[64 * 9];
@@ -17,8 +17,8 @@ __global__ void __launch_bounds__(256) k_conv0(const float* __restrict__ lr, con
   __syncthreads();
   const long long T = (long long)B * A * A * P * P;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long tok = gid >> 4;
-  const int cg = (int)(gid & 15);
+  const long long tok = ((gid >> 9) << 5) + (gid & 31);  // 512 threads per 32-token block
+  const int cg = (int)((gid >> 5) & 15);
   if (tok >= T) return;
   const int x = (int)(tok % P);
   const int y = (int)((tok / P) % P);
@@ -45,7 +45,35 @@ __global__ void __launch_bounds__(256) k_conv0(const float* __restrict__ lr, con
     for (int k = 0; k < 9; ++k) s = fmaf(w[k], t[k], s);
     op[j] = s;
   }
-  reinterpret_cast<float4*>(out + tok * 64)[cg] = o;
+  *reinterpret_cast<float4*>(out + t32_off(tok, cg, 16)) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout conversion for the stage-level entry points: channels-last [T][C] <-> T32.
+__global__ void __launch_bounds__(256) k_layout(const float* __restrict__ in, float* __restrict__ out, long long T,
+                                               int C4, int to_t32) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4
+  if (gid >= T * C4) return;
+  long long t;
+  int ch;
+  if (to_t32) {  // coalesced reads of rows
+    t = gid / C4;
+    ch = (int)(gid - t * C4);
+    *reinterpret_cast<float4*>(out + t32_off(t, ch, C4)) = __ldg(reinterpret_cast<const float4*>(in) + gid);
+  } else {
+    t = gid / C4;
+    ch = (int)(gid - t * C4);
+    reinterpret_cast<float4*>(out)[gid] = __ldg(reinterpret_cast<const float4*>(in + t32_off(t, ch, C4)));
+  }
+}
+
+int launch_layout(Handle* h, const float* in, float* out, long long T, int C, int to_t32, cudaStream_t st) {
+  const long long n = T * (C / 4);
+  k_layout<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, T, C / 4, to_t32);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(LFT_ERR_CUDA, "k_layout launch failed: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -57,7 +85,7 @@ __global__ void __launch_bounds__(256) k_conv0(const float* __restrict__ lr, con
 // nine taps are nine descriptor offsets into ONE staged copy of the inputs (no im2col).
 // A CTA computes 128 consecutive positions; pad positions are computed and discarded (6% at P=32).
 template <int N>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads2, 2)
 k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* __restrict__ out,
           const float* __restrict__ res, int V, int P, int passes, int epi) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -76,16 +104,16 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
   const long long G = (long long)V * VS;
   const long long g0 = (long long)blockIdx.x * 128;
 
-  cta_setup<NST>(ctl, warp, lane, 128, N <= 64 ? 64 : 128);
+  cta_setup<NST>(ctl, warp, lane, kRowThreads2, N <= 64 ? 64 : 128, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
 
   GemmPhase ph{wp, (uint32_t)N, 9};
-  if (warp == kWarpProducer) {
+  if (warp == kWarpProducer2) {
     if (lane == 0) {
       RingState<NST> rs;
       ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
     }
-  } else if (warp == kWarpMma) {
+  } else if (warp == kWarpMma2) {
     if (lane == 0) {
       RingState<NST> rs;
       mbar_wait(a_ready, 0);
@@ -97,69 +125,50 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
     }
   } else {
     // ---- stage the input window: rows r <-> positions g0 - kConvOff + r, lanes <-> rows
-    for (int r = tid; r < kConvRows; r += 128) {
-      const long long g = g0 - kConvOff + r;
-      const float* src = nullptr;
-      if (g >= 0 && g < G) {
-        const long long v = g / VS;
-        const int q = (int)(g - v * VS);
-        const int y = q / P1, x = q - y * P1;
-        if (y < P && x < P) src = in + ((v * P + y) * P + x) * 64;
-      }
-      float4 f[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        f[i] = src ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
-        uint4 hi, lo;
-        split8(reinterpret_cast<const float*>(&f[2 * kc]), hi, lo);
-        st_shared_v4(a_hi + kc * (kConvRows * 16) + r * 16, hi);
-        st_shared_v4(a_lo + kc * (kConvRows * 16) + r * 16, lo);
-      }
-    }
+    conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, tid);
     fence_proxy_async_smem();
     mbar_arrive(a_ready);
 
-    // ---- epilogue: lane <-> position
-    mbar_wait(mma_done, 0);
-    tc_fence_after();
-    const long long g = g0 + tid;
+    // ---- epilogue: row m <-> position, column half q
+    const int m = (warp & 3) * 32 + lane, q = warp >> 2;
+    constexpr int HC = N / 2;  // own columns
+    const long long g = g0 + m;
     long long tok = -1;
     if (g < G) {
       const long long v = g / VS;
-      const int q = (int)(g - v * VS);
-      const int y = q / P1, x = q - y * P1;
+      const int qq = (int)(g - v * VS);
+      const int y = qq / P1, x = qq - y * P1;
       if (y < P && x < P) tok = (v * P + y) * P + x;
     }
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < N; c0 += 16) {
-      float v[16];
-      tmem_ld16(trow + c0, v);
-      if (tok >= 0) {
-        if (epi & 1) {
+    float4 r4[HC / 4];
+    if ((epi & 2) && tok >= 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
-        }
-        if (epi & 2) {
-          const float4* rp = reinterpret_cast<const float4*>(res + tok * N + c0);
+      for (int i = 0; i < HC / 4; ++i)
+        r4[i] = __ldg(reinterpret_cast<const float4*>(res + t32_off(tok, q * (HC / 4) + i, N / 4)));
+    }
+    mbar_wait(mma_done, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float v[HC];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 r4 = __ldg(rp + i);
-            v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
-          }
-        }
-        float4* op = reinterpret_cast<float4*>(out + tok * N + c0);
+    for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(trow + HC * q + 16 * c, v + 16 * c);
+    tmem_wait_ld();
+    if (tok >= 0) {
+      if (epi & 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < HC; ++i) v[i] = lrelu02(v[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < HC / 4; ++i) {
+        float4 o4 = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        if (epi & 2) { o4.x += r4[i].x; o4.y += r4[i].y; o4.z += r4[i].z; o4.w += r4[i].w; }
+        *reinterpret_cast<float4*>(out + t32_off(tok, q * (HC / 4) + i, N / 4)) = o4;
       }
     }
     tc_fence_before();
   }
-  cta_teardown(ctl, warp, N <= 64 ? 64 : 128);
+  cta_teardown(ctl, warp, N <= 64 ? 64 : 128, kWarpMma2);
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Self-test: D[128 x N] = A[128 x K] * W[N x K]^T through exactly the machinery the real kernels use
@@ -274,7 +283,8 @@ int launch_conv0(Handle* h, const float* lr, float* out, int B, int P, cudaStrea
   const int A = h->cfg.ang_res;
   const long long T = (long long)B * A * A * P * P;
   Scope sc(h, K_CONV0, st);
-  k_conv0<<<(unsigned)((T * 16 + 255) / 256), 256, 0, st>>>(lr, h->w_conv0, out, B, A, P);
+  const long long Tp = (T + 31) / 32 * 32;
+  k_conv0<<<(unsigned)((Tp * 16 + 255) / 256), 256, 0, st>>>(lr, h->w_conv0, out, B, A, P);
   return sc.finish();
 }
 
@@ -284,9 +294,9 @@ int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* 
   const unsigned grid = (unsigned)((G + 127) / 128);
   Scope sc(h, N == 64 ? K_CONV64 : K_CONV128, st);
   if (N == 64)
-    k_conv3x3<64><<<grid, kThreads, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi);
+    k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi);
   else
-    k_conv3x3<128><<<grid, kThreads, kSmemConv128, st>>>(in, wp, out, res, V, P, h->passes(), epi);
+    k_conv3x3<128><<<grid, kThreads2, kSmemConv128, st>>>(in, wp, out, res, V, P, h->passes(), epi);
   return sc.finish();
 }
 

@@ -1,12 +1,16 @@
-// SpaTrans (model/LFT.py:118-191) after the 3x3 token embedding (k_conv3x3<128>, kernels_conv.cu):
-//   k_spa_qkv  : Yn = LN(tok + PE_s);  Q = Yn Wq^T, K = Yn Wk^T, V = tok Wv^T          (tcgen05)
-//   k_spa_attn : per head (hd=16) softmax over the clamped 5x5 window (<=25 keys) -- the finite entries
-//                of gen_mask (LFT.py:147-162) -- never materialising the [hw,hw] mask     (CUDA cores)
-//   k_spa_ffn  : Y1 = tok + O Wo^T; Y2 = Y1 + W2 relu(W1 LN2(Y1)); out = Y2 Wlin^T (1x1x1 conv 128->64)
-//                (+ the global residual of LFT.py:76 on the last block)                    (tcgen05)
+// SpaTrans (model/LFT.py:118-191):
+//   k_spa_embed_qkv : tok = conv3x3(feat, MLP.weight) (== unfold 3x3 + Linear, LFT.py:164-169) as an implicit GEMM,
+//                     then Q = LN(tok+PE_s) Wq^T, K = LN(tok+PE_s) Wk^T, V = tok Wv^T  (LFT.py:180-186), all from ONE
+//                     raw A operand: LayerNorm is folded into the projection epilogue,
+//                       LN(z) W^T = rstd (tok W'^T + PE W'^T - mean u) + c,   W' = W diag(gamma), u = W' 1, c = W beta.
+//   k_spa_attn      : per head (hd=16) softmax over the clamped 5x5 window (<=25 keys) -- the finite entries
+//                     of gen_mask (LFT.py:147-162) -- never materialising the [hw,hw] mask     (CUDA cores)
+//   k_spa_ffn       : Y1 = tok + O Wo^T; Y2 = Y1 + W2 relu(W1 LN2(Y1)); out = Y2 Wlin^T (1x1x1 conv 128->64)
+//                     (+ the global residual of LFT.py:76 on the last block); LN2 folded the same way.
 // Q/K/V/O use a planar head-major layout [view][head][y][j][x][4] (channel = head*16 + j*4 + e) so that
 // both the row-owner threads of the GEMM kernels and the x-major threads of the window attention
 // read/write 16-byte pieces that are contiguous across a warp.
+// tcgen05 kernels: 2 threads per accumulator row (column halves), 8 row warps + producer + MMA warp.
 #include "host.h"
 #include "kernels.cuh"
 
@@ -21,9 +25,8 @@ LFT_DEVINL long long planar_off(long long v, int head, int y, int j, int x, int 
   return ((((v * 8 + head) * P + y) * 4 + j) * (long long)P + x) * 4;
 }
 
-// write 16 accumulator columns [c0, c0+16) (= head c0/16) of one token into the planar layout
-LFT_DEVINL void planar_store16(float* base, long long v, int c0, int y, int x, int P, const float* d) {
-  const int head = c0 >> 4;
+// write 16 accumulator columns (= one head) of one token into the planar layout
+LFT_DEVINL void planar_store16(float* base, long long v, int head, int y, int x, int P, const float* d) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     *reinterpret_cast<float4*>(base + planar_off(v, head, y, j, x, P)) =
@@ -42,134 +45,161 @@ LFT_DEVINL void a_store16(uint32_t A, int kc0, int m, const float* x) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
-k_spa_qkv(const float* __restrict__ tok, const float* __restrict__ pe, const float* __restrict__ ln,
-          const uint8_t* __restrict__ wq, const uint8_t* __restrict__ wk, const uint8_t* __restrict__ wv,
-          float* __restrict__ Q, float* __restrict__ K, float* __restrict__ Vv, long long T, int P, int passes) {
+__global__ void __launch_bounds__(kThreads2, 2)
+k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp, const float* __restrict__ pe,
+                const float* __restrict__ peqk, const float* __restrict__ tab, const uint8_t* __restrict__ wq,
+                const uint8_t* __restrict__ wk, const uint8_t* __restrict__ wv, float* __restrict__ tok,
+                float* __restrict__ Q, float* __restrict__ K, float* __restrict__ Vv, int V, int P, int passes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
-  const uint32_t A = smem_u32(smem) + kCtlBytes;
-  const uint32_t ring = A + 65536;
+  const uint32_t U = smem_u32(smem) + kCtlBytes;
+  const uint32_t c_hi = U, c_lo = U + kConvRows * 128;  // conv staging (51.5 KB), dead after the conv MMAs
+  const uint32_t A = U;                                  // K=128 operand: hi [0,32K), lo [32K,64K)
+  const uint32_t ring = U + 65536;
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  cta_setup<kSpaNST>(ctl, warp, lane, 128, 256);
+  const int P1 = P + 1;
+  const long long VS = (long long)P1 * P1;
+  const long long G = (long long)V * VS;
+  const long long g0 = (long long)blockIdx.x * 128;
+  cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
-  const GemmPhase g_q{wq, 128, 2}, g_k{wk, 128, 2}, g_v{wv, 128, 2};
+  const GemmPhase g_c{wmlp, 128, 9}, g_q{wq, 128, 2}, g_k{wk, 128, 2}, g_v{wv, 128, 2};
 
-  if (warp == kWarpProducer) {
+  if (warp == kWarpProducer2) {
     if (lane == 0) {
       RingState<kSpaNST> rs;
+      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes);
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes);
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes);
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes);
     }
-  } else if (warp == kWarpMma) {
+  } else if (warp == kWarpMma2) {
     if (lane == 0) {
       RingState<kSpaNST> rs;
       mbar_wait(a_ready, 0);
+      tc_fence_after();
+      auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
+      ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
+                                c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
+      umma_commit(mma_done);
+      mbar_wait(a_ready, 1);
       tc_fence_after();
       ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
                                 tmem + 0, true);
       ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
                                 tmem + 128, true);
       umma_commit(mma_done);
-      mbar_wait(a_ready, 1);
+      mbar_wait(a_ready, 0);
       tc_fence_after();
       ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
                                 tmem + 0, true);
       umma_commit(mma_done);
     }
   } else {
-    const int m = tid;
-    const long long t = (long long)blockIdx.x * 128 + m;
-    const bool ok = t < T;
-    const long long tt = ok ? t : 0;
-    const int PP = P * P;
-    const long long v = tt / PP;
-    const int p = (int)(tt - v * PP);
-    const int y = p / P, x = p - y * P;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const float4* trp = reinterpret_cast<const float4*>(tok + tt * 128);
-    const float4* pep = reinterpret_cast<const float4*>(pe + (long long)p * 128);
-
-    // phase 0: z = tok + PE (stash in TMEM [128,256)), LN -> A
-    float sum = 0.f;
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float z[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 a = ok ? __ldg(trp + 4 * c + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 b = __ldg(pep + 4 * c + i);
-        z[4 * i] = a.x + b.x; z[4 * i + 1] = a.y + b.y; z[4 * i + 2] = a.z + b.z; z[4 * i + 3] = a.w + b.w;
-        sum += (z[4 * i] + z[4 * i + 1]) + (z[4 * i + 2] + z[4 * i + 3]);
-      }
-      tmem_st16(trow + 128 + 16 * c, z);
-    }
-    tmem_wait_st();
-    const float mean = sum * (1.f / 128.f);
-    float var = 0.f;
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float z[16];
-      tmem_ld16(trow + 128 + 16 * c, z);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { const float d = z[i] - mean; var = fmaf(d, d, var); }
-    }
-    const float rstd = rsqrtf(var * (1.f / 128.f) + 1e-5f);
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float z[16];
-      tmem_ld16(trow + 128 + 16 * c, z);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) z[i] = (z[i] - mean) * rstd * __ldg(ln + 16 * c + i) + __ldg(ln + 128 + 16 * c + i);
-      a_store16(A, 2 * c, m, z);
-    }
+    conv_stage_window(feat, c_hi, c_lo, g0, G, VS, P, tid);
     fence_proxy_async_smem();
-    tc_fence_before();
     mbar_arrive(a_ready);
 
-    // phase 1: Q out, then refill A with raw tok (V operand), then K out while the V MMAs run
+    const int m = (warp & 3) * 32 + lane, q = warp >> 2;
+    const long long g = g0 + m;
+    bool ok = false;
+    long long v = 0;
+    int y = 0, x = 0;
+    if (g < G) {
+      v = g / VS;
+      const int qq = (int)(g - v * VS);
+      y = qq / P1;
+      x = qq - y * P1;
+      ok = (y < P && x < P);
+    }
+    if (!ok) { v = 0; y = 0; x = 0; }
+    const int PP = P * P;
+    const int p = y * P + x;
+    const long long token = (v * P + y) * P + x;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+
+    // ---- phase 1: tok (own 64 columns) -> global, LN statistics of tok+PE, raw tok -> A
+    float mean, rstd;
     mbar_wait(mma_done, 0);
     tc_fence_after();
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float d[16];
-      tmem_ld16(trow + 16 * c, d);
-      if (ok) planar_store16(Q, v, 16 * c, y, x, P, d);
-    }
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float z[16];
+    {
+      float t[64];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 a = ok ? __ldg(trp + 4 * c + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        z[4 * i] = a.x; z[4 * i + 1] = a.y; z[4 * i + 2] = a.z; z[4 * i + 3] = a.w;
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, t + 16 * c);
+      tmem_wait_ld();
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          *reinterpret_cast<float4*>(tok + t32_off(token, 16 * q + i, 32)) =
+              make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
       }
-      a_store16(A, 2 * c, m, z);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, t + 16 * c);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pe) + (long long)(16 * q + i) * PP + p);  // [chunk][p][4]
+        t[4 * i] += b.x; t[4 * i + 1] += b.y; t[4 * i + 2] += b.z; t[4 * i + 3] += b.w;
+      }
+      pair_ln_stats<64>(t, trow + 128 + 4 * q, trow + 128 + 4 * (1 - q), 1 + (warp & 3), mean, rstd);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(a_ready);
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float d[16];
-      tmem_ld16(trow + 128 + 16 * c, d);
-      if (ok) planar_store16(K, v, 16 * c, y, x, P, d);
-    }
-    // phase 2: V out
+
+    // ---- phase 2: Q, K epilogues (affine LN correction), V MMAs start as soon as Q has been read
+    const float4* pq4 = reinterpret_cast<const float4*>(peqk) + p;  // [chunk 64][P*P][4]: Q chunks 0..31, K 32..63
+    const float4* tab4 = reinterpret_cast<const float4*>(tab);     // [u_q | u_k | c_q | c_k] x 128
+    const float mr = mean * rstd;
     mbar_wait(mma_done, 1);
     tc_fence_after();
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
       float d[16];
-      tmem_ld16(trow + 16 * c, d);
-      if (ok) planar_store16(Vv, v, 16 * c, y, x, P, d);
+      const int col = 64 * q + 16 * c;
+      tmem_ld16(trow + col, d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 pv = __ldg(pq4 + (long long)(col / 4 + j) * PP);
+        const float4 uv = __ldg(tab4 + col / 4 + j), cv = __ldg(tab4 + 64 + col / 4 + j);
+        d[4 * j] = fmaf(rstd, d[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
+        d[4 * j + 1] = fmaf(rstd, d[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
+        d[4 * j + 2] = fmaf(rstd, d[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
+        d[4 * j + 3] = fmaf(rstd, d[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+      }
+      if (ok) planar_store16(Q, v, 4 * q + c, y, x, P, d);
+    }
+    tc_fence_before();
+    mbar_arrive(a_ready);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float d[16];
+      const int col = 64 * q + 16 * c;
+      tmem_ld16(trow + 128 + col, d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 pv = __ldg(pq4 + (long long)(32 + col / 4 + j) * PP);
+        const float4 uv = __ldg(tab4 + 32 + col / 4 + j), cv = __ldg(tab4 + 96 + col / 4 + j);
+        d[4 * j] = fmaf(rstd, d[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
+        d[4 * j + 1] = fmaf(rstd, d[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
+        d[4 * j + 2] = fmaf(rstd, d[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
+        d[4 * j + 3] = fmaf(rstd, d[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+      }
+      if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
+    }
+    // ---- phase 3: V
+    mbar_wait(mma_done, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float d[16];
+      tmem_ld16(trow + 64 * q + 16 * c, d);
+      if (ok) planar_store16(Vv, v, 4 * q + c, y, x, P, d);
     }
     tc_fence_before();
   }
-  cta_teardown(ctl, warp, 256);
+  cta_teardown(ctl, warp, 256, kWarpMma2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -223,13 +253,13 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
       const int ky = y + dy, kx = x + dx;
       const int i = (dy + 2) * 5 + dx + 2;
       if (ky >= 0 && ky < P && kx >= 0 && kx < P) {
-        const float p = __expf(s[i] - mx);
-        l += p;
+        const float pw = __expf(s[i] - mx);
+        l += pw;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 f = __ldg(reinterpret_cast<const float4*>(Vv + planar_off(v, head, ky, j, kx, P)));
-          o[4 * j] = fmaf(p, f.x, o[4 * j]); o[4 * j + 1] = fmaf(p, f.y, o[4 * j + 1]);
-          o[4 * j + 2] = fmaf(p, f.z, o[4 * j + 2]); o[4 * j + 3] = fmaf(p, f.w, o[4 * j + 3]);
+          o[4 * j] = fmaf(pw, f.x, o[4 * j]); o[4 * j + 1] = fmaf(pw, f.y, o[4 * j + 1]);
+          o[4 * j + 2] = fmaf(pw, f.z, o[4 * j + 2]); o[4 * j + 3] = fmaf(pw, f.w, o[4 * j + 3]);
         }
       }
     }
@@ -241,8 +271,8 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
-k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __restrict__ ln,
+__global__ void __launch_bounds__(kThreads2, 2)
+k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __restrict__ tab,
           const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1a, const uint8_t* __restrict__ w1b,
           const uint8_t* __restrict__ w2a, const uint8_t* __restrict__ w2b, const uint8_t* __restrict__ wlin,
           float* __restrict__ out, const float* __restrict__ final_res, long long T, int P, int passes) {
@@ -253,12 +283,12 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  cta_setup<kSpaNST>(ctl, warp, lane, 128, 256);
+  cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
   const GemmPhase g_o{wo, 128, 2}, g_1a{w1a, 128, 2}, g_2a{w2a, 128, 2}, g_1b{w1b, 128, 2}, g_2b{w2b, 128, 2},
       g_l{wlin, 64, 2};
 
-  if (warp == kWarpProducer) {
+  if (warp == kWarpProducer2) {
     if (lane == 0) {
       RingState<kSpaNST> rs;
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_o, passes);
@@ -268,7 +298,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2b, passes);
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_l, passes);
     }
-  } else if (warp == kWarpMma) {
+  } else if (warp == kWarpMma2) {
     if (lane == 0) {
       RingState<kSpaNST> rs;
       uint32_t par = 0;
@@ -281,14 +311,14 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
         umma_commit(mma_done);
       };
       step(g_o, 0, true);      // D[0,128)    = O Wo^T
-      step(g_1a, 0, true);     // D[0,128)    = LN2(Y1) W1[0:128]^T
+      step(g_1a, 0, true);     // D[0,128)    = Y1 W'1[0:128]^T
       step(g_2a, 128, false);  // S[128,256) += relu(.) W2[:,0:128]^T     (S was initialised to Y1)
-      step(g_1b, 0, true);     // D[0,128)    = LN2(Y1) W1[128:256]^T
+      step(g_1b, 0, true);     // D[0,128)    = Y1 W'1[128:256]^T
       step(g_2b, 128, false);  // S          += relu(.) W2[:,128:256]^T   -> S = Y2
       step(g_l, 0, true);      // D[0,64)     = Y2 Wlin^T
     }
   } else {
-    const int m = tid;
+    const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     const long long t = (long long)blockIdx.x * 128 + m;
     const bool ok = t < T;
     const long long tt = ok ? t : 0;
@@ -296,8 +326,8 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
     const long long v = tt / PP;
     const int p = (int)(tt - v * PP);
     const int y = p / P, x = p - y * P;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    float* trow_g = tok + tt * 128;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* trow_g = tok + t32_off(tt, 16 * q, 32);  // own half of the token row, chunk stride 128 floats (Y1 is spilled here)
     uint32_t par = 0;
     auto publish = [&]() {
       fence_proxy_async_smem();
@@ -309,127 +339,119 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
       par ^= 1;
       tc_fence_after();
     };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // phase 0: A <- O (planar gather)
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float z[16];
+    // phase 0: A <- O (planar gather of own heads 4q..4q+3)
+    {
+      float4 f[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 f = ok ? __ldg(reinterpret_cast<const float4*>(O + planar_off(v, c, y, j, x, P)))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-        z[4 * j] = f.x; z[4 * j + 1] = f.y; z[4 * j + 2] = f.z; z[4 * j + 3] = f.w;
-      }
-      a_store16(A, 2 * c, m, z);
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          f[4 * c + j] = ok ? __ldg(reinterpret_cast<const float4*>(O + planar_off(v, 4 * q + c, y, j, x, P))) : zero4;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, reinterpret_cast<const float*>(&f[4 * c]));
     }
     publish();
 
-    // phase 1: Y1 = tok + D -> global (in place) and TMEM S; LN2 -> A
-    await();
-    float sum = 0.f;
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float d[16];
-      tmem_ld16(trow + 16 * c, d);
+    // phase 1: Y1 = tok + D (own half): -> global (spill), TMEM S, raw A; LN2 statistics
+    float mean, rstd;
+    {
+      float4 tk[16];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 a = ok ? *reinterpret_cast<const float4*>(trow_g + 16 * c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        d[4 * i] += a.x; d[4 * i + 1] += a.y; d[4 * i + 2] += a.z; d[4 * i + 3] += a.w;
-        sum += (d[4 * i] + d[4 * i + 1]) + (d[4 * i + 2] + d[4 * i + 3]);
+      for (int i = 0; i < 16; ++i) tk[i] = ok ? *reinterpret_cast<const float4*>(trow_g + 128 * i) : zero4;  // in flight
+      await();
+      float yv[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, yv + 16 * c);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        yv[4 * i] += tk[i].x; yv[4 * i + 1] += tk[i].y; yv[4 * i + 2] += tk[i].z; yv[4 * i + 3] += tk[i].w;
       }
-      tmem_st16(trow + 128 + 16 * c, d);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st16(trow + 128 + 64 * q + 16 * c, yv + 16 * c);
       if (ok) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<float4*>(trow_g + 16 * c + 4 * i) = make_float4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+        for (int i = 0; i < 16; ++i)
+          *reinterpret_cast<float4*>(trow_g + 128 * i) = make_float4(yv[4 * i], yv[4 * i + 1], yv[4 * i + 2], yv[4 * i + 3]);
       }
-    }
-    tmem_wait_st();
-    const float mean = sum * (1.f / 128.f);
-    float var = 0.f;
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float z[16];
-      tmem_ld16(trow + 128 + 16 * c, z);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { const float d = z[i] - mean; var = fmaf(d, d, var); }
-    }
-    const float rstd = rsqrtf(var * (1.f / 128.f) + 1e-5f);
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float z[16];
-      tmem_ld16(trow + 128 + 16 * c, z);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) z[i] = (z[i] - mean) * rstd * __ldg(ln + 256 + 16 * c + i) + __ldg(ln + 384 + 16 * c + i);
-      a_store16(A, 2 * c, m, z);
+      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, yv + 16 * c);
+      pair_ln_stats<64>(yv, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
     }
     publish();
+    const float mr = mean * rstd;
 
-    // phases 2..5: hidden halves
+    // phases 2..5: hidden halves (LN2 folded: hidden = relu(rstd*D - rstd*mean*u1 + c1))
     for (int half = 0; half < 2; ++half) {
-      await();  // FFN1 half done: D[0,128)
-#pragma unroll 2
-      for (int c = 0; c < 8; ++c) {
-        float d[16];
-        tmem_ld16(trow + 16 * c, d);
+      float4 y1[16];
+      if (half == 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) d[i] = fmaxf(d[i], 0.f);
-        a_store16(A, 2 * c, m, d);
+        for (int i = 0; i < 16; ++i) y1[i] = ok ? *reinterpret_cast<const float4*>(trow_g + 128 * i) : zero4;  // prefetch Y1
+      }
+      await();  // FFN1 half done: D[0,128)
+      const float4* u1 = reinterpret_cast<const float4*>(tab + 512 + 128 * half + 64 * q);
+      const float4* c1 = reinterpret_cast<const float4*>(tab + 768 + 128 * half + 64 * q);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float d[16];
+        tmem_ld16(trow + 64 * q + 16 * c, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 uv = __ldg(u1 + 4 * c + j), cv = __ldg(c1 + 4 * c + j);
+          d[4 * j] = fmaxf(fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x)), 0.f);
+          d[4 * j + 1] = fmaxf(fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y)), 0.f);
+          d[4 * j + 2] = fmaxf(fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
+          d[4 * j + 3] = fmaxf(fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w)), 0.f);
+        }
+        a_store16(A, 8 * q + 2 * c, m, d);
       }
       publish();
       await();  // FFN2 half accumulated into S
       if (half == 0) {
-        // rebuild LN2(Y1) from the Y1 row written in phase 1 (same thread wrote it)
-#pragma unroll 2
-        for (int c = 0; c < 8; ++c) {
-          float z[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 a = ok ? *reinterpret_cast<const float4*>(trow_g + 16 * c + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            z[4 * i] = a.x; z[4 * i + 1] = a.y; z[4 * i + 2] = a.z; z[4 * i + 3] = a.w;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) z[i] = (z[i] - mean) * rstd * __ldg(ln + 256 + 16 * c + i) + __ldg(ln + 384 + 16 * c + i);
-          a_store16(A, 2 * c, m, z);
-        }
+        for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, reinterpret_cast<const float*>(&y1[4 * c]));
         publish();
       }
     }
-    // phase 6: A <- Y2 = S
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
+    // phase 6: A <- Y2 = S (own half)
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
       float z[16];
-      tmem_ld16(trow + 128 + 16 * c, z);
-      a_store16(A, 2 * c, m, z);
+      tmem_ld16(trow + 128 + 64 * q + 16 * c, z);
+      a_store16(A, 8 * q + 2 * c, m, z);
     }
     publish();
-    // phase 7: out = D[0,64) (+ global residual)
+    // phase 7: out = D[0,64) (+ global residual), own 32 columns
+    float4 r4[8];
+    if (final_res) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        r4[i] = ok ? __ldg(reinterpret_cast<const float4*>(final_res + t32_off(tt, 8 * q + i, 16))) : zero4;
+    }
     await();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float d[16];
-      tmem_ld16(trow + 16 * c, d);
+    {
+      float d[32];
+      tmem_ld16_nowait(trow + 32 * q, d);
+      tmem_ld16_nowait(trow + 32 * q + 16, d + 16);
+      tmem_wait_ld();
       if (ok) {
-        float4* op = reinterpret_cast<float4*>(out + t * 64 + 16 * c);
-        if (final_res) {
-          const float4* rp = reinterpret_cast<const float4*>(final_res + t * 64 + 16 * c);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 r = __ldg(rp + i);
-            d[4 * i] += r.x; d[4 * i + 1] += r.y; d[4 * i + 2] += r.z; d[4 * i + 3] += r.w;
-          }
+        for (int i = 0; i < 8; ++i) {
+          float4 o4 = make_float4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+          if (final_res) { o4.x += r4[i].x; o4.y += r4[i].y; o4.z += r4[i].z; o4.w += r4[i].w; }
+          *reinterpret_cast<float4*>(out + t32_off(tt, 8 * q + i, 16)) = o4;
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) op[i] = make_float4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
       }
     }
     tc_fence_before();
   }
-  cta_teardown(ctl, warp, 256);
+  cta_teardown(ctl, warp, 256, kWarpMma2);
 }
 
 int configure_spa() {
-  CUDA_TRY(cudaFuncSetAttribute(k_spa_qkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   return 0;
 }
@@ -442,12 +464,11 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
   const long long T = V * P * P;
   const Layer& L = h->layer[layer];
   int rc;
-  if ((rc = launch_conv3x3(h, 128, in, L.s_wmlp, w.tok, nullptr, (int)V, P, 0, st))) return rc;
-  const unsigned grid = (unsigned)((T + 127) / 128);
   {
+    const long long G = V * (P + 1) * (P + 1);
     Scope sc(h, K_SPA_QKV, st);
-    k_spa_qkv<<<grid, kThreads, kSmemSpa, st>>>(w.tok, L.s_pe, L.s_ln, L.s_wq, L.s_wk, L.s_wv, w.q, w.k, w.v, T, P,
-                                               h->passes());
+    k_spa_embed_qkv<<<(unsigned)((G + 127) / 128), kThreads2, kSmemSpa, st>>>(
+        in, L.s_wmlp, L.s_pe, L.s_peqk, L.s_tab, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes());
     if ((rc = sc.finish())) return rc;
   }
   {
@@ -458,8 +479,9 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
   }
   {
     Scope sc(h, K_SPA_FFN, st);
-    k_spa_ffn<<<grid, kThreads, kSmemSpa, st>>>(w.o, w.tok, L.s_ln, L.s_wo, L.s_w1a, L.s_w1b, L.s_w2a, L.s_w2b, L.s_wlin,
-                                               out, final_res, T, P, h->passes());
+    k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, L.s_tab, L.s_wo, L.s_w1a, L.s_w1b,
+                                                                        L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P,
+                                                                        h->passes());
     if ((rc = sc.finish())) return rc;
   }
   return 0;

@@ -77,12 +77,11 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t par = 0;
     {
-      const float4* src = reinterpret_cast<const float4*>(feat + tt * 64);
 #pragma unroll
       for (int kc = 0; kc < 8; ++kc) {
         float z[8];
-        const float4 f0 = ok ? __ldg(src + 2 * kc) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 f1 = ok ? __ldg(src + 2 * kc + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 f0 = ok ? __ldg(reinterpret_cast<const float4*>(feat + t32_off(tt, 2 * kc, 16))) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 f1 = ok ? __ldg(reinterpret_cast<const float4*>(feat + t32_off(tt, 2 * kc + 1, 16))) : make_float4(0.f, 0.f, 0.f, 0.f);
         z[0] = f0.x; z[1] = f0.y; z[2] = f0.z; z[3] = f0.w; z[4] = f1.x; z[5] = f1.y; z[6] = f1.z; z[7] = f1.w;
         uint4 hi, lo;
         split8(z, hi, lo);

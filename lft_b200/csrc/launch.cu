@@ -21,6 +21,7 @@ int configure_kernels() {
 size_t ws_floats_per_token(int scale) { return 4 * 64 + 5 * 128 + 9 * (size_t)scale * scale + 1; }
 
 Workspace carve(void* ws, long long T, int scale) {
+  T = (T + 31) / 32 * 32;  // T32 layout: whole 32-token blocks
   Workspace w;
   float* p = reinterpret_cast<float*>(ws);
   w.f0 = p; p += T * 64;
@@ -90,7 +91,8 @@ extern "C" {
 int lft_workspace_bytes(lft_handle* hh, int32_t B, int32_t P, size_t* bytes) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h || !bytes || B < 1 || P < 1) return fail(LFT_ERR_ARG, "bad argument");
-  const size_t T = (size_t)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
+  size_t T = (size_t)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
+  T = (T + 31) / 32 * 32;
   *bytes = T * ws_floats_per_token(h->cfg.scale) * sizeof(float) + 1024;
   return 0;
 }
@@ -105,7 +107,8 @@ int lft_stage_conv_init(lft_handle* hh, const float* lr, float* feat, int32_t B,
   if (ws_bytes < need) return fail(LFT_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
   const long long T = (long long)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
   Workspace w = carve(ws, T, h->cfg.scale);
-  return run_conv_init(h, lr, feat, w.f0, w.f1, w.f2, B, P, (cudaStream_t)stream);
+  if ((rc = run_conv_init(h, lr, w.fres, w.f0, w.f1, w.f2, B, P, (cudaStream_t)stream))) return rc;
+  return launch_layout(h, w.fres, feat, T, 64, 0, (cudaStream_t)stream);
 }
 
 int lft_stage_ang(lft_handle* hh, int32_t layer, const float* in, float* out, int32_t B, int32_t P, void* ws,
@@ -114,8 +117,14 @@ int lft_stage_ang(lft_handle* hh, int32_t layer, const float* in, float* out, in
   int rc = check_ready(h, B, P);
   if (rc) return rc;
   if (layer < 0 || layer >= kLayers) return fail(LFT_ERR_ARG, "layer out of range");
-  (void)ws; (void)ws_bytes;
-  return run_ang(h, layer, in, out, B, P, (cudaStream_t)stream);
+  size_t need;
+  lft_workspace_bytes(hh, B, P, &need);
+  if (ws_bytes < need) return fail(LFT_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
+  const long long T = (long long)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
+  Workspace w = carve(ws, T, h->cfg.scale);
+  if ((rc = launch_layout(h, in, w.f0, T, 64, 1, (cudaStream_t)stream))) return rc;
+  if ((rc = run_ang(h, layer, w.f0, w.f1, B, P, (cudaStream_t)stream))) return rc;
+  return launch_layout(h, w.f1, out, T, 64, 0, (cudaStream_t)stream);
 }
 
 int lft_stage_spa(lft_handle* hh, int32_t layer, const float* in, float* out, int32_t B, int32_t P, void* ws,
@@ -129,7 +138,9 @@ int lft_stage_spa(lft_handle* hh, int32_t layer, const float* in, float* out, in
   if (ws_bytes < need) return fail(LFT_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
   const long long T = (long long)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
   Workspace w = carve(ws, T, h->cfg.scale);
-  return run_spa(h, layer, in, out, nullptr, w, B, P, (cudaStream_t)stream);
+  if ((rc = launch_layout(h, in, w.f0, T, 64, 1, (cudaStream_t)stream))) return rc;
+  if ((rc = run_spa(h, layer, w.f0, w.f1, nullptr, w, B, P, (cudaStream_t)stream))) return rc;
+  return launch_layout(h, w.f1, out, T, 64, 0, (cudaStream_t)stream);
 }
 
 int lft_stage_upsample(lft_handle* hh, const float* feat, const float* lr, float* sr, int32_t B, int32_t P, void* ws,
@@ -142,7 +153,8 @@ int lft_stage_upsample(lft_handle* hh, const float* feat, const float* lr, float
   if (ws_bytes < need) return fail(LFT_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
   const long long T = (long long)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
   Workspace w = carve(ws, T, h->cfg.scale);
-  return run_upsample(h, feat, lr, sr, w.pp, B, P, 0, (cudaStream_t)stream);
+  if ((rc = launch_layout(h, feat, w.f0, T, 64, 1, (cudaStream_t)stream))) return rc;
+  return run_upsample(h, w.f0, lr, sr, w.pp, B, P, 0, (cudaStream_t)stream);
 }
 
 int lft_forward(lft_handle* hh, const float* lr, float* sr, int32_t B, int32_t P, void* ws, size_t ws_bytes,
