@@ -285,6 +285,11 @@ struct NoShift {
 };
 
 // LayerNorm statistics helpers operate on register chunks; see kernels.
+LFT_DEVINL float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 LFT_DEVINL float lrelu02(float x) { return x >= 0.f ? x : 0.2f * x; }
 
 }  // namespace lft

@@ -24,11 +24,14 @@ LFT_DEVINL float dot8(const float* q, const float4& k0, const float4& k1) {
   return s0 + s1;
 }
 
+// NV > 0: compile-time number of views (scores kept in registers, single QK pass); NV == 0: runtime N.
+template <int NV>
 __global__ void __launch_bounds__(kThreads2, 2)
 k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __restrict__ wqk,
       const uint8_t* __restrict__ wv, const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1,
       const uint8_t* __restrict__ w2, const float* __restrict__ tab, const float* __restrict__ peqk,
-      const float* __restrict__ pe, int N, int PP, long long npix, int passes) {
+      const float* __restrict__ pe, int Nrt, int PP, long long npix, int passes) {
+  const int N = NV > 0 ? NV : Nrt;
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t s_base = smem_u32(smem);
@@ -151,27 +154,23 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
           kv[4 * j + 3] = fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int ch = 8 * q + 4 * c + j;  // 16-byte chunk index within the 256-byte row
-          *reinterpret_cast<float4*>(ks_ptr + m * 256 + ((ch ^ (m & 7)) * 16)) =
+        for (int j = 0; j < 4; ++j)  // head-major [head][row][8 floats]: head = 4q + 2c + j/2, half j%2
+          *reinterpret_cast<float4*>(ks_ptr + (4 * q + 2 * c + (j >> 1)) * 4096 + m * 32 + (j & 1) * 16) =
               make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
-        }
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {  // V columns 128 + 32q + 16c (raw)
         tmem_ld16(trow + 128 + 32 * q + 16 * c, kv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int ch = 8 * q + 4 * c + j;
-          *reinterpret_cast<float4*>(vs_ptr + m * 256 + ((ch ^ (m & 7)) * 16)) =
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(vs_ptr + (4 * q + 2 * c + (j >> 1)) * 4096 + m * 32 + (j & 1) * 16) =
               make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
-        }
       }
       float qv[32];
       tmem_ld16_nowait(trow + 32 * q, qv);
       tmem_ld16_nowait(trow + 32 * q + 16, qv + 16);
       tmem_wait_ld();
-      const float scale = 0.35355339059327373f;  // 1/sqrt(8), folded into Q
+      const float scale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e)/sqrt(8), folded into Q (softmax via exp2)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 pv = __ldg(pq4 + (8 * q + j) * N);
@@ -190,29 +189,38 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
         float l = 1.f;
         if (pl < PPT) {
-          const int r0 = pl * N;
-          const int c0 = 2 * (4 * q + hh);
+          const float4* kb = reinterpret_cast<const float4*>(ks_ptr + (4 * q + hh) * 4096 + pl * N * 32);
+          const float4* vb = reinterpret_cast<const float4*>(vs_ptr + (4 * q + hh) * 4096 + pl * N * 32);
           float mx = -INFINITY;
-#pragma unroll 5
-          for (int t = 0; t < N; ++t) {
-            const int r = r0 + t;
-            const float4 k0 = *reinterpret_cast<const float4*>(ks_ptr + r * 256 + ((c0 ^ (r & 7)) * 16));
-            const float4 k1 = *reinterpret_cast<const float4*>(ks_ptr + r * 256 + (((c0 + 1) ^ (r & 7)) * 16));
-            mx = fmaxf(mx, dot8(qv + 8 * hh, k0, k1));
-          }
           l = 0.f;
-#pragma unroll 5
-          for (int t = 0; t < N; ++t) {
-            const int r = r0 + t;
-            const float4 k0 = *reinterpret_cast<const float4*>(ks_ptr + r * 256 + ((c0 ^ (r & 7)) * 16));
-            const float4 k1 = *reinterpret_cast<const float4*>(ks_ptr + r * 256 + (((c0 + 1) ^ (r & 7)) * 16));
-            const float pw = __expf(dot8(qv + 8 * hh, k0, k1) - mx);
-            l += pw;
-            const float4 v0 = *reinterpret_cast<const float4*>(vs_ptr + r * 256 + ((c0 ^ (r & 7)) * 16));
-            const float4 v1 = *reinterpret_cast<const float4*>(vs_ptr + r * 256 + (((c0 + 1) ^ (r & 7)) * 16));
-            acc[0] = fmaf(pw, v0.x, acc[0]); acc[1] = fmaf(pw, v0.y, acc[1]); acc[2] = fmaf(pw, v0.z, acc[2]);
-            acc[3] = fmaf(pw, v0.w, acc[3]); acc[4] = fmaf(pw, v1.x, acc[4]); acc[5] = fmaf(pw, v1.y, acc[5]);
-            acc[6] = fmaf(pw, v1.z, acc[6]); acc[7] = fmaf(pw, v1.w, acc[7]);
+          if constexpr (NV > 0 && NV <= 32) {
+            float sc[NV];
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+              sc[t] = dot8(qv + 8 * hh, kb[2 * t], kb[2 * t + 1]);
+              mx = fmaxf(mx, sc[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+              const float pw = fast_exp2(sc[t] - mx);
+              l += pw;
+              const float4 v0 = vb[2 * t], v1 = vb[2 * t + 1];
+              acc[0] = fmaf(pw, v0.x, acc[0]); acc[1] = fmaf(pw, v0.y, acc[1]); acc[2] = fmaf(pw, v0.z, acc[2]);
+              acc[3] = fmaf(pw, v0.w, acc[3]); acc[4] = fmaf(pw, v1.x, acc[4]); acc[5] = fmaf(pw, v1.y, acc[5]);
+              acc[6] = fmaf(pw, v1.z, acc[6]); acc[7] = fmaf(pw, v1.w, acc[7]);
+            }
+          } else {
+#pragma unroll 4
+            for (int t = 0; t < N; ++t) mx = fmaxf(mx, dot8(qv + 8 * hh, kb[2 * t], kb[2 * t + 1]));
+#pragma unroll 4
+            for (int t = 0; t < N; ++t) {
+              const float pw = fast_exp2(dot8(qv + 8 * hh, kb[2 * t], kb[2 * t + 1]) - mx);
+              l += pw;
+              const float4 v0 = vb[2 * t], v1 = vb[2 * t + 1];
+              acc[0] = fmaf(pw, v0.x, acc[0]); acc[1] = fmaf(pw, v0.y, acc[1]); acc[2] = fmaf(pw, v0.z, acc[2]);
+              acc[3] = fmaf(pw, v0.w, acc[3]); acc[4] = fmaf(pw, v1.x, acc[4]); acc[5] = fmaf(pw, v1.y, acc[5]);
+              acc[6] = fmaf(pw, v1.z, acc[6]); acc[7] = fmaf(pw, v1.w, acc[7]);
+            }
           }
         }
         const float inv = 1.f / l;
@@ -315,7 +323,9 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
 }
 
 int configure_ang() {
-  CUDA_TRY(cudaFuncSetAttribute(k_ang, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAng));
+  CUDA_TRY(cudaFuncSetAttribute(k_ang<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAng));
+  CUDA_TRY(cudaFuncSetAttribute(k_ang<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAng));
+  CUDA_TRY(cudaFuncSetAttribute(k_ang<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAng));
   return 0;
 }
 
@@ -326,8 +336,13 @@ int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cud
   const unsigned grid = (unsigned)((npix + PPT - 1) / PPT);
   const Layer& L = h->layer[layer];
   Scope sc(h, K_ANG, st);
-  k_ang<<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, L.a_tab, L.a_peqk, h->pe_ang,
-                                          N, P * P, npix, h->passes());
+#define LFT_ANG_LAUNCH(NV)                                                                                          \
+  k_ang<NV><<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, L.a_tab, L.a_peqk, \
+                                               h->pe_ang, N, P * P, npix, h->passes())
+  if (N == 25) LFT_ANG_LAUNCH(25);
+  else if (N == 9) LFT_ANG_LAUNCH(9);
+  else LFT_ANG_LAUNCH(0);
+#undef LFT_ANG_LAUNCH
   return sc.finish();
 }
 

@@ -203,71 +203,115 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
 }
 
 // ------------------------------------------------------------------------------------------------
-// Window attention: one thread = one (token, head). gid -> x fastest, then y, head, view.
+// Window attention. One thread = one head of TWO vertically adjacent queries (y0, x), (y0+1, x): the
+// 6 x 5 keys their windows cover are loaded once (30 instead of 50 key loads), scores stay in registers.
+// gid -> x fastest (coalesced 16-byte pieces of the planar layout), then row pair, head, view.
+LFT_DEVINL float dot16(const float* q, const float4& a, const float4& b, const float4& c, const float4& d) {
+  float s0 = q[0] * a.x, s1 = q[4] * b.x, s2 = q[8] * c.x, s3 = q[12] * d.x;
+  s0 = fmaf(q[1], a.y, s0); s1 = fmaf(q[5], b.y, s1); s2 = fmaf(q[9], c.y, s2); s3 = fmaf(q[13], d.y, s3);
+  s0 = fmaf(q[2], a.z, s0); s1 = fmaf(q[6], b.z, s1); s2 = fmaf(q[10], c.z, s2); s3 = fmaf(q[14], d.z, s3);
+  s0 = fmaf(q[3], a.w, s0); s1 = fmaf(q[7], b.w, s1); s2 = fmaf(q[11], c.w, s2); s3 = fmaf(q[15], d.w, s3);
+  return (s0 + s1) + (s2 + s3);
+}
+LFT_DEVINL void axpy16(float* o, float p, const float4& a, const float4& b, const float4& c, const float4& d) {
+  o[0] = fmaf(p, a.x, o[0]); o[1] = fmaf(p, a.y, o[1]); o[2] = fmaf(p, a.z, o[2]); o[3] = fmaf(p, a.w, o[3]);
+  o[4] = fmaf(p, b.x, o[4]); o[5] = fmaf(p, b.y, o[5]); o[6] = fmaf(p, b.z, o[6]); o[7] = fmaf(p, b.w, o[7]);
+  o[8] = fmaf(p, c.x, o[8]); o[9] = fmaf(p, c.y, o[9]); o[10] = fmaf(p, c.z, o[10]); o[11] = fmaf(p, c.w, o[11]);
+  o[12] = fmaf(p, d.x, o[12]); o[13] = fmaf(p, d.y, o[13]); o[14] = fmaf(p, d.z, o[14]); o[15] = fmaf(p, d.w, o[15]);
+}
+
 __global__ void __launch_bounds__(128)
 k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ Vv,
            float* __restrict__ O, long long nviews, int P) {
+  const int PH = (P + 1) >> 1;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = nviews * 8 * P * P;
+  const long long total = nviews * 8 * PH * P;
   if (gid >= total) return;
   const int x = (int)(gid % P);
-  const int y = (int)((gid / P) % P);
-  const int head = (int)((gid / ((long long)P * P)) & 7);
-  const long long v = gid / ((long long)P * P * 8);
-  float q[16];
+  const int y0 = 2 * (int)((gid / P) % PH);
+  const int head = (int)((gid / ((long long)P * PH)) & 7);
+  const long long v = gid / ((long long)P * PH * 8);
+  const bool two = (y0 + 1) < P;
+  const long long rowstride = (long long)P * 16;  // floats between consecutive y in the planar layout
+  const long long jstride = (long long)P * 4;     // floats between the 4 pieces of one (y, x)
+  const long long base = planar_off(v, head, 0, 0, x, P);
+  const float qs = 0.25f * 1.4426950408889634f;    // log2(e)/sqrt(16): softmax through exp2
+  float q0[16], q1[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float4 f = __ldg(reinterpret_cast<const float4*>(Q + planar_off(v, head, y, j, x, P)));
-    q[4 * j] = f.x; q[4 * j + 1] = f.y; q[4 * j + 2] = f.z; q[4 * j + 3] = f.w;
+    const float4 f = __ldg(reinterpret_cast<const float4*>(Q + base + y0 * rowstride + j * jstride));
+    q0[4 * j] = f.x * qs; q0[4 * j + 1] = f.y * qs; q0[4 * j + 2] = f.z * qs; q0[4 * j + 3] = f.w * qs;
+    const float4 g = two ? __ldg(reinterpret_cast<const float4*>(Q + base + (y0 + 1) * rowstride + j * jstride))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    q1[4 * j] = g.x * qs; q1[4 * j + 1] = g.y * qs; q1[4 * j + 2] = g.z * qs; q1[4 * j + 3] = g.w * qs;
   }
-  float s[25];
-  float mx = -INFINITY;
+  float s0[25], s1[25];
+  float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-  for (int dy = -2; dy <= 2; ++dy)
-#pragma unroll
-    for (int dx = -2; dx <= 2; ++dx) {
-      const int ky = y + dy, kx = x + dx;
-      const int i = (dy + 2) * 5 + dx + 2;
-      if (ky >= 0 && ky < P && kx >= 0 && kx < P) {
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(K + planar_off(v, head, ky, j, kx, P)));
-          acc = fmaf(q[4 * j], f.x, acc); acc = fmaf(q[4 * j + 1], f.y, acc);
-          acc = fmaf(q[4 * j + 2], f.z, acc); acc = fmaf(q[4 * j + 3], f.w, acc);
-        }
-        s[i] = acc * 0.25f;  // 1/sqrt(16)
-        mx = fmaxf(mx, s[i]);
-      } else {
-        s[i] = -INFINITY;
-      }
-    }
-  float l = 0.f;
-  float o[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) o[e] = 0.f;
-#pragma unroll
-  for (int dy = -2; dy <= 2; ++dy)
+  for (int kr = 0; kr < 6; ++kr) {
+    const int ky = y0 - 2 + kr;
+    const bool rowok = ky >= 0 && ky < P;
 #pragma unroll
     for (int dx = -2; dx <= 2; ++dx) {
-      const int ky = y + dy, kx = x + dx;
-      const int i = (dy + 2) * 5 + dx + 2;
-      if (ky >= 0 && ky < P && kx >= 0 && kx < P) {
-        const float pw = __expf(s[i] - mx);
-        l += pw;
+      const int kx = x + dx;
+      const bool ok = rowok && kx >= 0 && kx < P;
+      float a0 = -INFINITY, a1 = -INFINITY;
+      if (ok) {
+        const float* kp = K + base + ky * rowstride + dx * 4;
+        const float4 k0 = __ldg(reinterpret_cast<const float4*>(kp));
+        const float4 k1 = __ldg(reinterpret_cast<const float4*>(kp + jstride));
+        const float4 k2 = __ldg(reinterpret_cast<const float4*>(kp + 2 * jstride));
+        const float4 k3 = __ldg(reinterpret_cast<const float4*>(kp + 3 * jstride));
+        if (kr <= 4) a0 = dot16(q0, k0, k1, k2, k3);
+        if (kr >= 1) a1 = dot16(q1, k0, k1, k2, k3);
+      }
+      if (kr <= 4) { s0[kr * 5 + dx + 2] = a0; m0 = fmaxf(m0, a0); }
+      if (kr >= 1) { s1[(kr - 1) * 5 + dx + 2] = a1; m1 = fmaxf(m1, a1); }
+    }
+  }
+  if (!two) m1 = 0.f;
+  float l0 = 0.f, l1 = 0.f;
+  float o0[16], o1[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(Vv + planar_off(v, head, ky, j, kx, P)));
-          o[4 * j] = fmaf(pw, f.x, o[4 * j]); o[4 * j + 1] = fmaf(pw, f.y, o[4 * j + 1]);
-          o[4 * j + 2] = fmaf(pw, f.z, o[4 * j + 2]); o[4 * j + 3] = fmaf(pw, f.w, o[4 * j + 3]);
+  for (int e = 0; e < 16; ++e) { o0[e] = 0.f; o1[e] = 0.f; }
+#pragma unroll
+  for (int kr = 0; kr < 6; ++kr) {
+    const int ky = y0 - 2 + kr;
+    const bool rowok = ky >= 0 && ky < P;
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int kx = x + dx;
+      if (rowok && kx >= 0 && kx < P) {
+        const float* vp = Vv + base + ky * rowstride + dx * 4;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(vp));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(vp + jstride));
+        const float4 v2 = __ldg(reinterpret_cast<const float4*>(vp + 2 * jstride));
+        const float4 v3 = __ldg(reinterpret_cast<const float4*>(vp + 3 * jstride));
+        if (kr <= 4) {
+          const float p0 = fast_exp2(s0[kr * 5 + dx + 2] - m0);
+          l0 += p0;
+          axpy16(o0, p0, v0, v1, v2, v3);
+        }
+        if (kr >= 1) {
+          const float p1 = fast_exp2(s1[(kr - 1) * 5 + dx + 2] - m1);
+          l1 += p1;
+          axpy16(o1, p1, v0, v1, v2, v3);
         }
       }
     }
-  const float inv = 1.f / l;
+  }
+  const float i0 = 1.f / l0;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<float4*>(O + planar_off(v, head, y, j, x, P)) =
-        make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+    *reinterpret_cast<float4*>(O + base + y0 * rowstride + j * jstride) =
+        make_float4(o0[4 * j] * i0, o0[4 * j + 1] * i0, o0[4 * j + 2] * i0, o0[4 * j + 3] * i0);
+  if (two) {
+    const float i1 = 1.f / l1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(O + base + (y0 + 1) * rowstride + j * jstride) =
+          make_float4(o1[4 * j] * i1, o1[4 * j + 1] * i1, o1[4 * j + 2] * i1, o1[4 * j + 3] * i1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -473,7 +517,7 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
   }
   {
     Scope sc(h, K_SPA_ATTN, st);
-    const long long total = T * 8;
+    const long long total = V * 8 * ((P + 1) / 2) * P;
     k_spa_attn<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(w.q, w.k, w.v, w.o, V, P);
     if ((rc = sc.finish())) return rc;
   }
