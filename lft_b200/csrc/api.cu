@@ -215,8 +215,8 @@ static int finalize(Handle* h) {
       std::vector<float> uq, cq, uk, ck, u1, c1;
       const float *g1 = W(p + "norm.weight"), *b1 = W(p + "norm.bias");
       const float *g2 = W(p + "feed_forward.0.weight"), *b2 = W(p + "feed_forward.0.bias");
-      if ((rc = fold_pack(in_w, 0, 128, S, g1, b1, &L.s_wq, uq, cq, &L.h_wq_fold))) return rc;
-      if ((rc = fold_pack(in_w, 128, 128, S, g1, b1, &L.s_wk, uk, ck, &L.h_wk_fold))) return rc;
+      if ((rc = fold_pack(in_w, 0, 128, S, g1, b1, &L.s_wq, uq, cq, nullptr))) return rc;
+      if ((rc = fold_pack(in_w, 128, 128, S, g1, b1, &L.s_wk, uk, ck, nullptr))) return rc;
       if ((rc = fold_pack(W(p + "feed_forward.1.weight"), 0, 128, S, g2, b2, &L.s_w1a, u1, c1, nullptr))) return rc;
       if ((rc = fold_pack(W(p + "feed_forward.1.weight"), 128, 128, S, g2, b2, &L.s_w1b, u1, c1, nullptr))) return rc;
       std::vector<float> tab;
@@ -303,22 +303,17 @@ int ensure_spa_pe(Handle* h, int P) {
       for (int n = 0; n < S; ++n) tab_pl[((size_t)(n / 4) * PPn + t) * 4 + (n % 4)] = tab[(size_t)t * S + n];
     int rc = upload_f32(h, tab_pl, &h->layer[i].s_pe);
     if (rc) return rc;
-    // (PE_s W'q^T | PE_s W'k^T): the position-encoding term of the LN-folded Q/K projections
-    const std::vector<float>& wq = h->layer[i].h_wq_fold;
-    const std::vector<float>& wk = h->layer[i].h_wk_fold;
-    std::vector<float> pq((size_t)P * P * 256);
-    for (int t = 0; t < P * P; ++t)
+    // PE_s Wv^T: V = tok Wv^T is computed from the operand z = tok + PE_s, so this constant is subtracted
+    const float* wv = h->host_w["altblock." + std::to_string(i) + ".spa_trans.attention.in_proj_weight"].data() +
+                      (size_t)256 * S;
+    std::vector<float> pvt((size_t)PPn * S);
+    for (int t = 0; t < PPn; ++t)
       for (int n = 0; n < S; ++n) {
-        double aq = 0.0, ak = 0.0;
-        for (int k = 0; k < S; ++k) {
-          const double pv = tab[(size_t)t * S + k];
-          aq += pv * (double)wq[(size_t)n * S + k];
-          ak += pv * (double)wk[(size_t)n * S + k];
-        }
-        pq[((size_t)(n / 4) * PPn + t) * 4 + (n % 4)] = (float)aq;          // chunks 0..31: Q
-        pq[((size_t)(32 + n / 4) * PPn + t) * 4 + (n % 4)] = (float)ak;     // chunks 32..63: K
+        double a = 0.0;
+        for (int k = 0; k < S; ++k) a += (double)tab[(size_t)t * S + k] * (double)wv[(size_t)n * S + k];
+        pvt[((size_t)(n / 4) * PPn + t) * 4 + (n % 4)] = (float)a;
       }
-    if ((rc = upload_f32(h, pq, &h->layer[i].s_peqk))) return rc;
+    if ((rc = upload_f32(h, pvt, &h->layer[i].s_pev))) return rc;
   }
   h->pe_P = P;
   return 0;

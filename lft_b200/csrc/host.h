@@ -49,9 +49,9 @@ struct Layer {
   const uint8_t *s_w1a = nullptr, *s_w1b = nullptr, *s_w2a = nullptr, *s_w2b = nullptr, *s_wlin = nullptr;
   const float* s_ln = nullptr;  // [norm.w | norm.b | ff0.w | ff0.b] x 128
   const float* s_pe = nullptr;    // [P*P][128] SAI2Token(spa_position), rebuilt when P changes
-  const float* s_peqk = nullptr;  // [P*P][256]  (PE_s W'q^T | PE_s W'k^T), rebuilt when P changes
+  const float* s_pev = nullptr;   // chunk-planar [32][P*P][4]: PE_s Wv^T, rebuilt when P changes
   const float* s_tab = nullptr;   // [u_q 128 | u_k 128 | c_q 128 | c_k 128 | u_1 256 | c_1 256]
-  std::vector<float> h_wq_fold, h_wk_fold;  // host copies of W'q, W'k (gamma folded) for the PE tables
+
 };
 
 struct ProfEvent {

@@ -1,8 +1,9 @@
 // SpaTrans (model/LFT.py:118-191):
 //   k_spa_embed_qkv : tok = conv3x3(feat, MLP.weight) (== unfold 3x3 + Linear, LFT.py:164-169) as an implicit GEMM,
 //                     then Q = LN(tok+PE_s) Wq^T, K = LN(tok+PE_s) Wk^T, V = tok Wv^T  (LFT.py:180-186), all from ONE
-//                     raw A operand: LayerNorm is folded into the projection epilogue,
-//                       LN(z) W^T = rstd (tok W'^T + PE W'^T - mean u) + c,   W' = W diag(gamma), u = W' 1, c = W beta.
+//                     A operand z = tok + PE_s: LayerNorm is folded into the projection epilogue,
+//                       LN(z) W^T = rstd (z W'^T - mean u) + c,   W' = W diag(gamma), u = W' 1, c = W beta,
+//                     and V = z Wv^T - PE_s Wv^T (constant table).
 //   k_spa_attn      : per head (hd=16) softmax over the clamped 5x5 window (<=25 keys) -- the finite entries
 //                     of gen_mask (LFT.py:147-162) -- never materialising the [hw,hw] mask     (CUDA cores)
 //   k_spa_ffn       : Y1 = tok + O Wo^T; Y2 = Y1 + W2 relu(W1 LN2(Y1)); out = Y2 Wlin^T (1x1x1 conv 128->64)
@@ -47,7 +48,7 @@ LFT_DEVINL void a_store16(uint32_t A, int kc0, int m, const float* x) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads2, 2)
 k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp, const float* __restrict__ pe,
-                const float* __restrict__ peqk, const float* __restrict__ tab, const uint8_t* __restrict__ wq,
+                const float* __restrict__ pev, const float* __restrict__ tab, const uint8_t* __restrict__ wq,
                 const uint8_t* __restrict__ wk, const uint8_t* __restrict__ wv, float* __restrict__ tok,
                 float* __restrict__ Q, float* __restrict__ K, float* __restrict__ Vv, int V, int P, int passes) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -120,82 +121,93 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     const long long token = (v * P + y) * P + x;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 
-    // ---- phase 1: tok (own 64 columns) -> global, LN statistics of tok+PE, raw tok -> A
+    // ---- phase 1: tok (own 64 columns) -> global; z = tok + PE_s -> A operand and LN statistics.
+    // (Q, K = LN(z) W^T via the folded epilogue; V = tok Wv^T = z Wv^T - PE_s Wv^T.)  PE is fetched before the wait.
     float mean, rstd;
-    mbar_wait(mma_done, 0);
-    tc_fence_after();
     {
-      float t[64];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, t + 16 * c);
-      tmem_wait_ld();
-      if (ok) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          *reinterpret_cast<float4*>(tok + t32_off(token, 16 * q + i, 32)) =
-              make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, t + 16 * c);
+      float z[64];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(pe) + (long long)(16 * q + i) * PP + p);  // [chunk][p][4]
-        t[4 * i] += b.x; t[4 * i + 1] += b.y; t[4 * i + 2] += b.z; t[4 * i + 3] += b.w;
+        z[4 * i] = b.x; z[4 * i + 1] = b.y; z[4 * i + 2] = b.z; z[4 * i + 3] = b.w;
       }
-      pair_ln_stats<64>(t, trow + 128 + 4 * q, trow + 128 + 4 * (1 - q), 1 + (warp & 3), mean, rstd);
+      mbar_wait(mma_done, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float t[16];
+        tmem_ld16(trow + 64 * q + 16 * c, t);
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(tok + t32_off(token, 16 * q + 4 * c + i, 32)) =
+                make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[16 * c + i] += t[i];
+        a_store16(A, 8 * q + 2 * c, m, z + 16 * c);
+      }
+      pair_ln_stats<64>(z, trow + 128 + 4 * q, trow + 128 + 4 * (1 - q), 1 + (warp & 3), mean, rstd);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(a_ready);
 
     // ---- phase 2: Q, K epilogues (affine LN correction), V MMAs start as soon as Q has been read
-    const float4* pq4 = reinterpret_cast<const float4*>(peqk) + p;  // [chunk 64][P*P][4]: Q chunks 0..31, K 32..63
-    const float4* tab4 = reinterpret_cast<const float4*>(tab);     // [u_q | u_k | c_q | c_k] x 128
+    const float4* tab4 = reinterpret_cast<const float4*>(tab);  // [u_q | u_k | c_q | c_k] x 128
     const float mr = mean * rstd;
     mbar_wait(mma_done, 1);
     tc_fence_after();
-#pragma unroll 1
+#pragma unroll 2
     for (int c = 0; c < 4; ++c) {
       float d[16];
       const int col = 64 * q + 16 * c;
       tmem_ld16(trow + col, d);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 pv = __ldg(pq4 + (long long)(col / 4 + j) * PP);
         const float4 uv = __ldg(tab4 + col / 4 + j), cv = __ldg(tab4 + 64 + col / 4 + j);
-        d[4 * j] = fmaf(rstd, d[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
-        d[4 * j + 1] = fmaf(rstd, d[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
-        d[4 * j + 2] = fmaf(rstd, d[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
-        d[4 * j + 3] = fmaf(rstd, d[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+        d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
+        d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
+        d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
+        d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
       }
       if (ok) planar_store16(Q, v, 4 * q + c, y, x, P, d);
     }
     tc_fence_before();
     mbar_arrive(a_ready);
-#pragma unroll 1
+#pragma unroll 2
     for (int c = 0; c < 4; ++c) {
       float d[16];
       const int col = 64 * q + 16 * c;
       tmem_ld16(trow + 128 + col, d);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 pv = __ldg(pq4 + (long long)(32 + col / 4 + j) * PP);
         const float4 uv = __ldg(tab4 + 32 + col / 4 + j), cv = __ldg(tab4 + 96 + col / 4 + j);
-        d[4 * j] = fmaf(rstd, d[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
-        d[4 * j + 1] = fmaf(rstd, d[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
-        d[4 * j + 2] = fmaf(rstd, d[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
-        d[4 * j + 3] = fmaf(rstd, d[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+        d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
+        d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
+        d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
+        d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
       }
       if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
     }
-    // ---- phase 3: V
-    mbar_wait(mma_done, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float d[16];
-      tmem_ld16(trow + 64 * q + 16 * c, d);
-      if (ok) planar_store16(Vv, v, 4 * q + c, y, x, P, d);
+    // ---- phase 3: V = D - PE_s Wv^T  (table prefetched before the wait)
+    {
+      float4 pv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pv[i] = __ldg(reinterpret_cast<const float4*>(pev) + (long long)(16 * q + i) * PP + p);
+      mbar_wait(mma_done, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float d[16];
+        tmem_ld16(trow + 64 * q + 16 * c, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          d[4 * j] -= pv[4 * c + j].x; d[4 * j + 1] -= pv[4 * c + j].y;
+          d[4 * j + 2] -= pv[4 * c + j].z; d[4 * j + 3] -= pv[4 * c + j].w;
+        }
+        if (ok) planar_store16(Vv, v, 4 * q + c, y, x, P, d);
+      }
     }
     tc_fence_before();
   }
@@ -204,8 +216,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
 
 // ------------------------------------------------------------------------------------------------
 // Window attention. One thread = one head of TWO vertically adjacent queries (y0, x), (y0+1, x): the
-// 6 x 5 keys their windows cover are loaded once (30 instead of 50 key loads), scores stay in registers.
-// gid -> x fastest (coalesced 16-byte pieces of the planar layout), then row pair, head, view.
+// 6 x 5 keys their windows cover are read once (30 instead of 50 key reads).
 LFT_DEVINL float dot16(const float* q, const float4& a, const float4& b, const float4& c, const float4& d) {
   float s0 = q[0] * a.x, s1 = q[4] * b.x, s2 = q[8] * c.x, s3 = q[12] * d.x;
   s0 = fmaf(q[1], a.y, s0); s1 = fmaf(q[5], b.y, s1); s2 = fmaf(q[9], c.y, s2); s3 = fmaf(q[13], d.y, s3);
@@ -220,97 +231,132 @@ LFT_DEVINL void axpy16(float* o, float p, const float4& a, const float4& b, cons
   o[12] = fmaf(p, d.x, o[12]); o[13] = fmaf(p, d.y, o[13]); o[14] = fmaf(p, d.z, o[14]); o[15] = fmaf(p, d.w, o[15]);
 }
 
+// CTA = (view, head, block of kAttnRB query rows): the K and V planes of rows [r0-2, r0+RB+2) are contiguous
+// in the planar layout and are staged in shared memory with two bulk copies (TMA engine).  Softmax is
+// evaluated online, one key row at a time (5 scores per query live at once).
+constexpr int kAttnRB = 8;
+constexpr size_t kSmemAttn = 2 * (kAttnRB + 4) * 4 * 32 * 16 + 16;
+
 __global__ void __launch_bounds__(128)
 k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ Vv,
-           float* __restrict__ O, long long nviews, int P) {
-  const int PH = (P + 1) >> 1;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = nviews * 8 * PH * P;
-  if (gid >= total) return;
-  const int x = (int)(gid % P);
-  const int y0 = 2 * (int)((gid / P) % PH);
-  const int head = (int)((gid / ((long long)P * PH)) & 7);
-  const long long v = gid / ((long long)P * PH * 8);
-  const bool two = (y0 + 1) < P;
-  const long long rowstride = (long long)P * 16;  // floats between consecutive y in the planar layout
-  const long long jstride = (long long)P * 4;     // floats between the 4 pieces of one (y, x)
+           float* __restrict__ O, int P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int nblk = (P + kAttnRB - 1) / kAttnRB;
+  const int rb = blockIdx.x % nblk;
+  const int head = (blockIdx.x / nblk) & 7;
+  const long long v = blockIdx.x / (nblk * 8);
+  const int r0 = rb * kAttnRB;
+  const int ys = max(r0 - 2, 0), ye = min(r0 + kAttnRB + 2, P);   // staged key rows [ys, ye)
+  const uint32_t rowbytes = (uint32_t)P * 64;                      // one (y) plane: 4 pieces x P x 16 B
+  const uint32_t nbytes = (uint32_t)(ye - ys) * rowbytes;
+  const uint32_t bar = smem_u32(smem);
+  uint8_t* ks = smem + 16;
+  uint8_t* vs = ks + (kAttnRB + 4) * rowbytes;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, 2 * nbytes);
+    const long long src = planar_off(v, head, ys, 0, 0, P);
+    bulk_g2s(smem_u32(ks), K + src, nbytes, bar);
+    bulk_g2s(smem_u32(vs), Vv + src, nbytes, bar);
+  }
+  const int x = threadIdx.x % P;
+  const int rp = threadIdx.x / P;
+  const int y0 = r0 + 2 * rp;
+  const bool active = (rp < kAttnRB / 2) && (y0 < P);
+  const bool two = active && (y0 + 1) < P;
+  const long long rowstride = (long long)P * 16;  // floats between consecutive y
+  const int jstride = P * 4;                      // floats between the 4 pieces of one (y, x)
   const long long base = planar_off(v, head, 0, 0, x, P);
-  const float qs = 0.25f * 1.4426950408889634f;    // log2(e)/sqrt(16): softmax through exp2
+  const float qs = 0.25f * 1.4426950408889634f;   // log2(e)/sqrt(16): softmax through exp2
   float q0[16], q1[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float4 f = __ldg(reinterpret_cast<const float4*>(Q + base + y0 * rowstride + j * jstride));
+    const float4 f = active ? __ldg(reinterpret_cast<const float4*>(Q + base + y0 * rowstride + j * jstride))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
     q0[4 * j] = f.x * qs; q0[4 * j + 1] = f.y * qs; q0[4 * j + 2] = f.z * qs; q0[4 * j + 3] = f.w * qs;
     const float4 g = two ? __ldg(reinterpret_cast<const float4*>(Q + base + (y0 + 1) * rowstride + j * jstride))
                          : make_float4(0.f, 0.f, 0.f, 0.f);
     q1[4 * j] = g.x * qs; q1[4 * j + 1] = g.y * qs; q1[4 * j + 2] = g.z * qs; q1[4 * j + 3] = g.w * qs;
   }
-  float s0[25], s1[25];
-  float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-  for (int kr = 0; kr < 6; ++kr) {
-    const int ky = y0 - 2 + kr;
-    const bool rowok = ky >= 0 && ky < P;
-#pragma unroll
-    for (int dx = -2; dx <= 2; ++dx) {
-      const int kx = x + dx;
-      const bool ok = rowok && kx >= 0 && kx < P;
-      float a0 = -INFINITY, a1 = -INFINITY;
-      if (ok) {
-        const float* kp = K + base + ky * rowstride + dx * 4;
-        const float4 k0 = __ldg(reinterpret_cast<const float4*>(kp));
-        const float4 k1 = __ldg(reinterpret_cast<const float4*>(kp + jstride));
-        const float4 k2 = __ldg(reinterpret_cast<const float4*>(kp + 2 * jstride));
-        const float4 k3 = __ldg(reinterpret_cast<const float4*>(kp + 3 * jstride));
-        if (kr <= 4) a0 = dot16(q0, k0, k1, k2, k3);
-        if (kr >= 1) a1 = dot16(q1, k0, k1, k2, k3);
-      }
-      if (kr <= 4) { s0[kr * 5 + dx + 2] = a0; m0 = fmaxf(m0, a0); }
-      if (kr >= 1) { s1[(kr - 1) * 5 + dx + 2] = a1; m1 = fmaxf(m1, a1); }
-    }
-  }
-  if (!two) m1 = 0.f;
-  float l0 = 0.f, l1 = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float o0[16], o1[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) { o0[e] = 0.f; o1[e] = 0.f; }
+  mbar_wait(bar, 0);
+  if (active) {
 #pragma unroll
-  for (int kr = 0; kr < 6; ++kr) {
-    const int ky = y0 - 2 + kr;
-    const bool rowok = ky >= 0 && ky < P;
+    for (int kr = 0; kr < 6; ++kr) {
+      const int ky = y0 - 2 + kr;
+      if (ky < 0 || ky >= P) continue;
+      const float* krow = reinterpret_cast<const float*>(ks) + (size_t)(ky - ys) * (rowbytes / 4) + x * 4;
+      const float* vrow = reinterpret_cast<const float*>(vs) + (size_t)(ky - ys) * (rowbytes / 4) + x * 4;
+      float a0[5], a1[5];
+      float n0 = m0, n1 = m1;
 #pragma unroll
-    for (int dx = -2; dx <= 2; ++dx) {
-      const int kx = x + dx;
-      if (rowok && kx >= 0 && kx < P) {
-        const float* vp = Vv + base + ky * rowstride + dx * 4;
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(vp));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(vp + jstride));
-        const float4 v2 = __ldg(reinterpret_cast<const float4*>(vp + 2 * jstride));
-        const float4 v3 = __ldg(reinterpret_cast<const float4*>(vp + 3 * jstride));
-        if (kr <= 4) {
-          const float p0 = fast_exp2(s0[kr * 5 + dx + 2] - m0);
-          l0 += p0;
-          axpy16(o0, p0, v0, v1, v2, v3);
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int kx = x + dx;
+        a0[dx + 2] = -INFINITY;
+        a1[dx + 2] = -INFINITY;
+        if (kx >= 0 && kx < P) {
+          const float4 k0 = *reinterpret_cast<const float4*>(krow + dx * 4);
+          const float4 k1 = *reinterpret_cast<const float4*>(krow + dx * 4 + jstride);
+          const float4 k2 = *reinterpret_cast<const float4*>(krow + dx * 4 + 2 * jstride);
+          const float4 k3 = *reinterpret_cast<const float4*>(krow + dx * 4 + 3 * jstride);
+          if (kr <= 4) { a0[dx + 2] = dot16(q0, k0, k1, k2, k3); n0 = fmaxf(n0, a0[dx + 2]); }
+          if (kr >= 1) { a1[dx + 2] = dot16(q1, k0, k1, k2, k3); n1 = fmaxf(n1, a1[dx + 2]); }
         }
-        if (kr >= 1) {
-          const float p1 = fast_exp2(s1[(kr - 1) * 5 + dx + 2] - m1);
-          l1 += p1;
-          axpy16(o1, p1, v0, v1, v2, v3);
+      }
+      if (kr <= 4) {
+        const float sc = fast_exp2(m0 - n0);
+        m0 = n0;
+        l0 *= sc;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o0[e] *= sc;
+      }
+      if (kr >= 1 && two) {
+        const float sc = fast_exp2(m1 - n1);
+        m1 = n1;
+        l1 *= sc;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o1[e] *= sc;
+      }
+#pragma unroll
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int kx = x + dx;
+        if (kx >= 0 && kx < P) {
+          const float4 v0 = *reinterpret_cast<const float4*>(vrow + dx * 4);
+          const float4 v1 = *reinterpret_cast<const float4*>(vrow + dx * 4 + jstride);
+          const float4 v2 = *reinterpret_cast<const float4*>(vrow + dx * 4 + 2 * jstride);
+          const float4 v3 = *reinterpret_cast<const float4*>(vrow + dx * 4 + 3 * jstride);
+          if (kr <= 4) {
+            const float p0 = fast_exp2(a0[dx + 2] - m0);
+            l0 += p0;
+            axpy16(o0, p0, v0, v1, v2, v3);
+          }
+          if (kr >= 1 && two) {
+            const float p1 = fast_exp2(a1[dx + 2] - m1);
+            l1 += p1;
+            axpy16(o1, p1, v0, v1, v2, v3);
+          }
         }
       }
     }
-  }
-  const float i0 = 1.f / l0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<float4*>(O + base + y0 * rowstride + j * jstride) =
-        make_float4(o0[4 * j] * i0, o0[4 * j + 1] * i0, o0[4 * j + 2] * i0, o0[4 * j + 3] * i0);
-  if (two) {
-    const float i1 = 1.f / l1;
+    const float i0 = 1.f / l0;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<float4*>(O + base + (y0 + 1) * rowstride + j * jstride) =
-          make_float4(o1[4 * j] * i1, o1[4 * j + 1] * i1, o1[4 * j + 2] * i1, o1[4 * j + 3] * i1);
+      *reinterpret_cast<float4*>(O + base + y0 * rowstride + j * jstride) =
+          make_float4(o0[4 * j] * i0, o0[4 * j + 1] * i0, o0[4 * j + 2] * i0, o0[4 * j + 3] * i0);
+    if (two) {
+      const float i1 = 1.f / l1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(O + base + (y0 + 1) * rowstride + j * jstride) =
+            make_float4(o1[4 * j] * i1, o1[4 * j + 1] * i1, o1[4 * j + 2] * i1, o1[4 * j + 3] * i1);
+    }
   }
 }
 
@@ -497,6 +543,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
 int configure_spa() {
   CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAttn));
   return 0;
 }
 
@@ -512,13 +559,13 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     const long long G = V * (P + 1) * (P + 1);
     Scope sc(h, K_SPA_QKV, st);
     k_spa_embed_qkv<<<(unsigned)((G + 127) / 128), kThreads2, kSmemSpa, st>>>(
-        in, L.s_wmlp, L.s_pe, L.s_peqk, L.s_tab, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes());
+        in, L.s_wmlp, L.s_pe, L.s_pev, L.s_tab, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes());
     if ((rc = sc.finish())) return rc;
   }
   {
     Scope sc(h, K_SPA_ATTN, st);
-    const long long total = V * 8 * ((P + 1) / 2) * P;
-    k_spa_attn<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(w.q, w.k, w.v, w.o, V, P);
+    const int nblk = (P + kAttnRB - 1) / kAttnRB;
+    k_spa_attn<<<(unsigned)(V * 8 * nblk), 128, kSmemAttn, st>>>(w.q, w.k, w.v, w.o, P);
     if ((rc = sc.finish())) return rc;
   }
   {
