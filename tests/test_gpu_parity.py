@@ -201,5 +201,5 @@ def test_profile_and_launch_count():
     torch.cuda.synchronize()
     prof = eng.profile_read()
     eng.profile_enable(False)
-    assert eng.launch_count() - n0 == 4 + 4 * 5 + 2   # conv0+3 conv, 4x(ang, embed, qkv, attn, ffn), up gemm+gather
+    assert eng.launch_count() - n0 == 4 + 4 * 4 + 2   # conv0 + 3 conv, 4 x (ang, embed+qkv, attn, ffn), up gemm + gather
     assert prof["ang_fused"]["launches"] == 4 and prof["spa_ffn"]["ms"] > 0
