@@ -17,6 +17,8 @@ LIB = os.path.join(OUT_DIR, "liblft_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+if os.environ.get("LFT_TIMELINE"):
+    FLAGS.append("-DLFT_TIMELINE")
 
 
 def sources():

@@ -186,7 +186,7 @@ static int finalize(Handle* h) {
       tab.insert(tab.end(), cqk.begin(), cqk.end());
       tab.insert(tab.end(), u1.begin(), u1.end());
       tab.insert(tab.end(), c1.begin(), c1.end());
-      if ((rc = upload_f32(h, tab, &L.a_tab))) return rc;
+      L.a_tab = tab;
       const int NA = A * A;
       std::vector<float> peqk((size_t)NA * 128);  // chunk-planar [n/4][a][4]
       for (int a = 0; a < NA; ++a)
@@ -226,7 +226,7 @@ static int finalize(Handle* h) {
       tab.insert(tab.end(), ck.begin(), ck.end());
       tab.insert(tab.end(), u1.begin(), u1.end());
       tab.insert(tab.end(), c1.begin(), c1.end());
-      if ((rc = upload_f32(h, tab, &L.s_tab))) return rc;
+      L.s_tab = tab;
     }
     if ((rc = lin_pack(in_w, 256, 128, S, 0, S, &L.s_wv))) return rc;
     if ((rc = lin_pack(W(p + "attention.out_proj.weight"), 0, 128, S, 0, S, &L.s_wo))) return rc;
@@ -343,6 +343,7 @@ int lft_create(const lft_config* cfg, lft_handle** out) {
   if (prop.major != 10) return fail(LFT_ERR_CUDA, "device is sm_%d%d; this library is sm_100a only", prop.major, prop.minor);
   Handle* h = new Handle();
   h->cfg = *cfg;
+  h->num_sms = prop.multiProcessorCount;
   build_spec(h);
   int rc = configure_kernels();
   if (rc) { delete h; return rc; }

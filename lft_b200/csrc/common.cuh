@@ -75,6 +75,8 @@ LFT_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uin
       : "memory");
 }
 
+LFT_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---------------------------------------------------------------- TMEM
 LFT_DEVINL void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
@@ -237,6 +239,11 @@ LFT_DEVINL void ring_produce(RingState<NST>& rs, uint32_t ring_base, uint32_t st
 //   a_kslab_stride: byte distance between consecutive 64-wide k slabs of A (= 8*a_lbo for a plain
 //   operand; 0 together with per-slab `row_shift` for the conv taps).
 //   row_shift(ks): rows to shift A by for slab ks (conv taps), else 0.
+// Descriptors are built once per phase/stage and advanced by adding to their low word (the start-address
+// field never carries: shared addresses are < 256 KB).
+LFT_DEVINL uint64_t umma_desc_from(uint32_t lo32) { return ((uint64_t)0x4008u << 32) | lo32; }  // SBO=128 B, version 1
+LFT_DEVINL uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return (saddr >> 4) | ((lbo_bytes >> 4) << 16); }
+
 template <int NST, typename ShiftFn>
 LFT_DEVINL void ring_consume_mma(RingState<NST>& rs, uint32_t ring_base, uint32_t stage_bytes, uint32_t full0,
                                  uint32_t empty0, const GemmPhase& g, int passes, uint32_t a_hi, uint32_t a_lo,
@@ -244,36 +251,38 @@ LFT_DEVINL void ring_consume_mma(RingState<NST>& rs, uint32_t ring_base, uint32_
                                  bool fresh) {
   const uint32_t idesc = umma_idesc_bf16(g.N);
   const uint32_t b_lbo = g.N * 16u;
+  const uint32_t a_step = (2u * a_lbo) >> 4, b_step = (2u * b_lbo) >> 4;  // one K=16 step, in 16-byte units
+  const uint32_t ahi0 = umma_desc_lo(a_hi, a_lbo), alo0 = umma_desc_lo(a_lo, a_lbo);
   uint32_t acc = fresh ? 0u : 1u;
   for (uint32_t ks = 0; ks < g.kslabs; ++ks) {
     const int sh = row_shift(ks);
-    const uint32_t a_off = ks * a_kslab_stride + (uint32_t)(sh * 16);
+    // offset in 16-byte rows; a negative conv-tap shift is a plain 32-bit subtraction from the start-address
+    // field (callers keep >= kConvOff rows of headroom, so it never borrows from the LBO field)
+    const uint32_t a_off = (uint32_t)((int)((ks * a_kslab_stride) >> 4) + sh);
+    const uint32_t ah = ahi0 + a_off, al = alo0 + a_off;
     // hi weights: A_hi*W_hi (+ A_lo*W_hi)
     mbar_wait(full0 + 8u * rs.stage, rs.phase);
     tc_fence_after();
-    uint32_t b = ring_base + rs.stage * stage_bytes;
+    uint32_t b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      umma_bf16(d_tmem, umma_desc(a_hi + a_off + j * 2 * a_lbo, a_lbo, 128), umma_desc(b + j * 2 * b_lbo, b_lbo, 128),
-                idesc, acc);
+    for (uint32_t j = 0; j < 4; ++j) {
+      umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), idesc, acc);
       acc = 1u;
     }
     if (passes == 3) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        umma_bf16(d_tmem, umma_desc(a_lo + a_off + j * 2 * a_lbo, a_lbo, 128),
-                  umma_desc(b + j * 2 * b_lbo, b_lbo, 128), idesc, 1u);
+      for (uint32_t j = 0; j < 4; ++j)
+        umma_bf16(d_tmem, umma_desc_from(al + j * a_step), umma_desc_from(b0 + j * b_step), idesc, 1u);
     }
     umma_commit(empty0 + 8u * rs.stage);
     rs.advance();
     if (passes == 3) {  // lo weights: A_hi*W_lo
       mbar_wait(full0 + 8u * rs.stage, rs.phase);
       tc_fence_after();
-      b = ring_base + rs.stage * stage_bytes;
+      b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        umma_bf16(d_tmem, umma_desc(a_hi + a_off + j * 2 * a_lbo, a_lbo, 128),
-                  umma_desc(b + j * 2 * b_lbo, b_lbo, 128), idesc, 1u);
+      for (uint32_t j = 0; j < 4; ++j)
+        umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), idesc, 1u);
       umma_commit(empty0 + 8u * rs.stage);
       rs.advance();
     }
@@ -285,6 +294,35 @@ struct NoShift {
 };
 
 // LayerNorm statistics helpers operate on register chunks; see kernels.
+// ---------------------------------------------------------------- packed fp32x2 math (Blackwell FFMA2)
+typedef unsigned long long f32x2;
+LFT_DEVINL f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+LFT_DEVINL void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+LFT_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+LFT_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+LFT_DEVINL f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+LFT_DEVINL float hsum2(f32x2 v) {
+  float a, b;
+  unpack2(v, a, b);
+  return a + b;
+}
+
 LFT_DEVINL float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

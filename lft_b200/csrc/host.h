@@ -42,7 +42,7 @@ struct Layer {
   // AngTrans (LFT.py:194-238)
   const uint8_t *a_wqk = nullptr, *a_wv = nullptr, *a_wo = nullptr, *a_w1 = nullptr, *a_w2 = nullptr;
   const float* a_ln = nullptr;    // [norm.w | norm.b | ff0.w | ff0.b] x 64
-  const float* a_tab = nullptr;   // LN-folded epilogue constants [u_qk 128 | c_qk 128 | u_1 128 | c_1 128]
+  std::vector<float> a_tab;       // LN-folded epilogue constants [u_qk 128 | c_qk 128 | u_1 128 | c_1 128] (host; kernel param)
   const float* a_peqk = nullptr;  // [A*A][128]  PE_a W'qk^T
   // SpaTrans (LFT.py:118-191)
   const uint8_t *s_wmlp = nullptr, *s_wq = nullptr, *s_wk = nullptr, *s_wv = nullptr, *s_wo = nullptr;
@@ -50,7 +50,7 @@ struct Layer {
   const float* s_ln = nullptr;  // [norm.w | norm.b | ff0.w | ff0.b] x 128
   const float* s_pe = nullptr;    // [P*P][128] SAI2Token(spa_position), rebuilt when P changes
   const float* s_pev = nullptr;   // chunk-planar [32][P*P][4]: PE_s Wv^T, rebuilt when P changes
-  const float* s_tab = nullptr;   // [u_q 128 | u_k 128 | c_q 128 | c_k 128 | u_1 256 | c_1 256]
+  std::vector<float> s_tab;       // [u_q 128 | u_k 128 | c_q 128 | c_k 128 | u_1 256 | c_1 256] (host; kernel params)
 
 };
 
@@ -74,6 +74,7 @@ struct Handle {
   bool profiling = false;
   std::vector<ProfEvent> events;
   int64_t launches = 0;
+  int num_sms = 148;
   int passes() const { return cfg.precision == LFT_PREC_FP32 ? 3 : 1; }
 };
 
@@ -113,6 +114,7 @@ int configure_conv();
 int configure_ang();
 int configure_spa();
 int configure_up();
+int debug_timeline_spa(long long* out);
 int launch_conv0(Handle* h, const float* lr, float* out, int B, int P, cudaStream_t st);
 int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* out, const float* res, int V, int P,
                    int epi, cudaStream_t st);

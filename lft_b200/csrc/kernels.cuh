@@ -59,6 +59,22 @@ LFT_DEVINL void cta_teardown(Ctl* ctl, int warp, uint32_t tmem_cols, int mma_war
   }
 }
 
+// LN-fold epilogue constants travel as __grid_constant__ kernel parameters (constant bank, uniform reads).
+struct Tab512 { float v[512]; };
+
+// Optional phase timeline of the middle CTA (debug aid, compiled in with -DLFT_TIMELINE): slot s of row
+// warp 0 lane 0 -> g_tl[0][s], of the MMA thread -> g_tl[1][s].
+#ifdef LFT_TIMELINE
+static __device__ long long g_tl[2][32];
+#define LFT_TL(s)                                                                                   \
+  do {                                                                                              \
+    if (blockIdx.x == gridDim.x / 2 && (threadIdx.x == 0 || threadIdx.x == 32 * kWarpMma2))          \
+      g_tl[threadIdx.x == 0 ? 0 : 1][s] = clock64();                                                \
+  } while (0)
+#else
+#define LFT_TL(s) do {} while (0)
+#endif
+
 // "T32" activation layout for [T, C] fp32 tensors: blocks of 32 consecutive tokens, inside a block the
 // 16-byte channel chunks are the slow axis:  off(t, c) = (((t>>5)*(C/4) + c/4) * 32 + (t&31)) * 4 + c%4.
 // A warp whose lanes own 32 consecutive tokens reads/writes one chunk as 512 contiguous bytes.

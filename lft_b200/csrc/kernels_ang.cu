@@ -10,18 +10,21 @@
 #include "host.h"
 #include "kernels.cuh"
 
+#include <cstring>
+
 namespace lft {
 
 constexpr int kAngNST = 3;
 constexpr uint32_t kAngStage = 128 * 128;  // largest slab: N=128 rows
 constexpr size_t kSmemAng = kCtlBytes + 65536 + kAngNST * kAngStage;
 
-LFT_DEVINL float dot8(const float* q, const float4& k0, const float4& k1) {
-  float s0 = q[0] * k0.x, s1 = q[4] * k1.x;
-  s0 = fmaf(q[1], k0.y, s0); s1 = fmaf(q[5], k1.y, s1);
-  s0 = fmaf(q[2], k0.z, s0); s1 = fmaf(q[6], k1.z, s1);
-  s0 = fmaf(q[3], k0.w, s0); s1 = fmaf(q[7], k1.w, s1);
-  return s0 + s1;
+// q . k over 8 dims with packed FFMA2: q as 4 f32x2, k row as two 16-byte loads
+LFT_DEVINL float dot8(const f32x2* q, const ulonglong2& k0, const ulonglong2& k1) {
+  f32x2 a = mul2(q[0], k0.x);
+  f32x2 b = mul2(q[1], k0.y);
+  a = fma2(q[2], k1.x, a);
+  b = fma2(q[3], k1.y, b);
+  return hsum2(add2(a, b));
 }
 
 // NV > 0: compile-time number of views (scores kept in registers, single QK pass); NV == 0: runtime N.
@@ -29,7 +32,7 @@ template <int NV>
 __global__ void __launch_bounds__(kThreads2, 2)
 k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __restrict__ wqk,
       const uint8_t* __restrict__ wv, const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1,
-      const uint8_t* __restrict__ w2, const float* __restrict__ tab, const float* __restrict__ peqk,
+      const uint8_t* __restrict__ w2, const __grid_constant__ Tab512 tab, const float* __restrict__ peqk,
       const float* __restrict__ pe, int Nrt, int PP, long long npix, int passes) {
   const int N = NV > 0 ? NV : Nrt;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -138,7 +141,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     {
       const float mr = mean * rstd;
       const float4* pq4 = reinterpret_cast<const float4*>(peqk) + aa;  // [chunk 32][N][4]: Q chunks 0..15, K 16..31
-      const float4* tab4 = reinterpret_cast<const float4*>(tab);      // [u_qk 128 | c_qk 128 | u_1 128 | c_1 128]
+      const float4* tab4 = reinterpret_cast<const float4*>(tab.v);    // [u_qk 128 | c_qk 128 | u_1 128 | c_1 128] (constant bank)
       float kv[16];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {  // K columns 64 + 32q + 16c
@@ -147,7 +150,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
-          const float4 uv = __ldg(tab4 + col / 4 + j), cv = __ldg(tab4 + 32 + col / 4 + j);
+          const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
           kv[4 * j] = fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
           kv[4 * j + 1] = fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
           kv[4 * j + 2] = fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
@@ -171,61 +174,67 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       tmem_ld16_nowait(trow + 32 * q + 16, qv + 16);
       tmem_wait_ld();
       const float scale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e)/sqrt(8), folded into Q (softmax via exp2)
+      f32x2 q2[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 pv = __ldg(pq4 + (8 * q + j) * N);
-        const float4 uv = __ldg(tab4 + 8 * q + j), cv = __ldg(tab4 + 32 + 8 * q + j);
-        qv[4 * j] = scale * fmaf(rstd, qv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
-        qv[4 * j + 1] = scale * fmaf(rstd, qv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
-        qv[4 * j + 2] = scale * fmaf(rstd, qv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
-        qv[4 * j + 3] = scale * fmaf(rstd, qv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+        const float4 uv = tab4[8 * q + j], cv = tab4[32 + 8 * q + j];
+        q2[2 * j] = pack2(scale * fmaf(rstd, qv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x)),
+                          scale * fmaf(rstd, qv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y)));
+        q2[2 * j + 1] = pack2(scale * fmaf(rstd, qv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z)),
+                              scale * fmaf(rstd, qv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w)));
       }
       rows_bar_sync256();
       float o[32];
 #pragma unroll
       for (int hh = 0; hh < 4; ++hh) {
-        float acc[8];
+        f32x2 acc[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int e = 0; e < 4; ++e) acc[e] = 0ull;
         float l = 1.f;
         if (pl < PPT) {
-          const float4* kb = reinterpret_cast<const float4*>(ks_ptr + (4 * q + hh) * 4096 + pl * N * 32);
-          const float4* vb = reinterpret_cast<const float4*>(vs_ptr + (4 * q + hh) * 4096 + pl * N * 32);
+          const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(ks_ptr + (4 * q + hh) * 4096 + pl * N * 32);
+          const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(vs_ptr + (4 * q + hh) * 4096 + pl * N * 32);
           float mx = -INFINITY;
           l = 0.f;
           if constexpr (NV > 0 && NV <= 32) {
             float sc[NV];
 #pragma unroll
             for (int t = 0; t < NV; ++t) {
-              sc[t] = dot8(qv + 8 * hh, kb[2 * t], kb[2 * t + 1]);
+              sc[t] = dot8(q2 + 4 * hh, kb[2 * t], kb[2 * t + 1]);
               mx = fmaxf(mx, sc[t]);
             }
 #pragma unroll
             for (int t = 0; t < NV; ++t) {
               const float pw = fast_exp2(sc[t] - mx);
               l += pw;
-              const float4 v0 = vb[2 * t], v1 = vb[2 * t + 1];
-              acc[0] = fmaf(pw, v0.x, acc[0]); acc[1] = fmaf(pw, v0.y, acc[1]); acc[2] = fmaf(pw, v0.z, acc[2]);
-              acc[3] = fmaf(pw, v0.w, acc[3]); acc[4] = fmaf(pw, v1.x, acc[4]); acc[5] = fmaf(pw, v1.y, acc[5]);
-              acc[6] = fmaf(pw, v1.z, acc[6]); acc[7] = fmaf(pw, v1.w, acc[7]);
+              const f32x2 pp = pack2(pw, pw);
+              const ulonglong2 v0 = vb[2 * t], v1 = vb[2 * t + 1];
+              acc[0] = fma2(pp, v0.x, acc[0]); acc[1] = fma2(pp, v0.y, acc[1]);
+              acc[2] = fma2(pp, v1.x, acc[2]); acc[3] = fma2(pp, v1.y, acc[3]);
             }
           } else {
 #pragma unroll 4
-            for (int t = 0; t < N; ++t) mx = fmaxf(mx, dot8(qv + 8 * hh, kb[2 * t], kb[2 * t + 1]));
+            for (int t = 0; t < N; ++t) mx = fmaxf(mx, dot8(q2 + 4 * hh, kb[2 * t], kb[2 * t + 1]));
 #pragma unroll 4
             for (int t = 0; t < N; ++t) {
-              const float pw = fast_exp2(dot8(qv + 8 * hh, kb[2 * t], kb[2 * t + 1]) - mx);
+              const float pw = fast_exp2(dot8(q2 + 4 * hh, kb[2 * t], kb[2 * t + 1]) - mx);
               l += pw;
-              const float4 v0 = vb[2 * t], v1 = vb[2 * t + 1];
-              acc[0] = fmaf(pw, v0.x, acc[0]); acc[1] = fmaf(pw, v0.y, acc[1]); acc[2] = fmaf(pw, v0.z, acc[2]);
-              acc[3] = fmaf(pw, v0.w, acc[3]); acc[4] = fmaf(pw, v1.x, acc[4]); acc[5] = fmaf(pw, v1.y, acc[5]);
-              acc[6] = fmaf(pw, v1.z, acc[6]); acc[7] = fmaf(pw, v1.w, acc[7]);
+              const f32x2 pp = pack2(pw, pw);
+              const ulonglong2 v0 = vb[2 * t], v1 = vb[2 * t + 1];
+              acc[0] = fma2(pp, v0.x, acc[0]); acc[1] = fma2(pp, v0.y, acc[1]);
+              acc[2] = fma2(pp, v1.x, acc[2]); acc[3] = fma2(pp, v1.y, acc[3]);
             }
           }
         }
         const float inv = 1.f / l;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[8 * hh + e] = acc[e] * inv;
+        for (int e = 0; e < 4; ++e) {
+          float a, b;
+          unpack2(acc[e], a, b);
+          o[8 * hh + 2 * e] = a * inv;
+          o[8 * hh + 2 * e + 1] = b * inv;
+        }
       }
       rows_bar_sync256();  // everyone is done reading K/V: R1 can take the O operand
 #pragma unroll
@@ -279,8 +288,8 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
         tmem_ld16(trow + col, d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 uv = __ldg(reinterpret_cast<const float4*>(tab + 256 + col) + j);
-          const float4 cv = __ldg(reinterpret_cast<const float4*>(tab + 384 + col) + j);
+          const float4 uv = reinterpret_cast<const float4*>(tab.v + 256 + col)[j];
+          const float4 cv = reinterpret_cast<const float4*>(tab.v + 384 + col)[j];
           d[4 * j] = fmaxf(fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x)), 0.f);
           d[4 * j + 1] = fmaxf(fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y)), 0.f);
           d[4 * j + 2] = fmaxf(fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
@@ -335,9 +344,11 @@ int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cud
   const int PPT = 128 / N;
   const unsigned grid = (unsigned)((npix + PPT - 1) / PPT);
   const Layer& L = h->layer[layer];
+  Tab512 ta;
+  memcpy(ta.v, L.a_tab.data(), sizeof(ta.v));
   Scope sc(h, K_ANG, st);
 #define LFT_ANG_LAUNCH(NV)                                                                                          \
-  k_ang<NV><<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, L.a_tab, L.a_peqk, \
+  k_ang<NV><<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, ta, L.a_peqk, \
                                                h->pe_ang, N, P * P, npix, h->passes())
   if (N == 25) LFT_ANG_LAUNCH(25);
   else if (N == 9) LFT_ANG_LAUNCH(9);

@@ -15,6 +15,8 @@
 #include "host.h"
 #include "kernels.cuh"
 
+#include <cstring>
+
 namespace lft {
 
 constexpr int kSpaNST = 3;
@@ -48,7 +50,7 @@ LFT_DEVINL void a_store16(uint32_t A, int kc0, int m, const float* x) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads2, 2)
 k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp, const float* __restrict__ pe,
-                const float* __restrict__ pev, const float* __restrict__ tab, const uint8_t* __restrict__ wq,
+                const float* __restrict__ pev, const __grid_constant__ Tab512 tab, const uint8_t* __restrict__ wq,
                 const uint8_t* __restrict__ wk, const uint8_t* __restrict__ wv, float* __restrict__ tok,
                 float* __restrict__ Q, float* __restrict__ K, float* __restrict__ Vv, int V, int P, int passes) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -154,7 +156,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     mbar_arrive(a_ready);
 
     // ---- phase 2: Q, K epilogues (affine LN correction), V MMAs start as soon as Q has been read
-    const float4* tab4 = reinterpret_cast<const float4*>(tab);  // [u_q | u_k | c_q | c_k] x 128
+    const float4* tab4 = reinterpret_cast<const float4*>(tab.v);  // [u_q | u_k | c_q | c_k] x 128 (constant bank)
     const float mr = mean * rstd;
     mbar_wait(mma_done, 1);
     tc_fence_after();
@@ -165,7 +167,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       tmem_ld16(trow + col, d);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 uv = __ldg(tab4 + col / 4 + j), cv = __ldg(tab4 + 64 + col / 4 + j);
+        const float4 uv = tab4[col / 4 + j], cv = tab4[64 + col / 4 + j];
         d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
         d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
         d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
@@ -182,7 +184,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       tmem_ld16(trow + 128 + col, d);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 uv = __ldg(tab4 + 32 + col / 4 + j), cv = __ldg(tab4 + 96 + col / 4 + j);
+        const float4 uv = tab4[32 + col / 4 + j], cv = tab4[96 + col / 4 + j];
         d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
         d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
         d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
@@ -217,18 +219,19 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
 // ------------------------------------------------------------------------------------------------
 // Window attention. One thread = one head of TWO vertically adjacent queries (y0, x), (y0+1, x): the
 // 6 x 5 keys their windows cover are read once (30 instead of 50 key reads).
-LFT_DEVINL float dot16(const float* q, const float4& a, const float4& b, const float4& c, const float4& d) {
-  float s0 = q[0] * a.x, s1 = q[4] * b.x, s2 = q[8] * c.x, s3 = q[12] * d.x;
-  s0 = fmaf(q[1], a.y, s0); s1 = fmaf(q[5], b.y, s1); s2 = fmaf(q[9], c.y, s2); s3 = fmaf(q[13], d.y, s3);
-  s0 = fmaf(q[2], a.z, s0); s1 = fmaf(q[6], b.z, s1); s2 = fmaf(q[10], c.z, s2); s3 = fmaf(q[14], d.z, s3);
-  s0 = fmaf(q[3], a.w, s0); s1 = fmaf(q[7], b.w, s1); s2 = fmaf(q[11], c.w, s2); s3 = fmaf(q[15], d.w, s3);
-  return (s0 + s1) + (s2 + s3);
+LFT_DEVINL float dot16(const f32x2* q, const ulonglong2& a, const ulonglong2& b, const ulonglong2& c,
+                        const ulonglong2& d) {
+  f32x2 s0 = mul2(q[0], a.x), s1 = mul2(q[1], a.y);
+  s0 = fma2(q[2], b.x, s0); s1 = fma2(q[3], b.y, s1);
+  s0 = fma2(q[4], c.x, s0); s1 = fma2(q[5], c.y, s1);
+  s0 = fma2(q[6], d.x, s0); s1 = fma2(q[7], d.y, s1);
+  return hsum2(add2(s0, s1));
 }
-LFT_DEVINL void axpy16(float* o, float p, const float4& a, const float4& b, const float4& c, const float4& d) {
-  o[0] = fmaf(p, a.x, o[0]); o[1] = fmaf(p, a.y, o[1]); o[2] = fmaf(p, a.z, o[2]); o[3] = fmaf(p, a.w, o[3]);
-  o[4] = fmaf(p, b.x, o[4]); o[5] = fmaf(p, b.y, o[5]); o[6] = fmaf(p, b.z, o[6]); o[7] = fmaf(p, b.w, o[7]);
-  o[8] = fmaf(p, c.x, o[8]); o[9] = fmaf(p, c.y, o[9]); o[10] = fmaf(p, c.z, o[10]); o[11] = fmaf(p, c.w, o[11]);
-  o[12] = fmaf(p, d.x, o[12]); o[13] = fmaf(p, d.y, o[13]); o[14] = fmaf(p, d.z, o[14]); o[15] = fmaf(p, d.w, o[15]);
+LFT_DEVINL void axpy16(f32x2* o, float p, const ulonglong2& a, const ulonglong2& b, const ulonglong2& c,
+                       const ulonglong2& d) {
+  const f32x2 pp = pack2(p, p);
+  o[0] = fma2(pp, a.x, o[0]); o[1] = fma2(pp, a.y, o[1]); o[2] = fma2(pp, b.x, o[2]); o[3] = fma2(pp, b.y, o[3]);
+  o[4] = fma2(pp, c.x, o[4]); o[5] = fma2(pp, c.y, o[5]); o[6] = fma2(pp, d.x, o[6]); o[7] = fma2(pp, d.y, o[7]);
 }
 
 // CTA = (view, head, block of kAttnRB query rows): the K and V planes of rows [r0-2, r0+RB+2) are contiguous
@@ -272,20 +275,22 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
   const int jstride = P * 4;                      // floats between the 4 pieces of one (y, x)
   const long long base = planar_off(v, head, 0, 0, x, P);
   const float qs = 0.25f * 1.4426950408889634f;   // log2(e)/sqrt(16): softmax through exp2
-  float q0[16], q1[16];
+  f32x2 q0[8], q1[8];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float4 f = active ? __ldg(reinterpret_cast<const float4*>(Q + base + y0 * rowstride + j * jstride))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
-    q0[4 * j] = f.x * qs; q0[4 * j + 1] = f.y * qs; q0[4 * j + 2] = f.z * qs; q0[4 * j + 3] = f.w * qs;
+    q0[2 * j] = pack2(f.x * qs, f.y * qs);
+    q0[2 * j + 1] = pack2(f.z * qs, f.w * qs);
     const float4 g = two ? __ldg(reinterpret_cast<const float4*>(Q + base + (y0 + 1) * rowstride + j * jstride))
                          : make_float4(0.f, 0.f, 0.f, 0.f);
-    q1[4 * j] = g.x * qs; q1[4 * j + 1] = g.y * qs; q1[4 * j + 2] = g.z * qs; q1[4 * j + 3] = g.w * qs;
+    q1[2 * j] = pack2(g.x * qs, g.y * qs);
+    q1[2 * j + 1] = pack2(g.z * qs, g.w * qs);
   }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  float o0[16], o1[16];
+  f32x2 o0[8], o1[8];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) { o0[e] = 0.f; o1[e] = 0.f; }
+  for (int e = 0; e < 8; ++e) { o0[e] = 0ull; o1[e] = 0ull; }
   mbar_wait(bar, 0);
   if (active) {
 #pragma unroll
@@ -302,10 +307,10 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
         a0[dx + 2] = -INFINITY;
         a1[dx + 2] = -INFINITY;
         if (kx >= 0 && kx < P) {
-          const float4 k0 = *reinterpret_cast<const float4*>(krow + dx * 4);
-          const float4 k1 = *reinterpret_cast<const float4*>(krow + dx * 4 + jstride);
-          const float4 k2 = *reinterpret_cast<const float4*>(krow + dx * 4 + 2 * jstride);
-          const float4 k3 = *reinterpret_cast<const float4*>(krow + dx * 4 + 3 * jstride);
+          const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(krow + dx * 4);
+          const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(krow + dx * 4 + jstride);
+          const ulonglong2 k2 = *reinterpret_cast<const ulonglong2*>(krow + dx * 4 + 2 * jstride);
+          const ulonglong2 k3 = *reinterpret_cast<const ulonglong2*>(krow + dx * 4 + 3 * jstride);
           if (kr <= 4) { a0[dx + 2] = dot16(q0, k0, k1, k2, k3); n0 = fmaxf(n0, a0[dx + 2]); }
           if (kr >= 1) { a1[dx + 2] = dot16(q1, k0, k1, k2, k3); n1 = fmaxf(n1, a1[dx + 2]); }
         }
@@ -314,24 +319,26 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
         const float sc = fast_exp2(m0 - n0);
         m0 = n0;
         l0 *= sc;
+        const f32x2 sc2 = pack2(sc, sc);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o0[e] *= sc;
+        for (int e = 0; e < 8; ++e) o0[e] = mul2(o0[e], sc2);
       }
       if (kr >= 1 && two) {
         const float sc = fast_exp2(m1 - n1);
         m1 = n1;
         l1 *= sc;
+        const f32x2 sc2 = pack2(sc, sc);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o1[e] *= sc;
+        for (int e = 0; e < 8; ++e) o1[e] = mul2(o1[e], sc2);
       }
 #pragma unroll
       for (int dx = -2; dx <= 2; ++dx) {
         const int kx = x + dx;
         if (kx >= 0 && kx < P) {
-          const float4 v0 = *reinterpret_cast<const float4*>(vrow + dx * 4);
-          const float4 v1 = *reinterpret_cast<const float4*>(vrow + dx * 4 + jstride);
-          const float4 v2 = *reinterpret_cast<const float4*>(vrow + dx * 4 + 2 * jstride);
-          const float4 v3 = *reinterpret_cast<const float4*>(vrow + dx * 4 + 3 * jstride);
+          const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(vrow + dx * 4);
+          const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(vrow + dx * 4 + jstride);
+          const ulonglong2 v2 = *reinterpret_cast<const ulonglong2*>(vrow + dx * 4 + 2 * jstride);
+          const ulonglong2 v3 = *reinterpret_cast<const ulonglong2*>(vrow + dx * 4 + 3 * jstride);
           if (kr <= 4) {
             const float p0 = fast_exp2(a0[dx + 2] - m0);
             l0 += p0;
@@ -346,23 +353,31 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
       }
     }
     const float i0 = 1.f / l0;
+    const f32x2 i02 = pack2(i0, i0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<float4*>(O + base + y0 * rowstride + j * jstride) =
-          make_float4(o0[4 * j] * i0, o0[4 * j + 1] * i0, o0[4 * j + 2] * i0, o0[4 * j + 3] * i0);
+    for (int j = 0; j < 4; ++j) {
+      ulonglong2 r;
+      r.x = mul2(o0[2 * j], i02);
+      r.y = mul2(o0[2 * j + 1], i02);
+      *reinterpret_cast<ulonglong2*>(O + base + y0 * rowstride + j * jstride) = r;
+    }
     if (two) {
       const float i1 = 1.f / l1;
+      const f32x2 i12 = pack2(i1, i1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float4*>(O + base + (y0 + 1) * rowstride + j * jstride) =
-            make_float4(o1[4 * j] * i1, o1[4 * j + 1] * i1, o1[4 * j + 2] * i1, o1[4 * j + 3] * i1);
+      for (int j = 0; j < 4; ++j) {
+        ulonglong2 r;
+        r.x = mul2(o1[2 * j], i12);
+        r.y = mul2(o1[2 * j + 1], i12);
+        *reinterpret_cast<ulonglong2*>(O + base + (y0 + 1) * rowstride + j * jstride) = r;
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads2, 2)
-k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __restrict__ tab,
+k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_constant__ Tab512 tab,
           const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1a, const uint8_t* __restrict__ w1b,
           const uint8_t* __restrict__ w2a, const uint8_t* __restrict__ w2b, const uint8_t* __restrict__ wlin,
           float* __restrict__ out, const float* __restrict__ final_res, long long T, int P, int passes) {
@@ -373,6 +388,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  LFT_TL(30);
   cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
   const GemmPhase g_o{wo, 128, 2}, g_1a{w1a, 128, 2}, g_2a{w2a, 128, 2}, g_1b{w1b, 128, 2}, g_2b{w2b, 128, 2},
@@ -383,8 +399,8 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
       RingState<kSpaNST> rs;
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_o, passes);
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_1a, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2a, passes);
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_1b, passes);
+      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2a, passes);
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2b, passes);
       ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_l, passes);
     }
@@ -392,59 +408,68 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
     if (lane == 0) {
       RingState<kSpaNST> rs;
       uint32_t par = 0;
-      auto step = [&](const GemmPhase& g, uint32_t dcol, bool fresh) {
+      int tl = 0;
+      auto wait_a = [&]() {
         mbar_wait(a_ready, par);
         par ^= 1;
         tc_fence_after();
+        LFT_TL(tl); ++tl;
+      };
+      auto gemm = [&](const GemmPhase& g, uint32_t dcol, bool fresh) {
         ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
                                   tmem + dcol, fresh);
-        umma_commit(mma_done);
       };
-      step(g_o, 0, true);      // D[0,128)    = O Wo^T
-      step(g_1a, 0, true);     // D[0,128)    = Y1 W'1[0:128]^T
-      step(g_2a, 128, false);  // S[128,256) += relu(.) W2[:,0:128]^T     (S was initialised to Y1)
-      step(g_1b, 0, true);     // D[0,128)    = Y1 W'1[128:256]^T
-      step(g_2b, 128, false);  // S          += relu(.) W2[:,128:256]^T   -> S = Y2
-      step(g_l, 0, true);      // D[0,64)     = Y2 Wlin^T
+      auto done = [&]() { umma_commit(mma_done); LFT_TL(tl); ++tl; };
+      wait_a(); gemm(g_o, 0, true); done();                                  // D[0,128)   = O Wo^T
+      wait_a(); gemm(g_1a, 0, true); gemm(g_1b, 128, true); done();          // D[0,256)   = Y1 W'1^T  (both halves)
+      wait_a(); gemm(g_2a, 0, true); done();                                 // D[0,128)   = relu(.)[:, :128] W2[:, :128]^T
+      wait_a(); gemm(g_2b, 0, false); done();                                // D[0,128)  += relu(.)[:, 128:] W2[:, 128:]^T
+      wait_a(); gemm(g_l, 128, true); done();                                // D[128,192) = Y2 Wlin^T
     }
   } else {
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     const long long t = (long long)blockIdx.x * 128 + m;
     const bool ok = t < T;
-    const long long tt = ok ? t : 0;
-    const int PP = P * P;
-    const long long v = tt / PP;
-    const int p = (int)(tt - v * PP);
+    const unsigned tt = ok ? (unsigned)t : 0u;  // T < 2^31 (checked on the host): 32-bit index math
+    const unsigned PP = (unsigned)(P * P);
+    const unsigned vu = tt / PP;
+    const long long v = vu;
+    const int p = (int)(tt - vu * PP);
     const int y = p / P, x = p - y * P;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* trow_g = tok + t32_off(tt, 16 * q, 32);  // own half of the token row, chunk stride 128 floats (Y1 is spilled here)
     uint32_t par = 0;
+    int tl = 1;
     auto publish = [&]() {
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(a_ready);
+      LFT_TL(tl); ++tl;
     };
     auto await = [&]() {
       mbar_wait(mma_done, par);
       par ^= 1;
       tc_fence_after();
+      LFT_TL(tl); ++tl;
     };
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    LFT_TL(0);
 
     // phase 0: A <- O (planar gather of own heads 4q..4q+3)
     {
       float4 f[16];
+      const float* ob = O + planar_off(v, 4 * q, y, 0, x, P);
+      const long long hs = (long long)PP * 16, js = (long long)P * 4;  // head / piece strides in floats
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          f[4 * c + j] = ok ? __ldg(reinterpret_cast<const float4*>(O + planar_off(v, 4 * q + c, y, j, x, P))) : zero4;
+        for (int j = 0; j < 4; ++j) f[4 * c + j] = ok ? __ldg(reinterpret_cast<const float4*>(ob + c * hs + j * js)) : zero4;
 #pragma unroll
       for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, reinterpret_cast<const float*>(&f[4 * c]));
     }
     publish();
 
-    // phase 1: Y1 = tok + D (own half): -> global (spill), TMEM S, raw A; LN2 statistics
+    // phase 1: Y1 = tok + D (own half) -> global spill + raw A operand; LN2 statistics (folded into FFN1's epilogue)
     float mean, rstd;
     {
       float4 tk[16];
@@ -459,8 +484,6 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
       for (int i = 0; i < 16; ++i) {
         yv[4 * i] += tk[i].x; yv[4 * i + 1] += tk[i].y; yv[4 * i + 2] += tk[i].z; yv[4 * i + 3] += tk[i].w;
       }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_st16(trow + 128 + 64 * q + 16 * c, yv + 16 * c);
       if (ok) {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -472,48 +495,68 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
     }
     publish();
     const float mr = mean * rstd;
+    const float4* u1 = reinterpret_cast<const float4*>(tab.v);        // [u_1 256 | c_1 256] (constant bank)
+    const float4* c1 = reinterpret_cast<const float4*>(tab.v + 256);
 
-    // phases 2..5: hidden halves (LN2 folded: hidden = relu(rstd*D - rstd*mean*u1 + c1))
-    for (int half = 0; half < 2; ++half) {
-      float4 y1[16];
-      if (half == 0) {
+    // phase 2: hidden[:, :128] (own 64 columns of D[0,128)) -> A
+    await();
+#pragma unroll 2
+    for (int c = 0; c < 4; ++c) {
+      float d[16];
+      tmem_ld16(trow + 64 * q + 16 * c, d);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y1[i] = ok ? *reinterpret_cast<const float4*>(trow_g + 128 * i) : zero4;  // prefetch Y1
+      for (int j = 0; j < 4; ++j) {
+        const float4 uv = u1[16 * q + 4 * c + j], cv = c1[16 * q + 4 * c + j];
+        d[4 * j] = fmaxf(fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x)), 0.f);
+        d[4 * j + 1] = fmaxf(fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y)), 0.f);
+        d[4 * j + 2] = fmaxf(fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
+        d[4 * j + 3] = fmaxf(fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w)), 0.f);
       }
-      await();  // FFN1 half done: D[0,128)
-      const float4* u1 = reinterpret_cast<const float4*>(tab + 512 + 128 * half + 64 * q);
-      const float4* c1 = reinterpret_cast<const float4*>(tab + 768 + 128 * half + 64 * q);
-#pragma unroll 1
+      a_store16(A, 8 * q + 2 * c, m, d);
+    }
+    publish();
+
+    // phase 3: hidden[:, 128:] is computed from D[128,256) while the FFN2a MMAs run; stored once A is free
+    {
+      float hb[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 128 + 64 * q + 16 * c, hb + 16 * c);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 uv = u1[32 + 16 * q + j], cv = c1[32 + 16 * q + j];
+        hb[4 * j] = fmaxf(fmaf(rstd, hb[4 * j], fmaf(-mr, uv.x, cv.x)), 0.f);
+        hb[4 * j + 1] = fmaxf(fmaf(rstd, hb[4 * j + 1], fmaf(-mr, uv.y, cv.y)), 0.f);
+        hb[4 * j + 2] = fmaxf(fmaf(rstd, hb[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
+        hb[4 * j + 3] = fmaxf(fmaf(rstd, hb[4 * j + 3], fmaf(-mr, uv.w, cv.w)), 0.f);
+      }
+      await();  // FFN2a done: A is free
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, hb + 16 * c);
+    }
+    publish();
+
+    // phase 4: Y2 = Y1 (spilled row, prefetched) + D[0,128) -> A
+    {
+      float4 y1[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) y1[i] = ok ? *reinterpret_cast<const float4*>(trow_g + 128 * i) : zero4;
+      await();
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
         float d[16];
         tmem_ld16(trow + 64 * q + 16 * c, d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 uv = __ldg(u1 + 4 * c + j), cv = __ldg(c1 + 4 * c + j);
-          d[4 * j] = fmaxf(fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x)), 0.f);
-          d[4 * j + 1] = fmaxf(fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y)), 0.f);
-          d[4 * j + 2] = fmaxf(fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
-          d[4 * j + 3] = fmaxf(fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w)), 0.f);
+          d[4 * j] += y1[4 * c + j].x; d[4 * j + 1] += y1[4 * c + j].y;
+          d[4 * j + 2] += y1[4 * c + j].z; d[4 * j + 3] += y1[4 * c + j].w;
         }
         a_store16(A, 8 * q + 2 * c, m, d);
       }
-      publish();
-      await();  // FFN2 half accumulated into S
-      if (half == 0) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, reinterpret_cast<const float*>(&y1[4 * c]));
-        publish();
-      }
-    }
-    // phase 6: A <- Y2 = S (own half)
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float z[16];
-      tmem_ld16(trow + 128 + 64 * q + 16 * c, z);
-      a_store16(A, 8 * q + 2 * c, m, z);
     }
     publish();
-    // phase 7: out = D[0,64) (+ global residual), own 32 columns
+
+    // phase 5: out = D[128,192) (+ global residual), own 32 columns
     float4 r4[8];
     if (final_res) {
 #pragma unroll
@@ -523,8 +566,8 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
     await();
     {
       float d[32];
-      tmem_ld16_nowait(trow + 32 * q, d);
-      tmem_ld16_nowait(trow + 32 * q + 16, d + 16);
+      tmem_ld16_nowait(trow + 128 + 32 * q, d);
+      tmem_ld16_nowait(trow + 128 + 32 * q + 16, d + 16);
       tmem_wait_ld();
       if (ok) {
 #pragma unroll
@@ -538,6 +581,17 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const float* __r
     tc_fence_before();
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
+  LFT_TL(31);
+}
+
+int debug_timeline_spa(long long* out) {
+#ifdef LFT_TIMELINE
+  CUDA_TRY(cudaMemcpyFromSymbol(out, g_tl, sizeof(long long) * 64));
+  return 0;
+#else
+  (void)out;
+  return fail(LFT_ERR_STATE, "library built without -DLFT_TIMELINE");
+#endif
 }
 
 int configure_spa() {
@@ -557,9 +611,11 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
   int rc;
   {
     const long long G = V * (P + 1) * (P + 1);
+    Tab512 tq;
+    memcpy(tq.v, L.s_tab.data(), sizeof(tq.v));  // [u_q | u_k | c_q | c_k]
     Scope sc(h, K_SPA_QKV, st);
     k_spa_embed_qkv<<<(unsigned)((G + 127) / 128), kThreads2, kSmemSpa, st>>>(
-        in, L.s_wmlp, L.s_pe, L.s_pev, L.s_tab, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes());
+        in, L.s_wmlp, L.s_pe, L.s_pev, tq, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes());
     if ((rc = sc.finish())) return rc;
   }
   {
@@ -569,8 +625,10 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     if ((rc = sc.finish())) return rc;
   }
   {
+    Tab512 tf;
+    memcpy(tf.v, L.s_tab.data() + 512, sizeof(tf.v));  // [u_1 256 | c_1 256]
     Scope sc(h, K_SPA_FFN, st);
-    k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, L.s_tab, L.s_wo, L.s_w1a, L.s_w1b,
+    k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
                                                                         L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P,
                                                                         h->passes());
     if ((rc = sc.finish())) return rc;

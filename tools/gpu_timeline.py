@@ -1,0 +1,18 @@
+"""Print the phase timeline (cycles) of the middle CTA of the last k_spa_ffn launch (needs LFT_TIMELINE build)."""
+import ctypes as C, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lft_b200 import capi, synth
+from lft_b200.engine import Engine
+A, s = 5, 4
+eng = Engine(A, s); eng.load_state_dict(synth.synth_state_dict(A, s, 0))
+lr = torch.from_numpy(synth.synth_lr_mosaic(64, A, 32, 32, 0)).cuda()
+for _ in range(2): eng.forward(lr)
+torch.cuda.synchronize()
+buf = (C.c_int64 * 64)()
+capi.check(eng.lib.lft_debug_timeline(buf))
+row = [buf[i] for i in range(32)]; mma = [buf[32 + i] for i in range(32)]
+t0 = min(x for x in row + mma if x > 0)
+print("entry->first mark:", row[0] - row[30], " last row mark -> exit:", row[31] - max(row[:30]), " total:", row[31] - row[30])
+print("row :", [x - t0 for x in row[:30] if x > 0])
+print("mma :", [x - t0 for x in mma if x > 0])
