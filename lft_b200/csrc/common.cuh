@@ -171,7 +171,7 @@ LFT_DEVINL void umma_commit(uint32_t bar) {
 }
 
 // ---------------------------------------------------------------- bf16 split
-// x = hi + lo (+ O(2^-17 |x|)); hi = bf16(x), lo = bf16(x - hi).  3 MMAs (hi*hi, lo*hi, hi*lo)
+// x = hi + lo (+ O(2^-17 |x|)); hi = bf16 truncation of x, lo = bf16_rn(x - hi).  3 MMAs (hi*hi, lo*hi, hi*lo)
 // reproduce an fp32 product to ~2^-16 relative.
 struct bf16x8 { uint4 v; };
 LFT_DEVINL uint32_t pack_bf16(float a, float b) {
@@ -179,17 +179,14 @@ LFT_DEVINL uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 LFT_DEVINL void split8(const float* x, uint4& hi, uint4& lo) {
-  float r[8];
+  // hi = x truncated to its top 16 bits (one PRMT per pair), lo = bf16_rn(x - hi) (exact subtraction):
+  // |x - hi - lo| <= 2^-17 |x|.
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __nv_bfloat16 b = __float2bfloat16_rn(x[i]);
-    r[i] = x[i] - __bfloat162float(b);
-  }
-#pragma unroll
   for (int i = 0; i < 4; ++i) {
-    h[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
-    l[i] = pack_bf16(r[2 * i], r[2 * i + 1]);
+    const uint32_t a = __float_as_uint(x[2 * i]), b = __float_as_uint(x[2 * i + 1]);
+    h[i] = __byte_perm(a, b, 0x7632);
+    l[i] = pack_bf16(x[2 * i] - __uint_as_float(a & 0xffff0000u), x[2 * i + 1] - __uint_as_float(b & 0xffff0000u));
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);

@@ -90,11 +90,12 @@ LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, u
   for (int r = tid; r < kConvRows; r += kRowThreads2) {
     const long long g = g0 - kConvOff + r;
     long long tok = -1;
-    if (g >= 0 && g < G) {
-      const long long v = g / VS;
-      const int qq = (int)(g - v * VS);
+    if (g >= 0 && g < G) {  // G < 2^31 (host-checked): 32-bit index math
+      const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
+      const unsigned v = gu / vsu;
+      const int qq = (int)(gu - v * vsu);
       const int y = qq / P1, x = qq - y * P1;
-      if (y < P && x < P) tok = (v * P + y) * P + x;
+      if (y < P && x < P) tok = (long long)((v * P + y) * P + x);
     }
     float4 f[16];
 #pragma unroll

@@ -97,8 +97,8 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     const bool rowok = (pl < PPT) && (gp < npix);
     long long tok = 0;
     if (rowok) {
-      const long long b = gp / PP;
-      const int p = (int)(gp - b * PP);
+      const unsigned b = (unsigned)gp / (unsigned)PP;  // npix < 2^31
+      const int p = (int)((unsigned)gp - b * (unsigned)PP);
       tok = (b * N + a) * PP + p;
     }
     const int aa = rowok ? a : 0;

@@ -20,10 +20,11 @@ __global__ void __launch_bounds__(256) k_conv0(const float* __restrict__ lr, con
   const long long tok = ((gid >> 9) << 5) + (gid & 31);  // 512 threads per 32-token block
   const int cg = (int)((gid >> 5) & 15);
   if (tok >= T) return;
-  const int x = (int)(tok % P);
-  const int y = (int)((tok / P) % P);
-  const int a = (int)((tok / ((long long)P * P)) % (A * A));
-  const int b = (int)(tok / ((long long)P * P * A * A));
+  const unsigned tu = (unsigned)tok, Pu = (unsigned)P, PPu = Pu * Pu, NAu = (unsigned)(A * A);  // T < 2^31
+  const int x = (int)(tu % Pu);
+  const int y = (int)((tu / Pu) % Pu);
+  const int a = (int)((tu / PPu) % NAu);
+  const int b = (int)(tu / (PPu * NAu));
   const int u = a / A, v = a % A;
   const int W = A * P;
   const float* img = lr + (long long)b * W * W + (long long)(u * P) * W + v * P;
@@ -135,10 +136,11 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
     const long long g = g0 + m;
     long long tok = -1;
     if (g < G) {
-      const long long v = g / VS;
-      const int qq = (int)(g - v * VS);
+      const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
+      const unsigned v = gu / vsu;
+      const int qq = (int)(gu - v * vsu);
       const int y = qq / P1, x = qq - y * P1;
-      if (y < P && x < P) tok = (v * P + y) * P + x;
+      if (y < P && x < P) tok = (long long)((v * P + y) * P + x);
     }
     float4 r4[HC / 4];
     if ((epi & 2) && tok >= 0) {

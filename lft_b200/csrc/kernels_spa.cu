@@ -111,8 +111,9 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     long long v = 0;
     int y = 0, x = 0;
     if (g < G) {
-      v = g / VS;
-      const int qq = (int)(g - v * VS);
+      const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
+      v = gu / vsu;
+      const int qq = (int)(gu - (unsigned)v * vsu);
       y = qq / P1;
       x = qq - y * P1;
       ok = (y < P && x < P);

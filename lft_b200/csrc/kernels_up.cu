@@ -68,9 +68,10 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
     const bool ok = t < T;
     const long long tt = ok ? t : 0;
     const int PP = P * P, N = A * A;
-    const int x = (int)(tt % P), y = (int)((tt / P) % P);
-    const int a = (int)((tt / PP) % N);
-    const long long b = tt / ((long long)PP * N);
+    const unsigned tu = (unsigned)tt;  // T < 2^31
+    const int x = (int)(tu % (unsigned)P), y = (int)((tu / (unsigned)P) % (unsigned)P);
+    const int a = (int)((tu / (unsigned)PP) % (unsigned)N);
+    const long long b = tu / ((unsigned)PP * (unsigned)N);
     const int u = a / A, v = a - u * A;
     const int H = A * P * s;
     const long long Y0 = (long long)(u * P + y) * s, X0 = (long long)(v * P + x) * s;
@@ -161,16 +162,19 @@ k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* _
   const long long total = (long long)B * A * A * cs * cs;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
+  const unsigned gu = (unsigned)gid;  // total < 2^31 (host-checked)
   int b, u, v, yy, xx;
   if (crop) {  // [b][u][v][cy][cx]
-    xx = (int)(gid % cs) + c0;
-    yy = (int)((gid / cs) % cs) + c0;
-    v = (int)((gid / ((long long)cs * cs)) % A);
-    u = (int)((gid / ((long long)cs * cs * A)) % A);
-    b = (int)(gid / ((long long)cs * cs * A * A));
+    const unsigned csu = (unsigned)cs, Au = (unsigned)A;
+    xx = (int)(gu % csu) + c0;
+    yy = (int)((gu / csu) % csu) + c0;
+    v = (int)((gu / (csu * csu)) % Au);
+    u = (int)((gu / (csu * csu * Au)) % Au);
+    b = (int)(gu / (csu * csu * Au * Au));
   } else {     // mosaic order [b][Y][X]
-    const int X = (int)(gid % H), Y = (int)((gid / H) % H);
-    b = (int)(gid / ((long long)H * H));
+    const unsigned Hu = (unsigned)H;
+    const int X = (int)(gu % Hu), Y = (int)((gu / Hu) % Hu);
+    b = (int)(gu / (Hu * Hu));
     u = Y / Ps; yy = Y - u * Ps;
     v = X / Ps; xx = X - v * Ps;
   }

@@ -86,6 +86,14 @@ static int check_ready(Handle* h, int B, int P) {
   return ensure_spa_pe(h, P);
 }
 
+// the stage entry points do not chunk: the whole batch must fit the kernels' 32-bit index spaces
+static int check_stage_size(Handle* h, int B, int P) {
+  const long long A = h->cfg.ang_res, s = h->cfg.scale;
+  if ((long long)B * A * P * s * A * P * s >= (1LL << 30))
+    return fail(LFT_ERR_ARG, "stage entry points support B*(A*P*s)^2 < 2^30; use lft_forward for larger batches");
+  return 0;
+}
+
 extern "C" {
 
 int lft_workspace_bytes(lft_handle* hh, int32_t B, int32_t P, size_t* bytes) {
@@ -102,6 +110,7 @@ int lft_stage_conv_init(lft_handle* hh, const float* lr, float* feat, int32_t B,
   Handle* h = reinterpret_cast<Handle*>(hh);
   int rc = check_ready(h, B, P);
   if (rc) return rc;
+  if ((rc = check_stage_size(h, B, P))) return rc;
   size_t need;
   lft_workspace_bytes(hh, B, P, &need);
   if (ws_bytes < need) return fail(LFT_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
@@ -116,6 +125,7 @@ int lft_stage_ang(lft_handle* hh, int32_t layer, const float* in, float* out, in
   Handle* h = reinterpret_cast<Handle*>(hh);
   int rc = check_ready(h, B, P);
   if (rc) return rc;
+  if ((rc = check_stage_size(h, B, P))) return rc;
   if (layer < 0 || layer >= kLayers) return fail(LFT_ERR_ARG, "layer out of range");
   size_t need;
   lft_workspace_bytes(hh, B, P, &need);
@@ -132,6 +142,7 @@ int lft_stage_spa(lft_handle* hh, int32_t layer, const float* in, float* out, in
   Handle* h = reinterpret_cast<Handle*>(hh);
   int rc = check_ready(h, B, P);
   if (rc) return rc;
+  if ((rc = check_stage_size(h, B, P))) return rc;
   if (layer < 0 || layer >= kLayers) return fail(LFT_ERR_ARG, "layer out of range");
   size_t need;
   lft_workspace_bytes(hh, B, P, &need);
@@ -148,6 +159,7 @@ int lft_stage_upsample(lft_handle* hh, const float* feat, const float* lr, float
   Handle* h = reinterpret_cast<Handle*>(hh);
   int rc = check_ready(h, B, P);
   if (rc) return rc;
+  if ((rc = check_stage_size(h, B, P))) return rc;
   size_t need;
   lft_workspace_bytes(hh, B, P, &need);
   if (ws_bytes < need) return fail(LFT_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
@@ -168,7 +180,11 @@ int lft_forward(lft_handle* hh, const float* lr, float* sr, int32_t B, int32_t P
   per -= 1024;
   if (ws_bytes < per + 1024) return fail(LFT_ERR_WORKSPACE, "workspace too small for one patch: %zu < %zu", ws_bytes, per + 1024);
   const int A = h->cfg.ang_res, s = h->cfg.scale;
-  const long long chunk = (long long)((ws_bytes - 1024) / per);
+  long long chunk = (long long)((ws_bytes - 1024) / per);
+  {  // kernels use 32-bit index math: keep B*(A*P*s)^2 (largest per-chunk index space) below 2^30
+    const long long cap = (1LL << 30) / ((long long)A * P * s * A * P * s);
+    if (chunk > cap) chunk = cap < 1 ? 1 : cap;
+  }
   const size_t lr_stride = (size_t)A * P * A * P, sr_stride = lr_stride * s * s;
   for (long long b0 = 0; b0 < B; b0 += chunk) {
     const int Bc = (int)((B - b0) < chunk ? (B - b0) : chunk);
@@ -228,7 +244,11 @@ int lft_forward_lf(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, i
   per -= 1024;
   if (ws_bytes < per + 1024) return fail(LFT_ERR_WORKSPACE, "workspace too small for one patch: %zu < %zu", ws_bytes, per + 1024);
   const int A = h->cfg.ang_res, s = h->cfg.scale;
-  const long long chunk = (long long)((ws_bytes - 1024) / per);
+  long long chunk = (long long)((ws_bytes - 1024) / per);
+  {
+    const long long cap = (1LL << 30) / ((long long)A * P * s * A * P * s);
+    if (chunk > cap) chunk = cap < 1 ? 1 : cap;
+  }
   const size_t crop_stride = (size_t)A * A * 16 * s * 16 * s;
   for (long long q0 = p0; q0 < p1; q0 += chunk) {
     const int Bc = (int)((p1 - q0) < chunk ? (p1 - q0) : chunk);
