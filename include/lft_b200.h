@@ -115,9 +115,9 @@ int lft_profile_enable(lft_handle* h, int32_t on);
 int lft_profile_read(lft_handle* h, int32_t* n_kinds, const char** names, int64_t* launches, double* total_ms);
 int64_t lft_launch_count(lft_handle* h); /* kernels launched by this handle since creation */
 
-/* Debug: per-phase clock64() marks of the middle CTA of the last k_spa_ffn launch (row warp: out[0..31],
- * MMA thread: out[32..63]); only available in builds with -DLFT_TIMELINE, else LFT_ERR_STATE. */
-int lft_debug_timeline(int64_t* out64);
+/* Debug: per-phase clock64() marks of the middle CTA of the last k_spa_ffn (which=0) / k_ang (which=1) launch
+ * (row warp: out[0..31], MMA thread: out[32..63]); only in builds with -DLFT_TIMELINE, else LFT_ERR_STATE. */
+int lft_debug_timeline(int32_t which, int64_t* out64);
 
 /* Bring-up self test of the tcgen05 GEMM machinery: D[M x N] = A[M x K] * W[N x K]^T (M multiple of 128,
  * K multiple of 64, N multiple of 16 <= 256), host pointers in/out; aux[M x 16] = 2*A[:, :16]+1 via TMEM. */

@@ -91,10 +91,12 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
   } else {
     // ------------------------------------------------------------ row owner: row m, channel half q
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
-    const int PPT = 128 / N;
-    const int pl = m / N, a = m - pl * N;
+    // rows are view-major inside the tile (m = a*PPT + pl): consecutive lanes = consecutive pixels of one view,
+    // so one 16-byte request of a warp touches ~7 cache lines of the T32 layout instead of 25
+    const int PPT = NV > 0 ? 128 / NV : 128 / N;
+    const int a = m / PPT, pl = m - a * PPT;
     const long long gp = (long long)blockIdx.x * PPT + pl;
-    const bool rowok = (pl < PPT) && (gp < npix);
+    const bool rowok = (a < N) && (gp < npix);
     long long tok = 0;
     if (rowok) {
       const unsigned b = (unsigned)gp / (unsigned)PP;  // npix < 2^31
@@ -106,6 +108,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     const int bar_id = 1 + (warp & 3);
     float mean, rstd;
 
+    LFT_TL(0);
     // ---- phase 0: load X (own 32 channels), stash in TMEM, LN1 statistics of X+PE, raw X -> R1
     {
       float x[32];
@@ -135,9 +138,11 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       mbar_arrive(a_ready);
     }
 
+    LFT_TL(1);
     // ---- phase 1: attention. K (affine-corrected) -> R2, V -> R1 (fp32, all 8 heads), Q in registers
     mbar_wait(mma_done, 0);
     tc_fence_after();
+    LFT_TL(2);
     {
       const float mr = mean * rstd;
       const float4* pq4 = reinterpret_cast<const float4*>(peqk) + aa;  // [chunk 32][N][4]: Q chunks 0..15, K 16..31
@@ -157,8 +162,8 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
           kv[4 * j + 3] = fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)  // head-major [head][row][8 floats]: head = 4q + 2c + j/2, half j%2
-          *reinterpret_cast<float4*>(ks_ptr + (4 * q + 2 * c + (j >> 1)) * 4096 + m * 32 + (j & 1) * 16) =
+        for (int j = 0; j < 4; ++j)  // [head][half][row][4 floats]: head = 4q + 2c + j/2, half = j%2 (conflict-free)
+          *reinterpret_cast<float4*>(ks_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + m * 16) =
               make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
       }
 #pragma unroll
@@ -166,7 +171,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
         tmem_ld16(trow + 128 + 32 * q + 16 * c, kv);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(vs_ptr + (4 * q + 2 * c + (j >> 1)) * 4096 + m * 32 + (j & 1) * 16) =
+          *reinterpret_cast<float4*>(vs_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + m * 16) =
               make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
       }
       float qv[32];
@@ -185,6 +190,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
                               scale * fmaf(rstd, qv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w)));
       }
       rows_bar_sync256();
+      LFT_TL(3);
       float o[32];
 #pragma unroll
       for (int hh = 0; hh < 4; ++hh) {
@@ -192,16 +198,19 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[e] = 0ull;
         float l = 1.f;
-        if (pl < PPT) {
-          const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(ks_ptr + (4 * q + hh) * 4096 + pl * N * 32);
-          const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(vs_ptr + (4 * q + hh) * 4096 + pl * N * 32);
+        if (a < N) {
+          // K/V of this pixel: rows m' = t*PPT + pl of the [head][half][row][4 floats] planes; the PPT pixels
+          // a warp touches for one key are 16*PPT contiguous bytes -> one wavefront per load
+          const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(ks_ptr + (4 * q + hh) * 4096) + pl;
+          const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(vs_ptr + (4 * q + hh) * 4096) + pl;
+          const int ts = PPT;
           float mx = -INFINITY;
           l = 0.f;
           if constexpr (NV > 0 && NV <= 32) {
             float sc[NV];
 #pragma unroll
             for (int t = 0; t < NV; ++t) {
-              sc[t] = dot8(q2 + 4 * hh, kb[2 * t], kb[2 * t + 1]);
+              sc[t] = dot8(q2 + 4 * hh, kb[ts * t], kb[ts * t + 128]);
               mx = fmaxf(mx, sc[t]);
             }
 #pragma unroll
@@ -209,19 +218,19 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
               const float pw = fast_exp2(sc[t] - mx);
               l += pw;
               const f32x2 pp = pack2(pw, pw);
-              const ulonglong2 v0 = vb[2 * t], v1 = vb[2 * t + 1];
+              const ulonglong2 v0 = vb[ts * t], v1 = vb[ts * t + 128];
               acc[0] = fma2(pp, v0.x, acc[0]); acc[1] = fma2(pp, v0.y, acc[1]);
               acc[2] = fma2(pp, v1.x, acc[2]); acc[3] = fma2(pp, v1.y, acc[3]);
             }
           } else {
 #pragma unroll 4
-            for (int t = 0; t < N; ++t) mx = fmaxf(mx, dot8(q2 + 4 * hh, kb[2 * t], kb[2 * t + 1]));
+            for (int t = 0; t < N; ++t) mx = fmaxf(mx, dot8(q2 + 4 * hh, kb[ts * t], kb[ts * t + 128]));
 #pragma unroll 4
             for (int t = 0; t < N; ++t) {
-              const float pw = fast_exp2(dot8(q2 + 4 * hh, kb[2 * t], kb[2 * t + 1]) - mx);
+              const float pw = fast_exp2(dot8(q2 + 4 * hh, kb[ts * t], kb[ts * t + 128]) - mx);
               l += pw;
               const f32x2 pp = pack2(pw, pw);
-              const ulonglong2 v0 = vb[2 * t], v1 = vb[2 * t + 1];
+              const ulonglong2 v0 = vb[ts * t], v1 = vb[ts * t + 128];
               acc[0] = fma2(pp, v0.x, acc[0]); acc[1] = fma2(pp, v0.y, acc[1]);
               acc[2] = fma2(pp, v1.x, acc[2]); acc[3] = fma2(pp, v1.y, acc[3]);
             }
@@ -236,6 +245,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
           o[8 * hh + 2 * e + 1] = b * inv;
         }
       }
+      LFT_TL(4);
       rows_bar_sync256();  // everyone is done reading K/V: R1 can take the O operand
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -249,9 +259,11 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       mbar_arrive(a_ready);
     }
 
+    LFT_TL(5);
     // ---- phase 2: X1 = X + O Wo^T (own 32 channels; stash), LN2 statistics, raw X1 -> R1
     mbar_wait(mma_done, 1);
     tc_fence_after();
+    LFT_TL(6);
     {
       float d[32], x[32];
       tmem_ld16_nowait(trow + 32 * q, d);
@@ -276,9 +288,11 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       mbar_arrive(a_ready);
     }
 
+    LFT_TL(7);
     // ---- phase 3: hidden = relu(LN2-folded D[0,128)), own 64 columns -> K=128 operand (hi in R1, lo in R2)
     mbar_wait(mma_done, 0);
     tc_fence_after();
+    LFT_TL(8);
     {
       const float mr = mean * rstd;
 #pragma unroll 1
@@ -308,9 +322,11 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       mbar_arrive(a_ready);
     }
 
+    LFT_TL(9);
     // ---- phase 4: X2 = X1 + D[128,192) -> global (own 32 channels)
     mbar_wait(mma_done, 1);
     tc_fence_after();
+    LFT_TL(10);
     {
       float d[32], x[32];
       tmem_ld16_nowait(trow + 128 + 32 * q, d);
@@ -327,8 +343,19 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       }
     }
     tc_fence_before();
+    LFT_TL(11);
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
+}
+
+int debug_timeline_ang(long long* out) {
+#ifdef LFT_TIMELINE
+  CUDA_TRY(cudaMemcpyFromSymbol(out, g_tl, sizeof(long long) * 64));
+  return 0;
+#else
+  (void)out;
+  return fail(LFT_ERR_STATE, "library built without -DLFT_TIMELINE");
+#endif
 }
 
 int configure_ang() {

@@ -9,10 +9,10 @@ eng = Engine(A, s); eng.load_state_dict(synth.synth_state_dict(A, s, 0))
 lr = torch.from_numpy(synth.synth_lr_mosaic(64, A, 32, 32, 0)).cuda()
 for _ in range(2): eng.forward(lr)
 torch.cuda.synchronize()
-buf = (C.c_int64 * 64)()
-capi.check(eng.lib.lft_debug_timeline(buf))
-row = [buf[i] for i in range(32)]; mma = [buf[32 + i] for i in range(32)]
-t0 = min(x for x in row + mma if x > 0)
-print("entry->first mark:", row[0] - row[30], " last row mark -> exit:", row[31] - max(row[:30]), " total:", row[31] - row[30])
-print("row :", [x - t0 for x in row[:30] if x > 0])
-print("mma :", [x - t0 for x in mma if x > 0])
+for which, name in ((0, "k_spa_ffn"), (1, "k_ang")):
+    buf = (C.c_int64 * 64)()
+    capi.check(eng.lib.lft_debug_timeline(which, buf))
+    row = [buf[i] for i in range(30)]; mma = [buf[32 + i] for i in range(30)]
+    t0 = min(x for x in row + mma if x > 0)
+    print(name, "row :", [x - t0 for x in row if x > 0])
+    print(name, "mma :", [x - t0 for x in mma if x > 0])
