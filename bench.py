@@ -32,13 +32,21 @@ MP_PER_LF = A * A * H0 * S * W0 * S / 1e6          # 6.5536
 TOKENS_PER_LF = PATCHES * A * A * 32 * 32          # 1,638,400
 # algorithmic FLOP per LR token and launch (window attention at its mean 23.16 keys)
 FLOP_PER_TOKEN = {
-    "conv0": 1152, "conv3x3_64": 73728, "conv3x3_128": 147456, "ang_fused": 71936, "spa_qkv": 98304,
+    "conv0": 1152, "conv3x3_64": 73728, "conv3x3_128": 147456, "ang_fused": 71936, "spa_embed_qkv": 147456 + 98304,
     "spa_attn": 11858, "spa_ffn": 180224, "up_gemm": 131072 + 18432, "up_gather": 32 * S * S,
 }
 FLOP_PER_LF = 2411464 * TOKENS_PER_LF              # 3.951 TFLOP
 # algorithmic HBM bytes per token for the bandwidth-bound kernels (fp32 in/out, once each)
 BYTES_PER_TOKEN = {"spa_attn": 4 * 128 * 4, "up_gather": (9 * 16 + 16) * 4, "conv0": 4 + 256}
-TENSOR_KINDS = {"conv3x3_64", "conv3x3_128", "ang_fused", "spa_qkv", "spa_ffn", "up_gemm"}
+TENSOR_KINDS = {"conv3x3_64", "conv3x3_128", "ang_fused", "spa_embed_qkv", "spa_ffn", "up_gemm"}
+
+
+def ncu_traffic(kind):
+    """DRAM bytes per launch of `kind` from the committed ncu --set full capture (profiles/r01_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kind)
+    return None
 
 
 def peaks():
@@ -249,7 +257,8 @@ def main():
             ach = BYTES_PER_TOKEN.get(top, 0) * TOKENS_PER_LF / (avg_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
         roof.update({"kernel": top, "avg_launch_ms": avg_ms, "share_of_step": kinds[top]["ms"] / args.steps / step_kernel_ms,
-                     "traffic": None, "peak_source": pk["src"],
+                     "traffic": ncu_traffic(top), "traffic_unit": "bytes/launch (dram read+write, ncu --set full, profiles/)",
+                     "peak_source": pk["src"],
                      "note": ("fp32 path issues 3 bf16 MMAs per product (hi*hi+lo*hi+hi*lo): attainable frac <= 1/3"
                               if args.precision == "fp32" else "single bf16 MMA per product")})
         whole = FLOP_PER_LF * world * args.steps / (total_ms * 1e-3) / 1e12

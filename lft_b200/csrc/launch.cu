@@ -3,7 +3,7 @@
 
 namespace lft {
 
-const char* const kKindNames[K_COUNT] = {"conv0",    "conv3x3_64", "conv3x3_128", "ang_fused", "spa_qkv",  "spa_attn",
+const char* const kKindNames[K_COUNT] = {"conv0",    "conv3x3_64", "conv3x3_128", "ang_fused", "spa_embed_qkv", "spa_attn",
                                          "spa_ffn",  "up_gemm",    "up_gather",   "lf_divide", "lf_integrate"};
 
 int configure_kernels() {
