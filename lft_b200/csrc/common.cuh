@@ -286,6 +286,28 @@ LFT_DEVINL void ring_consume_mma(RingState<NST>& rs, uint32_t ring_base, uint32_
   }
 }
 
+// One K=64 GEMM step against a B operand that is resident in shared memory (hi at b_hi, lo at b_lo):
+// D[128 x N] = A[128 x 64] * B[N x 64]^T with the usual 1 or 3 passes.
+LFT_DEVINL void mma_resident64(uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t b_hi, uint32_t b_lo, uint32_t N,
+                               uint32_t d_tmem, int passes) {
+  const uint32_t idesc = umma_idesc_bf16(N);
+  const uint32_t b_lbo = N * 16u;
+  const uint32_t a_step = (2u * a_lbo) >> 4, b_step = (2u * b_lbo) >> 4;
+  const uint32_t ah = umma_desc_lo(a_hi, a_lbo), al = umma_desc_lo(a_lo, a_lbo);
+  const uint32_t bh = umma_desc_lo(b_hi, b_lbo), bl = umma_desc_lo(b_lo, b_lbo);
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j)
+    umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(bh + j * b_step), idesc, j ? 1u : 0u);
+  if (passes == 3) {
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j)
+      umma_bf16(d_tmem, umma_desc_from(al + j * a_step), umma_desc_from(bh + j * b_step), idesc, 1u);
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j)
+      umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(bl + j * b_step), idesc, 1u);
+  }
+}
+
 struct NoShift {
   LFT_DEVINL int operator()(uint32_t) const { return 0; }
 };
@@ -325,6 +347,6 @@ LFT_DEVINL float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-LFT_DEVINL float lrelu02(float x) { return x >= 0.f ? x : 0.2f * x; }
+LFT_DEVINL float lrelu02(float x) { return fmaxf(x, 0.2f * x); }  // == x >= 0 ? x : 0.2x
 
 }  // namespace lft

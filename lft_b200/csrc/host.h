@@ -68,7 +68,8 @@ struct Handle {
   const float* w_conv0 = nullptr;
   const uint8_t* w_conv[3] = {nullptr, nullptr, nullptr};
   Layer layer[kLayers];
-  const uint8_t *w_up = nullptr, *w_up3 = nullptr;
+  const uint8_t* w_up = nullptr;
+  std::vector<float> w_up3_host;  // upsampling.3.weight [1][64][3][3] (kernel parameter of k_up_gemm)
   const float* pe_ang = nullptr;
   int pe_P = -1;
   bool profiling = false;

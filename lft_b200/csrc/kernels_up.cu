@@ -10,135 +10,149 @@
 #include "host.h"
 #include "kernels.cuh"
 
+#include <cstring>
+#include <type_traits>
+
 namespace lft {
 
-constexpr int kUpNST = 3;
+constexpr int kUpNST = 4;
 constexpr uint32_t kUpStage = 64 * 128;
-constexpr size_t kSmemUp = kCtlBytes + 65536 + kUpNST * kUpStage;
+constexpr size_t kSmemUp = kCtlBytes + 32768 + kUpNST * kUpStage;
 constexpr uint32_t kLbo64 = 128 * 16;
 
-__global__ void __launch_bounds__(kThreads, 2)
-k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const uint8_t* __restrict__ w3,
+struct W3Tab { float w[10 * 64]; };  // upsampling.3.weight as [tap][c] (constant bank); tap 9 = zero padding
+
+// The 1x1 conv (64 -> 64 s^2, one [64 x 64] GEMM per sub-pixel ij, PixelShuffle order) runs on tcgen05 with a
+// double-buffered TMEM accumulator; the row owners turn accumulator ij into LeakyReLU'd values and contract
+// them with the nine 3x3 taps on CUDA cores (64 -> 9, fp32 FFMA with constant-bank weights) while the tensor
+// core already computes sub-pixel ij+1.  Thread (row, q) reads the whole 64-column row and owns taps
+// 0..4 (q = 0) or 5..8 (q = 1); one completed HR row (s sub-pixels) is stored per tap as one 16-byte vector.
+//   barriers: aux[0] A1 ready (256) | aux[2], aux[3] accumulator full (commit) | a_ready / mma_done are reused as
+//   accumulator-free barriers of buffers 0 / 1 (256 arrivals each).
+__global__ void __launch_bounds__(kThreads2, 2)
+k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const __grid_constant__ W3Tab w3,
           float* __restrict__ Pp, long long T, int A, int P, int s, int passes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t A1 = smem_u32(smem) + kCtlBytes;
-  const uint32_t A2 = A1 + 32768;
-  const uint32_t ring = A2 + 32768;
+  const uint32_t ring = A1 + 32768;
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
-  const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
+  const uint32_t a1_ready = smem_u32(&ctl->aux[0]);
+  const uint32_t d1_full0 = smem_u32(&ctl->aux[2]);  // aux[2], aux[3]
+  const uint32_t d1_free0 = smem_u32(&ctl->aux[1]);  // buffer 0
+  const uint32_t d1_free1 = smem_u32(&ctl->a_ready); // buffer 1
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  cta_setup<kUpNST>(ctl, warp, lane, 128, 128);
+  cta_setup<kUpNST>(ctl, warp, lane, kRowThreads2, 128, kWarpMma2);
+  if (tid == 0) {  // accumulator-full barriers are completed by one tcgen05.commit each
+    mbar_init(d1_full0, 1);
+    mbar_init(d1_full0 + 8, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
   const uint32_t tmem = ctl->tmem;
   const int s2 = s * s;
-  const GemmPhase g3{w3, 16, 1};
 
-  if (warp == kWarpProducer) {
+  if (warp == kWarpProducer2) {
     if (lane == 0) {
       RingState<kUpNST> rs;
       for (int ij = 0; ij < s2; ++ij) {
-        const GemmPhase g1{wup + (size_t)ij * 2 * 64 * 128, 64, 1};
+        const GemmPhase g1{wup + (size_t)ij * 2 * kUpStage, 64, 1};
         ring_produce<kUpNST>(rs, ring, kUpStage, full0, empty0, g1, passes);
-        ring_produce<kUpNST>(rs, ring, kUpStage, full0, empty0, g3, passes);
       }
     }
-  } else if (warp == kWarpMma) {
+  } else if (warp == kWarpMma2) {
     if (lane == 0) {
       RingState<kUpNST> rs;
-      uint32_t par = 0;
-      mbar_wait(a_ready, par);
-      par ^= 1;
+      mbar_wait(a1_ready, 0);
       tc_fence_after();
       for (int ij = 0; ij < s2; ++ij) {
-        const GemmPhase g1{wup + (size_t)ij * 2 * 64 * 128, 64, 1};
+        const int b = ij & 1;
+        if (ij >= 2) {  // accumulator b was drained by the row owners (its (ij/2 - 1)-th release)
+          mbar_wait(b ? d1_free1 : d1_free0, ((ij >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        const GemmPhase g1{wup + (size_t)ij * 2 * kUpStage, 64, 1};
         ring_consume_mma<kUpNST>(rs, ring, kUpStage, full0, empty0, g1, passes, A1, A1 + 16384, kLbo64, 0, NoShift{},
-                                 tmem + 0, true);
-        umma_commit(mma_done);
-        mbar_wait(a_ready, par);
-        par ^= 1;
-        tc_fence_after();
-        ring_consume_mma<kUpNST>(rs, ring, kUpStage, full0, empty0, g3, passes, A2, A2 + 16384, kLbo64, 0, NoShift{},
-                                 tmem + 64 + 16 * (ij % s), true);
-        umma_commit(mma_done);
+                                 tmem + 64u * b, true);
+        umma_commit(d1_full0 + 8u * b);
       }
     }
   } else {
-    const int m = tid;
+    const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     const long long t = (long long)blockIdx.x * 128 + m;
     const bool ok = t < T;
-    const long long tt = ok ? t : 0;
-    const int PP = P * P, N = A * A;
-    const unsigned tu = (unsigned)tt;  // T < 2^31
+    const unsigned tu = ok ? (unsigned)t : 0u;  // T < 2^31
+    const unsigned PP = (unsigned)(P * P), N = (unsigned)(A * A);
     const int x = (int)(tu % (unsigned)P), y = (int)((tu / (unsigned)P) % (unsigned)P);
-    const int a = (int)((tu / (unsigned)PP) % (unsigned)N);
-    const long long b = tu / ((unsigned)PP * (unsigned)N);
+    const int a = (int)((tu / PP) % N);
+    const long long b = tu / (PP * N);
     const int u = a / A, v = a - u * A;
     const int H = A * P * s;
     const long long Y0 = (long long)(u * P + y) * s, X0 = (long long)(v * P + x) * s;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    uint32_t par = 0;
-    {
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    {  // A1 <- feat row (own 32 channels)
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
+      for (int kc = 0; kc < 4; ++kc) {
         float z[8];
-        const float4 f0 = ok ? __ldg(reinterpret_cast<const float4*>(feat + t32_off(tt, 2 * kc, 16))) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 f1 = ok ? __ldg(reinterpret_cast<const float4*>(feat + t32_off(tt, 2 * kc + 1, 16))) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 f0 = ok ? __ldg(reinterpret_cast<const float4*>(feat + t32_off(tu, 8 * q + 2 * kc, 16))) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 f1 = ok ? __ldg(reinterpret_cast<const float4*>(feat + t32_off(tu, 8 * q + 2 * kc + 1, 16))) : make_float4(0.f, 0.f, 0.f, 0.f);
         z[0] = f0.x; z[1] = f0.y; z[2] = f0.z; z[3] = f0.w; z[4] = f1.x; z[5] = f1.y; z[6] = f1.z; z[7] = f1.w;
         uint4 hi, lo;
         split8(z, hi, lo);
-        st_shared_v4(A1 + kc * kLbo64 + m * 16, hi);
-        st_shared_v4(A1 + 16384 + kc * kLbo64 + m * 16, lo);
+        st_shared_v4(A1 + (4 * q + kc) * kLbo64 + m * 16, hi);
+        st_shared_v4(A1 + 16384 + (4 * q + kc) * kLbo64 + m * 16, lo);
       }
       fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(a_ready);
+      mbar_arrive(a1_ready);
     }
+    float pj[4][5];                             // [sub-pixel column j][own tap]
     for (int ij = 0; ij < s2; ++ij) {
-      mbar_wait(mma_done, par);
-      par ^= 1;
+      const int bsel = ij & 1;
+      mbar_wait(d1_full0 + 8u * bsel, (ij >> 1) & 1);
       tc_fence_after();
+      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      // taps are compile-time per branch so the weights are immediate constant-bank operands of the FFMAs
+      auto taps = [&](auto tap0, auto ntaps) {
+        constexpr int T0 = decltype(tap0)::value, NT = decltype(ntaps)::value;
+        float d[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float d[16];
-        tmem_ld16(trow + 16 * c, d);
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * bsel + 16 * c, d + 16 * c);
+        tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) d[i] = lrelu02(d[i]);
+        for (int i = 0; i < 64; ++i) {
+          const float hv = lrelu02(d[i]);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint4 hi, lo;
-          split8(d + 8 * j, hi, lo);
-          st_shared_v4(A2 + (2 * c + j) * kLbo64 + m * 16, hi);
-          st_shared_v4(A2 + 16384 + (2 * c + j) * kLbo64 + m * 16, lo);
+          for (int tp = 0; tp < NT; ++tp) acc[tp] = fmaf(hv, w3.w[(T0 + tp) * 64 + i], acc[tp]);
         }
-      }
-      fence_proxy_async_smem();
+      };
+      if (q == 0) taps(std::integral_constant<int, 0>{}, std::integral_constant<int, 5>{});
+      else taps(std::integral_constant<int, 5>{}, std::integral_constant<int, 4>{});
       tc_fence_before();
-      mbar_arrive(a_ready);
-      mbar_wait(mma_done, par);
-      par ^= 1;
-      tc_fence_after();
-      if ((ij % s) == s - 1) {  // one HR row i = ij / s of this LR pixel is complete: taps x s sub-pixels
+      mbar_arrive(bsel ? d1_free1 : d1_free0);
+      const int j = ij % s;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        if (jj == j) {
+#pragma unroll
+          for (int tp = 0; tp < 5; ++tp) pj[jj][tp] = acc[tp];
+        }
+      if (j == s - 1 && ok) {  // one HR row i = ij / s of this LR pixel is complete
         const int i = ij / s;
-        float pj[4][16];
+        const int ntap = q ? 4 : 5;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < s) tmem_ld16(trow + 64 + 16 * j, pj[j]);
-        if (ok) {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            float* dst = Pp + ((b * 9 + tap) * H + (Y0 + i)) * H + X0;
+        for (int tp = 0; tp < 5; ++tp) {
+          if (tp < ntap) {
+            float* dst = Pp + ((b * 9 + (q ? 5 : 0) + tp) * H + (Y0 + i)) * H + X0;
             if (s == 4)
-              *reinterpret_cast<float4*>(dst) = make_float4(pj[0][tap], pj[1][tap], pj[2][tap], pj[3][tap]);
+              *reinterpret_cast<float4*>(dst) = make_float4(pj[0][tp], pj[1][tp], pj[2][tp], pj[3][tp]);
             else
-              *reinterpret_cast<float2*>(dst) = make_float2(pj[0][tap], pj[1][tap]);
+              *reinterpret_cast<float2*>(dst) = make_float2(pj[0][tp], pj[1][tp]);
           }
         }
-        tc_fence_before();
       }
     }
-    tc_fence_before();
   }
-  cta_teardown(ctl, warp, 128);
+  cta_teardown(ctl, warp, 128, kWarpMma2);
 }
 
 // PyTorch upsample_bicubic2d coefficients (A = -0.75)
@@ -269,9 +283,12 @@ int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float
   const long long T = (long long)B * A * A * P * P;
   int rc;
   {
+    W3Tab w3t;
+    memset(&w3t, 0, sizeof(w3t));
+    for (int tp = 0; tp < 9; ++tp)
+      for (int c = 0; c < 64; ++c) w3t.w[tp * 64 + c] = h->w_up3_host[(size_t)c * 9 + tp];  // [1][64][3][3] -> [tap][c]
     Scope sc(h, K_UP_GEMM, st);
-    k_up_gemm<<<(unsigned)((T + 127) / 128), kThreads, kSmemUp, st>>>(feat, h->w_up, h->w_up3, pp, T, A, P, s,
-                                                                      h->passes());
+    k_up_gemm<<<(unsigned)((T + 127) / 128), kThreads2, kSmemUp, st>>>(feat, h->w_up, w3t, pp, T, A, P, s, h->passes());
     if ((rc = sc.finish())) return rc;
   }
   {
