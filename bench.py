@@ -152,6 +152,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    # keep stdout to the single JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
 
     import torch
     import torch.distributed as dist
