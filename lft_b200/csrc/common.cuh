@@ -48,6 +48,15 @@ LFT_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One elected lane of a fully active warp.  MMA / bulk-copy issue loops run warp-uniformly and predicate only the
+// issuing instruction on this, so descriptors stay in uniform registers (issuing from inside `if (lane == 0)`
+// makes the compiler wrap every tcgen05.mma in a per-lane R2UR "waterfall" loop, ~100 cycles per MMA).
+LFT_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- proxies / fences
 LFT_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 LFT_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -170,6 +179,12 @@ LFT_DEVINL void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// commit issued by the elected lane of a fully active warp (same lane that issued the MMAs)
+LFT_DEVINL void umma_commit_elected(uint32_t bar) {
+  if (elect_one()) umma_commit(bar);
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------- bf16 split
 // x = hi + lo (+ O(2^-17 |x|)); hi = bf16 truncation of x, lo = bf16_rn(x - hi).  3 MMAs (hi*hi, lo*hi, hi*lo)
 // reproduce an fp32 product to ~2^-16 relative.
@@ -215,7 +230,8 @@ struct GemmPhase {
   uint32_t kslabs;    // K / 64
 };
 
-// Producer side of one GEMM phase. `passes` = 3 (fp32 via hi/lo) or 1 (bf16: hi slabs only).
+// Producer side of one GEMM phase (called by ALL lanes of the producer warp). `passes` = 3 (fp32 via hi/lo) or 1
+// (bf16: hi slabs only).
 template <int NST>
 LFT_DEVINL void ring_produce(RingState<NST>& rs, uint32_t ring_base, uint32_t stage_bytes, uint32_t full0,
                              uint32_t empty0, const GemmPhase& g, int passes) {
@@ -224,8 +240,11 @@ LFT_DEVINL void ring_produce(RingState<NST>& rs, uint32_t ring_base, uint32_t st
     const int nparts = passes == 3 ? 2 : 1;
     for (int part = 0; part < nparts; ++part) {
       mbar_wait(empty0 + 8u * rs.stage, rs.phase ^ 1u);
-      mbar_arrive_expect_tx(full0 + 8u * rs.stage, slab);
-      bulk_g2s(ring_base + rs.stage * stage_bytes, g.w + (size_t)(ks * 2 + part) * slab, slab, full0 + 8u * rs.stage);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full0 + 8u * rs.stage, slab);
+        bulk_g2s(ring_base + rs.stage * stage_bytes, g.w + (size_t)(ks * 2 + part) * slab, slab, full0 + 8u * rs.stage);
+      }
+      __syncwarp();
       rs.advance();
     }
   }
@@ -241,6 +260,7 @@ LFT_DEVINL void ring_produce(RingState<NST>& rs, uint32_t ring_base, uint32_t st
 LFT_DEVINL uint64_t umma_desc_from(uint32_t lo32) { return ((uint64_t)0x4008u << 32) | lo32; }  // SBO=128 B, version 1
 LFT_DEVINL uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return (saddr >> 4) | ((lbo_bytes >> 4) << 16); }
 
+// Called by ALL lanes of the MMA warp; one elected lane issues the MMAs and the commits.
 template <int NST, typename ShiftFn>
 LFT_DEVINL void ring_consume_mma(RingState<NST>& rs, uint32_t ring_base, uint32_t stage_bytes, uint32_t full0,
                                  uint32_t empty0, const GemmPhase& g, int passes, uint32_t a_hi, uint32_t a_lo,
@@ -261,26 +281,31 @@ LFT_DEVINL void ring_consume_mma(RingState<NST>& rs, uint32_t ring_base, uint32_
     mbar_wait(full0 + 8u * rs.stage, rs.phase);
     tc_fence_after();
     uint32_t b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
-#pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) {
-      umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), idesc, acc);
-      acc = 1u;
-    }
-    if (passes == 3) {
+    if (elect_one()) {
 #pragma unroll
       for (uint32_t j = 0; j < 4; ++j)
-        umma_bf16(d_tmem, umma_desc_from(al + j * a_step), umma_desc_from(b0 + j * b_step), idesc, 1u);
+        umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), idesc, j ? 1u : acc);
+      if (passes == 3) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16(d_tmem, umma_desc_from(al + j * a_step), umma_desc_from(b0 + j * b_step), idesc, 1u);
+      }
+      umma_commit(empty0 + 8u * rs.stage);
     }
-    umma_commit(empty0 + 8u * rs.stage);
+    __syncwarp();
+    acc = 1u;
     rs.advance();
     if (passes == 3) {  // lo weights: A_hi*W_lo
       mbar_wait(full0 + 8u * rs.stage, rs.phase);
       tc_fence_after();
       b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
+      if (elect_one()) {
 #pragma unroll
-      for (uint32_t j = 0; j < 4; ++j)
-        umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), idesc, 1u);
-      umma_commit(empty0 + 8u * rs.stage);
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), idesc, 1u);
+        umma_commit(empty0 + 8u * rs.stage);
+      }
+      __syncwarp();
       rs.advance();
     }
   }

@@ -54,40 +54,38 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
   const GemmPhase g_qk{wqk, 128, 1}, g_v{wv, 64, 1}, g_o{wo, 64, 1}, g_1{w1, 128, 1}, g_2{w2, 64, 2};
 
   if (warp == kWarpProducer2) {
-    if (lane == 0) {
-      RingState<kAngNST> rs;
-      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_qk, passes);
-      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_v, passes);
-      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes);
-      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes);
-      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes);
-    }
+
+    RingState<kAngNST> rs;
+    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_qk, passes);
+    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_v, passes);
+    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes);
+    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes);
+    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes);
   } else if (warp == kWarpMma2) {
-    if (lane == 0) {
-      RingState<kAngNST> rs;
-      mbar_wait(a_ready, 0);
-      tc_fence_after();
-      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_qk, passes, R1, R1 + 16384, LBO, 0, NoShift{},
-                                tmem + 0, true);
-      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_v, passes, R1, R1 + 16384, LBO, 0, NoShift{},
-                                tmem + 128, true);
-      umma_commit(mma_done);
-      mbar_wait(a_ready, 1);
-      tc_fence_after();
-      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes, R1, R1 + 16384, LBO, 0, NoShift{},
-                                tmem + 0, true);
-      umma_commit(mma_done);
-      mbar_wait(a_ready, 0);
-      tc_fence_after();
-      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes, R1, R1 + 16384, LBO, 0, NoShift{},
-                                tmem + 0, true);
-      umma_commit(mma_done);
-      mbar_wait(a_ready, 1);
-      tc_fence_after();
-      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes, R1, R2, LBO, 8 * LBO, NoShift{},
-                                tmem + 128, true);
-      umma_commit(mma_done);
-    }
+
+    RingState<kAngNST> rs;
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_qk, passes, R1, R1 + 16384, LBO, 0, NoShift{},
+                              tmem + 0, true);
+    ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_v, passes, R1, R1 + 16384, LBO, 0, NoShift{},
+                              tmem + 128, true);
+    umma_commit_elected(mma_done);
+    mbar_wait(a_ready, 1);
+    tc_fence_after();
+    ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes, R1, R1 + 16384, LBO, 0, NoShift{},
+                              tmem + 0, true);
+    umma_commit_elected(mma_done);
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes, R1, R1 + 16384, LBO, 0, NoShift{},
+                              tmem + 0, true);
+    umma_commit_elected(mma_done);
+    mbar_wait(a_ready, 1);
+    tc_fence_after();
+    ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes, R1, R2, LBO, 8 * LBO, NoShift{},
+                              tmem + 128, true);
+    umma_commit_elected(mma_done);
   } else {
     // ------------------------------------------------------------ row owner: row m, channel half q
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;

@@ -110,20 +110,18 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
 
   GemmPhase ph{wp, (uint32_t)N, 9};
   if (warp == kWarpProducer2) {
-    if (lane == 0) {
-      RingState<NST> rs;
-      ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
-    }
+
+    RingState<NST> rs;
+    ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
   } else if (warp == kWarpMma2) {
-    if (lane == 0) {
-      RingState<NST> rs;
-      mbar_wait(a_ready, 0);
-      tc_fence_after();
-      auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
-      ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi + kConvOff * 16, a_lo + kConvOff * 16,
-                            kConvRows * 16, 0, shift, tmem, true);
-      umma_commit(mma_done);
-    }
+
+    RingState<NST> rs;
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
+    ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi + kConvOff * 16, a_lo + kConvOff * 16,
+                          kConvRows * 16, 0, shift, tmem, true);
+    umma_commit_elected(mma_done);
   } else {
     // ---- stage the input window: rows r <-> positions g0 - kConvOff + r, lanes <-> rows
     conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, tid);
@@ -198,41 +196,17 @@ k_gemm_selftest(const float* __restrict__ A, int K, const uint8_t* __restrict__ 
   aux += (size_t)blockIdx.x * 128 * 16;
   GemmPhase ph{wp, (uint32_t)N, (uint32_t)(K / 64)};
   if (warp == kWarpProducer) {
-    if (lane == 0) {
-      RingState<NST> rs;
-      ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
-    }
+
+    RingState<NST> rs;
+    ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
   } else if (warp == kWarpMma) {
-    if (lane == 0) {
-      RingState<NST> rs;
-      mbar_wait(a_ready, 0);
-      tc_fence_after();
-      if (variant == 0) {
-        ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi, a_lo, a_lbo, 8 * a_lbo, NoShift{}, tmem,
-                              true);
-      } else {  // swapped LBO/SBO interpretation
-        const uint32_t idesc = umma_idesc_bf16(N);
-        uint32_t acc = 0;
-        for (uint32_t ks = 0; ks < ph.kslabs; ++ks) {
-          for (int part = 0; part < (passes == 3 ? 2 : 1); ++part) {
-            mbar_wait(full0 + 8u * rs.stage, rs.phase);
-            tc_fence_after();
-            const uint32_t b = ring + rs.stage * STAGE;
-            for (int rep = 0; rep < ((passes == 3 && part == 0) ? 2 : 1); ++rep) {
-              const uint32_t ab = (part == 0 && rep == 1) ? a_lo : a_hi;
-              for (int j = 0; j < 4; ++j) {
-                umma_bf16(tmem, umma_desc(ab + ks * 8 * a_lbo + j * 2 * a_lbo, 128, a_lbo),
-                          umma_desc(b + j * 2 * N * 16, 128, N * 16), idesc, acc);
-                acc = 1;
-              }
-            }
-            umma_commit(empty0 + 8u * rs.stage);
-            rs.advance();
-          }
-        }
-      }
-      umma_commit(mma_done);
-    }
+
+    RingState<NST> rs;
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    (void)variant;  // bring-up aid (swapped LBO/SBO descriptor fields) retired: variant 0 is the verified encoding
+    ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi, a_lo, a_lbo, 8 * a_lbo, NoShift{}, tmem, true);
+    umma_commit_elected(mma_done);
   } else {
     const int m = tid;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);

@@ -15,6 +15,7 @@
 #include "host.h"
 #include "kernels.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace lft {
@@ -71,35 +72,33 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
   const GemmPhase g_c{wmlp, 128, 9}, g_q{wq, 128, 2}, g_k{wk, 128, 2}, g_v{wv, 128, 2};
 
   if (warp == kWarpProducer2) {
-    if (lane == 0) {
-      RingState<kSpaNST> rs;
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes);
-    }
+
+    RingState<kSpaNST> rs;
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes);
   } else if (warp == kWarpMma2) {
-    if (lane == 0) {
-      RingState<kSpaNST> rs;
-      mbar_wait(a_ready, 0);
-      tc_fence_after();
-      auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
-      ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
-                                c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
-      umma_commit(mma_done);
-      mbar_wait(a_ready, 1);
-      tc_fence_after();
-      ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                                tmem + 0, true);
-      ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                                tmem + 128, true);
-      umma_commit(mma_done);
-      mbar_wait(a_ready, 0);
-      tc_fence_after();
-      ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                                tmem + 0, true);
-      umma_commit(mma_done);
-    }
+
+    RingState<kSpaNST> rs;
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
+    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
+                              c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
+    umma_commit_elected(mma_done);
+    mbar_wait(a_ready, 1);
+    tc_fence_after();
+    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
+                              tmem + 0, true);
+    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
+                              tmem + 128, true);
+    umma_commit_elected(mma_done);
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
+                              tmem + 0, true);
+    umma_commit_elected(mma_done);
   } else {
     conv_stage_window(feat, c_hi, c_lo, g0, G, VS, P, tid);
     fence_proxy_async_smem();
@@ -396,37 +395,35 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
       g_l{wlin, 64, 2};
 
   if (warp == kWarpProducer2) {
-    if (lane == 0) {
-      RingState<kSpaNST> rs;
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_o, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_1a, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_1b, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2a, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2b, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_l, passes);
-    }
+
+    RingState<kSpaNST> rs;
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_o, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_1a, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_1b, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2a, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2b, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_l, passes);
   } else if (warp == kWarpMma2) {
-    if (lane == 0) {
-      RingState<kSpaNST> rs;
-      uint32_t par = 0;
-      int tl = 0;
-      auto wait_a = [&]() {
-        mbar_wait(a_ready, par);
-        par ^= 1;
-        tc_fence_after();
-        LFT_TL(tl); ++tl;
-      };
-      auto gemm = [&](const GemmPhase& g, uint32_t dcol, bool fresh) {
-        ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                                  tmem + dcol, fresh);
-      };
-      auto done = [&]() { umma_commit(mma_done); LFT_TL(tl); ++tl; };
-      wait_a(); gemm(g_o, 0, true); done();                                  // D[0,128)   = O Wo^T
-      wait_a(); gemm(g_1a, 0, true); gemm(g_1b, 128, true); done();          // D[0,256)   = Y1 W'1^T  (both halves)
-      wait_a(); gemm(g_2a, 0, true); done();                                 // D[0,128)   = relu(.)[:, :128] W2[:, :128]^T
-      wait_a(); gemm(g_2b, 0, false); done();                                // D[0,128)  += relu(.)[:, 128:] W2[:, 128:]^T
-      wait_a(); gemm(g_l, 128, true); done();                                // D[128,192) = Y2 Wlin^T
-    }
+
+    RingState<kSpaNST> rs;
+    uint32_t par = 0;
+    int tl = 0;
+    auto wait_a = [&]() {
+      mbar_wait(a_ready, par);
+      par ^= 1;
+      tc_fence_after();
+      LFT_TL(tl); ++tl;
+    };
+    auto gemm = [&](const GemmPhase& g, uint32_t dcol, bool fresh) {
+      ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
+                                tmem + dcol, fresh);
+    };
+    auto done = [&]() { umma_commit_elected(mma_done); LFT_TL(tl); ++tl; };
+    wait_a(); gemm(g_o, 0, true); done();                                  // D[0,128)   = O Wo^T
+    wait_a(); gemm(g_1a, 0, true); gemm(g_1b, 128, true); done();          // D[0,256)   = Y1 W'1^T  (both halves)
+    wait_a(); gemm(g_2a, 0, true); done();                                 // D[0,128)   = relu(.)[:, :128] W2[:, :128]^T
+    wait_a(); gemm(g_2b, 0, false); done();                                // D[0,128)  += relu(.)[:, 128:] W2[:, 128:]^T
+    wait_a(); gemm(g_l, 128, true); done();                                // D[128,192) = Y2 Wlin^T
   } else {
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     const long long t = (long long)blockIdx.x * 128 + m;
@@ -597,7 +594,7 @@ int debug_timeline_spa(long long* out) {
 
 int configure_spa() {
   CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
-  CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa + 16384));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAttn));
   return 0;
 }
@@ -629,7 +626,8 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     Tab512 tf;
     memcpy(tf.v, L.s_tab.data() + 512, sizeof(tf.v));  // [u_1 256 | c_1 256]
     Scope sc(h, K_SPA_FFN, st);
-    k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
+    static const size_t extra = getenv("LFT_FFN_1CTA") ? 16384 : 0;  // experiment: force 1 CTA/SM
+    k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa + extra, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
                                                                         L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P,
                                                                         h->passes());
     if ((rc = sc.finish())) return rc;

@@ -53,29 +53,27 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
   const int s2 = s * s;
 
   if (warp == kWarpProducer2) {
-    if (lane == 0) {
-      RingState<kUpNST> rs;
-      for (int ij = 0; ij < s2; ++ij) {
-        const GemmPhase g1{wup + (size_t)ij * 2 * kUpStage, 64, 1};
-        ring_produce<kUpNST>(rs, ring, kUpStage, full0, empty0, g1, passes);
-      }
+
+    RingState<kUpNST> rs;
+    for (int ij = 0; ij < s2; ++ij) {
+      const GemmPhase g1{wup + (size_t)ij * 2 * kUpStage, 64, 1};
+      ring_produce<kUpNST>(rs, ring, kUpStage, full0, empty0, g1, passes);
     }
   } else if (warp == kWarpMma2) {
-    if (lane == 0) {
-      RingState<kUpNST> rs;
-      mbar_wait(a1_ready, 0);
-      tc_fence_after();
-      for (int ij = 0; ij < s2; ++ij) {
-        const int b = ij & 1;
-        if (ij >= 2) {  // accumulator b was drained by the row owners (its (ij/2 - 1)-th release)
-          mbar_wait(b ? d1_free1 : d1_free0, ((ij >> 1) - 1) & 1);
-          tc_fence_after();
-        }
-        const GemmPhase g1{wup + (size_t)ij * 2 * kUpStage, 64, 1};
-        ring_consume_mma<kUpNST>(rs, ring, kUpStage, full0, empty0, g1, passes, A1, A1 + 16384, kLbo64, 0, NoShift{},
-                                 tmem + 64u * b, true);
-        umma_commit(d1_full0 + 8u * b);
+
+    RingState<kUpNST> rs;
+    mbar_wait(a1_ready, 0);
+    tc_fence_after();
+    for (int ij = 0; ij < s2; ++ij) {
+      const int b = ij & 1;
+      if (ij >= 2) {  // accumulator b was drained by the row owners (its (ij/2 - 1)-th release)
+        mbar_wait(b ? d1_free1 : d1_free0, ((ij >> 1) - 1) & 1);
+        tc_fence_after();
       }
+      const GemmPhase g1{wup + (size_t)ij * 2 * kUpStage, 64, 1};
+      ring_consume_mma<kUpNST>(rs, ring, kUpStage, full0, empty0, g1, passes, A1, A1 + 16384, kLbo64, 0, NoShift{},
+                               tmem + 64u * b, true);
+      umma_commit_elected(d1_full0 + 8u * b);
     }
   } else {
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
