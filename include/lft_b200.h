@@ -115,7 +115,7 @@ int lft_profile_enable(lft_handle* h, int32_t on);
 int lft_profile_read(lft_handle* h, int32_t* n_kinds, const char** names, int64_t* launches, double* total_ms);
 int64_t lft_launch_count(lft_handle* h); /* kernels launched by this handle since creation */
 
-/* Debug: per-phase clock64() marks of the middle CTA of the last k_spa_ffn (which=0) / k_ang (which=1) launch
+/* Debug: per-phase clock64() marks of the middle CTA of the last k_spa_ffn (which=0) / k_ang (1) / k_spa_embed_qkv (2) launch
  * (row warp: out[0..31], MMA thread: out[32..63]); only in builds with -DLFT_TIMELINE, else LFT_ERR_STATE. */
 int lft_debug_timeline(int32_t which, int64_t* out64);
 

@@ -71,8 +71,15 @@ static __device__ long long g_tl[2][32];
     if (blockIdx.x == gridDim.x / 2 && (threadIdx.x == 0 || threadIdx.x == 32 * kWarpMma2))          \
       g_tl[threadIdx.x == 0 ? 0 : 1][s] = clock64();                                                \
   } while (0)
+static __device__ long long g_tl2[2][32];
+#define LFT_TL2(s)                                                                                  \
+  do {                                                                                              \
+    if (blockIdx.x == gridDim.x / 2 && (threadIdx.x == 0 || threadIdx.x == 32 * kWarpMma2))          \
+      g_tl2[threadIdx.x == 0 ? 0 : 1][s] = clock64();                                               \
+  } while (0)
 #else
 #define LFT_TL(s) do {} while (0)
+#define LFT_TL2(s) do {} while (0)
 #endif
 
 // "T32" activation layout for [T, C] fp32 tensors: blocks of 32 consecutive tokens, inside a block the

@@ -100,9 +100,11 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
                               tmem + 0, true);
     umma_commit_elected(mma_done);
   } else {
+    LFT_TL2(0);
     conv_stage_window(feat, c_hi, c_lo, g0, G, VS, P, tid);
     fence_proxy_async_smem();
     mbar_arrive(a_ready);
+    LFT_TL2(1);
 
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     const long long g = g0 + m;
@@ -135,6 +137,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       }
       mbar_wait(mma_done, 0);
       tc_fence_after();
+      LFT_TL2(2);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float t[16];
@@ -154,12 +157,14 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(a_ready);
+    LFT_TL2(3);
 
     // ---- phase 2: Q, K epilogues (affine LN correction), V MMAs start as soon as Q has been read
     const float4* tab4 = reinterpret_cast<const float4*>(tab.v);  // [u_q | u_k | c_q | c_k] x 128 (constant bank)
     const float mr = mean * rstd;
     mbar_wait(mma_done, 1);
     tc_fence_after();
+    LFT_TL2(4);
 #pragma unroll 2
     for (int c = 0; c < 4; ++c) {
       float d[16];
@@ -177,6 +182,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     }
     tc_fence_before();
     mbar_arrive(a_ready);
+    LFT_TL2(5);
 #pragma unroll 2
     for (int c = 0; c < 4; ++c) {
       float d[16];
@@ -197,8 +203,10 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       float4 pv[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) pv[i] = __ldg(reinterpret_cast<const float4*>(pev) + (long long)(16 * q + i) * PP + p);
+      LFT_TL2(6);
       mbar_wait(mma_done, 0);
       tc_fence_after();
+      LFT_TL2(7);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float d[16];
@@ -211,6 +219,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
         if (ok) planar_store16(Vv, v, 4 * q + c, y, x, P, d);
       }
     }
+    LFT_TL2(8);
     tc_fence_before();
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
@@ -580,6 +589,16 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
   LFT_TL(31);
+}
+
+int debug_timeline_embed(long long* out) {
+#ifdef LFT_TIMELINE
+  CUDA_TRY(cudaMemcpyFromSymbol(out, g_tl2, sizeof(long long) * 64));
+  return 0;
+#else
+  (void)out;
+  return fail(LFT_ERR_STATE, "library built without -DLFT_TIMELINE");
+#endif
 }
 
 int debug_timeline_spa(long long* out) {

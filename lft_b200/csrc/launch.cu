@@ -262,8 +262,8 @@ int lft_forward_lf(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, i
 }
 
 int lft_debug_timeline(int32_t which, int64_t* out64) {
-  return which == 0 ? debug_timeline_spa(reinterpret_cast<long long*>(out64))
-                    : debug_timeline_ang(reinterpret_cast<long long*>(out64));
+  long long* o = reinterpret_cast<long long*>(out64);
+  return which == 0 ? debug_timeline_spa(o) : (which == 1 ? debug_timeline_ang(o) : debug_timeline_embed(o));
 }
 
 int lft_gemm_selftest(const float* A, const float* W, float* D, float* aux, int32_t M, int32_t N, int32_t K,

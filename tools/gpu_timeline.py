@@ -9,7 +9,7 @@ eng = Engine(A, s); eng.load_state_dict(synth.synth_state_dict(A, s, 0))
 lr = torch.from_numpy(synth.synth_lr_mosaic(64, A, 32, 32, 0)).cuda()
 for _ in range(2): eng.forward(lr)
 torch.cuda.synchronize()
-for which, name in ((0, "k_spa_ffn"), (1, "k_ang")):
+for which, name in ((0, "k_spa_ffn"), (1, "k_ang"), (2, "k_spa_embed_qkv")):
     buf = (C.c_int64 * 64)()
     capi.check(eng.lib.lft_debug_timeline(which, buf))
     row = [buf[i] for i in range(30)]; mma = [buf[32 + i] for i in range(30)]
