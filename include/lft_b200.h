@@ -120,7 +120,8 @@ int64_t lft_launch_count(lft_handle* h); /* kernels launched by this handle sinc
 int lft_debug_timeline(int32_t which, int64_t* out64);
 
 /* Bring-up self test of the tcgen05 GEMM machinery: D[M x N] = A[M x K] * W[N x K]^T (M multiple of 128,
- * K multiple of 64, N multiple of 16 <= 256), host pointers in/out; aux[M x 16] = 2*A[:, :16]+1 via TMEM. */
+ * K multiple of 64, N multiple of 16 <= 256), host pointers in/out; aux[M x 16] = 2*A[:, :16]+1 via TMEM.
+ * variant 0: both operands from shared memory (SS, what the kernels use); variant 2: A operand from tensor memory (TS). */
 int lft_gemm_selftest(const float* A, const float* W, float* D, float* aux, int32_t M, int32_t N, int32_t K,
                       int32_t precision, int32_t variant);
 

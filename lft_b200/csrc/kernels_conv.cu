@@ -204,8 +204,44 @@ k_gemm_selftest(const float* __restrict__ A, int K, const uint8_t* __restrict__ 
     RingState<NST> rs;
     mbar_wait(a_ready, 0);
     tc_fence_after();
-    (void)variant;  // bring-up aid (swapped LBO/SBO descriptor fields) retired: variant 0 is the verified encoding
-    ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi, a_lo, a_lbo, 8 * a_lbo, NoShift{}, tmem, true);
+    if (variant != 2) {
+      ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi, a_lo, a_lbo, 8 * a_lbo, NoShift{}, tmem, true);
+    } else {
+      // TS form (A operand in TMEM): hi at columns [288, 288+K/2), lo at [288+K/2, 288+K)
+      const uint32_t idesc = umma_idesc_bf16(N);
+      const uint32_t b_lbo = N * 16u, b_step = (2u * b_lbo) >> 4;
+      const uint32_t ta_hi = tmem + 288, ta_lo = tmem + 288 + K / 2;
+      uint32_t acc = 0;
+      for (uint32_t ks = 0; ks < ph.kslabs; ++ks) {
+        mbar_wait(full0 + 8u * rs.stage, rs.phase);
+        tc_fence_after();
+        uint32_t b0 = umma_desc_lo(ring + rs.stage * STAGE, b_lbo);
+        if (elect_one()) {
+          for (uint32_t j = 0; j < 4; ++j) {
+            umma_bf16_ts(tmem, ta_hi + ks * 32 + j * 8, umma_desc_from(b0 + j * b_step), idesc, acc);
+            acc = 1;
+          }
+          if (passes == 3)
+            for (uint32_t j = 0; j < 4; ++j)
+              umma_bf16_ts(tmem, ta_lo + ks * 32 + j * 8, umma_desc_from(b0 + j * b_step), idesc, 1u);
+          umma_commit(empty0 + 8u * rs.stage);
+        }
+        __syncwarp();
+        rs.advance();
+        if (passes == 3) {
+          mbar_wait(full0 + 8u * rs.stage, rs.phase);
+          tc_fence_after();
+          b0 = umma_desc_lo(ring + rs.stage * STAGE, b_lbo);
+          if (elect_one()) {
+            for (uint32_t j = 0; j < 4; ++j)
+              umma_bf16_ts(tmem, ta_hi + ks * 32 + j * 8, umma_desc_from(b0 + j * b_step), idesc, 1u);
+            umma_commit(empty0 + 8u * rs.stage);
+          }
+          __syncwarp();
+          rs.advance();
+        }
+      }
+    }
     umma_commit_elected(mma_done);
   } else {
     const int m = tid;
@@ -223,7 +259,14 @@ k_gemm_selftest(const float* __restrict__ A, int K, const uint8_t* __restrict__ 
       split8(x, hi, lo);
       st_shared_v4(a_hi + kc * a_lbo + m * 16, hi);
       st_shared_v4(a_lo + kc * a_lbo + m * 16, lo);
+      if (variant == 2) {  // the same packed pairs, 4 columns per 8 elements, into this thread's TMEM lane
+        float fh[4] = {__uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
+        float fl[4] = {__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w)};
+        tmem_st4(trow + 288 + 4 * kc, fh);
+        tmem_st4(trow + 288 + K / 2 + 4 * kc, fl);
+      }
     }
+    tmem_wait_st();
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(a_ready);

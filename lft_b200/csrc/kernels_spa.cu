@@ -613,7 +613,7 @@ int debug_timeline_spa(long long* out) {
 
 int configure_spa() {
   CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
-  CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa + 16384));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAttn));
   return 0;
 }
@@ -645,8 +645,7 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     Tab512 tf;
     memcpy(tf.v, L.s_tab.data() + 512, sizeof(tf.v));  // [u_1 256 | c_1 256]
     Scope sc(h, K_SPA_FFN, st);
-    static const size_t extra = getenv("LFT_FFN_1CTA") ? 16384 : 0;  // experiment: force 1 CTA/SM
-    k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa + extra, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
+    k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
                                                                         L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P,
                                                                         h->passes());
     if ((rc = sc.finish())) return rc;

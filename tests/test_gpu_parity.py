@@ -45,6 +45,10 @@ def test_tcgen05_gemm_selftest():
             capi.check(lib.lft_gemm_selftest(A.ctypes.data, W.ctypes.data, D.ctypes.data, aux.ctypes.data, M, N, K, prec, 0))
             assert np.abs(D - ref).max() < tol
             assert np.array_equal(aux, 2 * A[:, :16] + 1)
+            # variant 2: A operand from tensor memory (tcgen05.mma TS form) must give the same bits
+            D2 = np.zeros((M, N), np.float32)
+            capi.check(lib.lft_gemm_selftest(A.ctypes.data, W.ctypes.data, D2.ctypes.data, aux.ctypes.data, M, N, K, prec, 2))
+            assert np.array_equal(D2, D)
 
 
 @pytest.mark.parametrize("name", ["fwd_A5_s4_h8_B1", "fwd_A5_s2_h8_B2", "fwd_A3_s2_h12_B1", "fwd_A5_s2_h32_B1",

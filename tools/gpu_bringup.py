@@ -23,7 +23,7 @@ def selftest():
         W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
         ref = A.astype(np.float64) @ W.astype(np.float64).T
         for prec in (0, 1):
-            for variant in (0,):
+            for variant in (0, 2):
                 D = np.zeros((M, N), np.float32)
                 aux = np.zeros((M, 16), np.float32)
                 rc = lib.lft_gemm_selftest(A.ctypes.data, W.ctypes.data, D.ctypes.data, aux.ctypes.data, M, N, K, prec, variant)
