@@ -125,6 +125,11 @@ int lft_debug_timeline(int32_t which, int64_t* out64);
 int lft_gemm_selftest(const float* A, const float* W, float* D, float* aux, int32_t M, int32_t N, int32_t K,
                       int32_t precision, int32_t variant);
 
+/* Micro-benchmark of the tcgen05 issue/operand path: every CTA issues reps*(K/16) MMAs (128 x N x 16, bf16) on resident
+ * operands; cycles[grid] = clock64 cycles from first issue to completion.  mode 0: A,B from smem (SS); 1: A from TMEM (TS).
+ * smem_bytes sets the dynamic shared memory per CTA (and thereby how many CTAs share an SM). */
+int lft_mma_bench(int32_t N, int32_t K, int32_t reps, int32_t mode, int32_t grid, int32_t smem_bytes, int64_t* cycles);
+
 #ifdef __cplusplus
 }
 #endif

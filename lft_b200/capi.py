@@ -63,6 +63,7 @@ SIGNATURES = {
     "lft_profile_read": (C.c_int, [C.c_void_p, c_i32_p, C.POINTER(C.c_char_p), c_i64_p, C.POINTER(C.c_double)]),
     "lft_launch_count": (C.c_int64, [C.c_void_p]),
     "lft_debug_timeline": (C.c_int, [C.c_int32, c_i64_p]),
+    "lft_mma_bench": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64_p]),
     "lft_gemm_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32]),
 }

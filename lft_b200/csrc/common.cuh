@@ -139,6 +139,11 @@ LFT_DEVINL void tmem_st4(uint32_t taddr, const float* v) {
                "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
                : "memory");
 }
+LFT_DEVINL void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 // 32 consecutive columns without the trailing wait (caller batches several loads, then tmem_wait_ld()).
 LFT_DEVINL void tmem_ld16_nowait(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -339,6 +344,60 @@ LFT_DEVINL void mma_resident64(uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uin
 #pragma unroll
     for (uint32_t j = 0; j < 4; ++j)
       umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(bl + j * b_step), idesc, 1u);
+  }
+}
+
+// 16 fp32 values of this thread's row -> bf16 hi/lo pairs in the TMEM A operand (TS form): elements k0..k0+15 occupy
+// the 8 columns k0/2.. of the hi and of the lo operand (lane = row).
+LFT_DEVINL void a_tmem_store16(uint32_t t_hi, uint32_t t_lo, int k0, const float* x) {
+  uint4 h0, l0, h1, l1;
+  split8(x, h0, l0);
+  split8(x + 8, h1, l1);
+  const uint32_t hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const uint32_t lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+  tmem_st8(t_hi + (k0 >> 1), hv);
+  tmem_st8(t_lo + (k0 >> 1), lv);
+}
+
+// TS-form GEMM phase: D[128 x N] (+)= A(tmem)[128 x K] * W[N x K]^T, weights through the ring (all lanes call it).
+template <int NST>
+LFT_DEVINL void ring_consume_mma_ts(RingState<NST>& rs, uint32_t ring_base, uint32_t stage_bytes, uint32_t full0,
+                                    uint32_t empty0, const GemmPhase& g, int passes, uint32_t ta_hi, uint32_t ta_lo,
+                                    uint32_t d_tmem, bool fresh) {
+  const uint32_t idesc = umma_idesc_bf16(g.N);
+  const uint32_t b_lbo = g.N * 16u, b_step = (2u * b_lbo) >> 4;
+  uint32_t acc = fresh ? 0u : 1u;
+  for (uint32_t ks = 0; ks < g.kslabs; ++ks) {
+    mbar_wait(full0 + 8u * rs.stage, rs.phase);
+    tc_fence_after();
+    uint32_t b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
+    if (elect_one()) {
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j)
+        umma_bf16_ts(d_tmem, ta_hi + ks * 32 + j * 8, umma_desc_from(b0 + j * b_step), idesc, j ? 1u : acc);
+      if (passes == 3) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16_ts(d_tmem, ta_lo + ks * 32 + j * 8, umma_desc_from(b0 + j * b_step), idesc, 1u);
+      }
+      umma_commit(empty0 + 8u * rs.stage);
+    }
+    __syncwarp();
+    acc = 1u;
+    rs.advance();
+    if (passes == 3) {
+      mbar_wait(full0 + 8u * rs.stage, rs.phase);
+      tc_fence_after();
+      b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
+      if (elect_one()) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16_ts(d_tmem, ta_hi + ks * 32 + j * 8, umma_desc_from(b0 + j * b_step), idesc, 1u);
+        umma_commit(empty0 + 8u * rs.stage);
+      }
+      __syncwarp();
+      rs.advance();
+    }
   }
 }
 

@@ -122,6 +122,7 @@ int launch_conv0(Handle* h, const float* lr, float* out, int B, int P, cudaStrea
 int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* out, const float* res, int V, int P,
                    int epi, cudaStream_t st);
 int launch_layout(Handle* h, const float* in, float* out, long long T, int C, int to_t32, cudaStream_t st);
+int launch_mma_bench(int N, int K, int reps, int mode, int grid, int smem_bytes, long long* host_out);
 int launch_selftest(const float* dA, int K, const uint8_t* dW, int N, float* dD, float* dX, int M, int passes,
                     int variant);
 

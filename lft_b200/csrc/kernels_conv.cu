@@ -287,6 +287,60 @@ k_gemm_selftest(const float* __restrict__ A, int K, const uint8_t* __restrict__ 
   cta_teardown(ctl, warp, 512);
 }
 
+// Micro-benchmark: issue `reps` x (K/16) MMAs of shape 128 x N x 16 back to back on resident operands (no ring, no
+// row owners) and report clock64 cycles per MMA.  mode 0: A and B from shared memory; mode 1: A from TMEM.
+__global__ void __launch_bounds__(64, 2) k_mma_bench(int N, int K, int reps, int mode, long long* out, int pad_smem) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (warp == 1) tmem_alloc(smem_u32(&tslot), 256);
+  for (int i = threadIdx.x; i < (128 * K * 2 + N * K * 2) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tslot;
+  if (warp == 1) {
+    const uint32_t a_lbo = 128 * 16, b_lbo = N * 16;
+    const uint32_t a0 = umma_desc_lo(smem_u32(smem), a_lbo), b0 = umma_desc_lo(smem_u32(smem) + 128 * K * 2, b_lbo);
+    const uint32_t idesc = umma_idesc_bf16(N);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (elect_one()) {
+        for (int j = 0; j < K / 16; ++j) {
+          if (mode == 0)
+            umma_bf16(tmem, umma_desc_from(a0 + j * ((2 * a_lbo) >> 4)), umma_desc_from(b0 + j * ((2 * b_lbo) >> 4)), idesc, 1u);
+          else
+            umma_bf16_ts(tmem, tmem + 256 - K / 2 + j * 8, umma_desc_from(b0 + j * ((2 * b_lbo) >> 4)), idesc, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    umma_commit_elected(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    if (threadIdx.x == 32) out[blockIdx.x] = t1 - t0;
+  }
+  (void)pad_smem;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+int launch_mma_bench(int N, int K, int reps, int mode, int grid, int smem_bytes, long long* host_out) {
+  long long* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(long long) * grid));
+  CUDA_TRY(cudaFuncSetAttribute(k_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  k_mma_bench<<<grid, 64, smem_bytes>>>(N, K, reps, mode, d, 0);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(host_out, d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ host
 constexpr size_t kSmemConv64 = kCtlBytes + 2 * kConvRows * 128 + 3 * 64 * 128;
 constexpr size_t kSmemConv128 = kCtlBytes + 2 * kConvRows * 128 + 3 * 128 * 128;

@@ -87,17 +87,19 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
                               c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
     umma_commit_elected(mma_done);
+    // Q, K, V: A operand z = tok + PE_s lives in TMEM columns [128,256) (hi | lo), written by the row owners (TS form)
+    const uint32_t ta_hi = tmem + 128, ta_lo = tmem + 192;
     mbar_wait(a_ready, 1);
     tc_fence_after();
-    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                              tmem + 0, true);
-    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                              tmem + 128, true);
+    ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, ta_hi, ta_lo, tmem + 0, true);
     umma_commit_elected(mma_done);
     mbar_wait(a_ready, 0);
     tc_fence_after();
-    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                              tmem + 0, true);
+    ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, ta_hi, ta_lo, tmem + 0, true);
+    umma_commit_elected(mma_done);
+    mbar_wait(a_ready, 1);
+    tc_fence_after();
+    ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, ta_hi, ta_lo, tmem + 0, true);
     umma_commit_elected(mma_done);
   } else {
     LFT_TL2(0);
@@ -150,16 +152,17 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) z[16 * c + i] += t[i];
-        a_store16(A, 8 * q + 2 * c, m, z + 16 * c);
+        a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, z + 16 * c);
       }
-      pair_ln_stats<64>(z, trow + 128 + 4 * q, trow + 128 + 4 * (1 - q), 1 + (warp & 3), mean, rstd);
+      // mailbox in this thread's own (already consumed) accumulator columns
+      pair_ln_stats<64>(z, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
     }
-    fence_proxy_async_smem();
+    tmem_wait_st();
     tc_fence_before();
     mbar_arrive(a_ready);
     LFT_TL2(3);
 
-    // ---- phase 2: Q, K epilogues (affine LN correction), V MMAs start as soon as Q has been read
+    // ---- phase 2: Q then K (one accumulator, TS-form MMAs): affine LN correction in the epilogue
     const float4* tab4 = reinterpret_cast<const float4*>(tab.v);  // [u_q | u_k | c_q | c_k] x 128 (constant bank)
     const float mr = mean * rstd;
     mbar_wait(mma_done, 1);
@@ -183,11 +186,13 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     tc_fence_before();
     mbar_arrive(a_ready);
     LFT_TL2(5);
+    mbar_wait(mma_done, 0);
+    tc_fence_after();
 #pragma unroll 2
     for (int c = 0; c < 4; ++c) {
       float d[16];
       const int col = 64 * q + 16 * c;
-      tmem_ld16(trow + 128 + col, d);
+      tmem_ld16(trow + col, d);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 uv = tab4[32 + col / 4 + j], cv = tab4[96 + col / 4 + j];
@@ -198,13 +203,15 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       }
       if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
     }
+    tc_fence_before();
+    mbar_arrive(a_ready);
     // ---- phase 3: V = D - PE_s Wv^T  (table prefetched before the wait)
     {
       float4 pv[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) pv[i] = __ldg(reinterpret_cast<const float4*>(pev) + (long long)(16 * q + i) * PP + p);
       LFT_TL2(6);
-      mbar_wait(mma_done, 0);
+      mbar_wait(mma_done, 1);
       tc_fence_after();
       LFT_TL2(7);
 #pragma unroll

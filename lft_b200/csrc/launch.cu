@@ -266,6 +266,11 @@ int lft_debug_timeline(int32_t which, int64_t* out64) {
   return which == 0 ? debug_timeline_spa(o) : (which == 1 ? debug_timeline_ang(o) : debug_timeline_embed(o));
 }
 
+int lft_mma_bench(int32_t N, int32_t K, int32_t reps, int32_t mode, int32_t grid, int32_t smem_bytes, int64_t* cycles) {
+  if (!cycles || N % 16 || N < 16 || N > 256 || K % 16 || K > 256 || grid < 1) return fail(LFT_ERR_ARG, "bad mma bench shape");
+  return launch_mma_bench(N, K, reps, mode, grid, smem_bytes, reinterpret_cast<long long*>(cycles));
+}
+
 int lft_gemm_selftest(const float* A, const float* W, float* D, float* aux, int32_t M, int32_t N, int32_t K,
                       int32_t precision, int32_t variant) {
   if (!A || !W || !D || !aux || M % 128 || K % 64 || N % 16 || N > 256 || N < 16 || K > 256)
