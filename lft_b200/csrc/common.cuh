@@ -207,10 +207,17 @@ LFT_DEVINL uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-LFT_DEVINL void split8(const float* x, uint4& hi, uint4& lo) {
-  // hi = x truncated to its top 16 bits (one PRMT per pair), lo = bf16_rn(x - hi) (exact subtraction):
-  // |x - hi - lo| <= 2^-17 |x|.
+LFT_DEVINL void split8(const float* x, uint4& hi, uint4& lo, bool fp32_mode) {
+  // fp32 mode: hi = x truncated to its top 16 bits (one PRMT per pair), lo = bf16_rn(x - hi) (exact subtraction):
+  // |x - hi - lo| <= 2^-17 |x|.  bf16 mode (no lo pass): hi = bf16_rn(x), unbiased.
   uint32_t h[4], l[4];
+  if (!fp32_mode) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t a = __float_as_uint(x[2 * i]), b = __float_as_uint(x[2 * i + 1]);
@@ -349,14 +356,16 @@ LFT_DEVINL void mma_resident64(uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uin
 
 // 16 fp32 values of this thread's row -> bf16 hi/lo pairs in the TMEM A operand (TS form): elements k0..k0+15 occupy
 // the 8 columns k0/2.. of the hi and of the lo operand (lane = row).
-LFT_DEVINL void a_tmem_store16(uint32_t t_hi, uint32_t t_lo, int k0, const float* x) {
+LFT_DEVINL void a_tmem_store16(uint32_t t_hi, uint32_t t_lo, int k0, const float* x, bool fp32_mode) {
   uint4 h0, l0, h1, l1;
-  split8(x, h0, l0);
-  split8(x + 8, h1, l1);
+  split8(x, h0, l0, fp32_mode);
+  split8(x + 8, h1, l1, fp32_mode);
   const uint32_t hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-  const uint32_t lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
   tmem_st8(t_hi + (k0 >> 1), hv);
-  tmem_st8(t_lo + (k0 >> 1), lv);
+  if (fp32_mode) {
+    const uint32_t lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+    tmem_st8(t_lo + (k0 >> 1), lv);
+  }
 }
 
 // TS-form GEMM phase: D[128 x N] (+)= A(tmem)[128 x K] * W[N x K]^T, weights through the ring (all lanes call it).

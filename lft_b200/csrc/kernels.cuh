@@ -92,7 +92,7 @@ LFT_DEVINL long long t32_off(long long t, int chunk, int C4) {
 // Stage the 64-channel input window of a 3x3 conv tile: smem rows r <-> padded positions g0-kConvOff+r,
 // one lane per row (T32 source: a warp reads 512 contiguous bytes per chunk), bf16 hi/lo, chunk-major.
 LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, uint32_t a_lo, long long g0, long long G,
-                                  long long VS, int P, int tid) {
+                                  long long VS, int P, int tid, bool fp32_mode) {
   const int P1 = P + 1;
   for (int r = tid; r < kConvRows; r += kRowThreads2) {
     const long long g = g0 - kConvOff + r;
@@ -111,9 +111,9 @@ LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, u
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc) {
       uint4 hi, lo;
-      split8(reinterpret_cast<const float*>(&f[2 * kc]), hi, lo);
+      split8(reinterpret_cast<const float*>(&f[2 * kc]), hi, lo, fp32_mode);
       st_shared_v4(a_hi + kc * (kConvRows * 16) + r * 16, hi);
-      st_shared_v4(a_lo + kc * (kConvRows * 16) + r * 16, lo);
+      if (fp32_mode) st_shared_v4(a_lo + kc * (kConvRows * 16) + r * 16, lo);
     }
   }
 }

@@ -121,7 +121,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 hi, lo;
-        split8(x + 8 * c, hi, lo);
+        split8(x + 8 * c, hi, lo, passes == 3);
         st_shared_v4(R1 + (4 * q + c) * LBO + m * 16, hi);
         st_shared_v4(R1 + 16384 + (4 * q + c) * LBO + m * 16, lo);
       }
@@ -248,7 +248,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 hi, lo;
-        split8(o + 8 * c, hi, lo);
+        split8(o + 8 * c, hi, lo, passes == 3);
         st_shared_v4(R1 + (4 * q + c) * LBO + m * 16, hi);
         st_shared_v4(R1 + 16384 + (4 * q + c) * LBO + m * 16, lo);
       }
@@ -276,7 +276,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 hi, lo;
-        split8(x + 8 * c, hi, lo);
+        split8(x + 8 * c, hi, lo, passes == 3);
         st_shared_v4(R1 + (4 * q + c) * LBO + m * 16, hi);
         st_shared_v4(R1 + 16384 + (4 * q + c) * LBO + m * 16, lo);
       }
@@ -310,7 +310,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           uint4 hi, lo;
-          split8(d + 8 * j, hi, lo);
+          split8(d + 8 * j, hi, lo, passes == 3);
           st_shared_v4(R1 + (8 * q + 2 * c + j) * LBO + m * 16, hi);
           st_shared_v4(R2 + (8 * q + 2 * c + j) * LBO + m * 16, lo);
         }

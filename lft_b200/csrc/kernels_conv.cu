@@ -124,7 +124,7 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
     umma_commit_elected(mma_done);
   } else {
     // ---- stage the input window: rows r <-> positions g0 - kConvOff + r, lanes <-> rows
-    conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, tid);
+    conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
     fence_proxy_async_smem();
     mbar_arrive(a_ready);
 
@@ -256,7 +256,7 @@ k_gemm_selftest(const float* __restrict__ A, int K, const uint8_t* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = A[(size_t)m * K + kc * 8 + i];
       uint4 hi, lo;
-      split8(x, hi, lo);
+      split8(x, hi, lo, passes == 3);
       st_shared_v4(a_hi + kc * a_lbo + m * 16, hi);
       st_shared_v4(a_lo + kc * a_lbo + m * 16, lo);
       if (variant == 2) {  // the same packed pairs, 4 columns per 8 elements, into this thread's TMEM lane

@@ -38,13 +38,13 @@ LFT_DEVINL void planar_store16(float* base, long long v, int head, int y, int x,
 }
 
 // split 16 fp32 values into two k-chunks (kc0, kc0+1) of the K=128 A operand (hi at A, lo at A+32K)
-LFT_DEVINL void a_store16(uint32_t A, int kc0, int m, const float* x) {
+LFT_DEVINL void a_store16(uint32_t A, int kc0, int m, const float* x, bool fp32_mode) {
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     uint4 hi, lo;
-    split8(x + 8 * j, hi, lo);
+    split8(x + 8 * j, hi, lo, fp32_mode);
     st_shared_v4(A + (kc0 + j) * kLbo + m * 16, hi);
-    st_shared_v4(A + 32768 + (kc0 + j) * kLbo + m * 16, lo);
+    if (fp32_mode) st_shared_v4(A + 32768 + (kc0 + j) * kLbo + m * 16, lo);
   }
 }
 
@@ -103,7 +103,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     umma_commit_elected(mma_done);
   } else {
     LFT_TL2(0);
-    conv_stage_window(feat, c_hi, c_lo, g0, G, VS, P, tid);
+    conv_stage_window(feat, c_hi, c_lo, g0, G, VS, P, tid, passes == 3);
     fence_proxy_async_smem();
     mbar_arrive(a_ready);
     LFT_TL2(1);
@@ -152,7 +152,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) z[16 * c + i] += t[i];
-        a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, z + 16 * c);
+        a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, z + 16 * c, passes == 3);
       }
       // mailbox in this thread's own (already consumed) accumulator columns
       pair_ln_stats<64>(z, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
@@ -479,7 +479,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j) f[4 * c + j] = ok ? __ldg(reinterpret_cast<const float4*>(ob + c * hs + j * js)) : zero4;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, reinterpret_cast<const float*>(&f[4 * c]));
+      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, reinterpret_cast<const float*>(&f[4 * c]), passes == 3);
     }
     publish();
 
@@ -504,7 +504,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
           *reinterpret_cast<float4*>(trow_g + 128 * i) = make_float4(yv[4 * i], yv[4 * i + 1], yv[4 * i + 2], yv[4 * i + 3]);
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, yv + 16 * c);
+      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, yv + 16 * c, passes == 3);
       pair_ln_stats<64>(yv, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
     }
     publish();
@@ -526,7 +526,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
         d[4 * j + 2] = fmaxf(fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
         d[4 * j + 3] = fmaxf(fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w)), 0.f);
       }
-      a_store16(A, 8 * q + 2 * c, m, d);
+      a_store16(A, 8 * q + 2 * c, m, d, passes == 3);
     }
     publish();
 
@@ -546,7 +546,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
       }
       await();  // FFN2a done: A is free
 #pragma unroll
-      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, hb + 16 * c);
+      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, hb + 16 * c, passes == 3);
     }
     publish();
 
@@ -565,7 +565,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
           d[4 * j] += y1[4 * c + j].x; d[4 * j + 1] += y1[4 * c + j].y;
           d[4 * j + 2] += y1[4 * c + j].z; d[4 * j + 3] += y1[4 * c + j].w;
         }
-        a_store16(A, 8 * q + 2 * c, m, d);
+        a_store16(A, 8 * q + 2 * c, m, d, passes == 3);
       }
     }
     publish();

@@ -96,7 +96,7 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
         const float4 f1 = ok ? __ldg(reinterpret_cast<const float4*>(feat + t32_off(tu, 8 * q + 2 * kc + 1, 16))) : make_float4(0.f, 0.f, 0.f, 0.f);
         z[0] = f0.x; z[1] = f0.y; z[2] = f0.z; z[3] = f0.w; z[4] = f1.x; z[5] = f1.y; z[6] = f1.z; z[7] = f1.w;
         uint4 hi, lo;
-        split8(z, hi, lo);
+        split8(z, hi, lo, passes == 3);
         st_shared_v4(A1 + (4 * q + kc) * kLbo64 + m * 16, hi);
         st_shared_v4(A1 + 16384 + (4 * q + kc) * kLbo64 + m * 16, lo);
       }

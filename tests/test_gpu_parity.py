@@ -195,6 +195,42 @@ def test_full_light_field_vs_oracle_test_loop():
     assert torch.equal(crops, eng.forward_lf_crops(lf.cuda(), 0, 12))
 
 
+def test_config2_2x_batch64_fp32_and_bf16():
+    """BASELINE config 2: 5x5 2x, batch of 64 LR patches 32x32/view: oracle on a sample of the batch (fp32 gate),
+    bf16 PSNR gate on the same sample, every patch equal to its own B=1 forward."""
+    A, s, h, B = 5, 2, 32, 64
+    sd = synth.synth_state_dict(A, s, 1)
+    lr = torch.from_numpy(synth.synth_lr_mosaic(B, A, h, h, 1))
+    eng = _engine(A, s, sd)
+    out = eng.forward(lr.cuda())
+    pick = [0, 31, 63]
+    ref = O.forward(sd, lr[pick], A, s)
+    assert (out[pick].cpu() - ref).abs().max() <= TOL_FP32
+    assert torch.equal(eng.forward(lr[31:32].cuda())[0], out[31])
+    eng.set_precision("bf16")
+    outb = eng.forward(lr[pick].cuda()).cpu().numpy()
+    refn = ref.numpy()
+    rng = np.random.default_rng(1)
+    hr = refn + rng.standard_normal(refn.shape).astype(np.float32) * 0.012   # ~38 dB, the 2x operating point
+    assert abs(_psnr(refn, hr) - _psnr(outb, hr)) <= 0.01
+    assert _psnr(outb, refn) > 55.0
+
+
+def test_config5_angres9_batch_chunked():
+    """BASELINE config 5: 9x9 (81 angular tokens), 32x32 patches: chunked batch == unchunked, finite, and the
+    first patch matches the oracle."""
+    A, s, h, B = 9, 4, 32, 6
+    sd = synth.synth_state_dict(A, s, 4)
+    lr = torch.from_numpy(synth.synth_lr_mosaic(B, A, h, h, 4))
+    eng = _engine(A, s, sd)
+    full = eng.forward(lr.cuda())
+    assert torch.isfinite(full).all()
+    small = eng.forward(lr.cuda(), max_ws_bytes=eng.workspace_bytes(2, h))
+    assert torch.equal(small, full)
+    ref = O.forward(sd, lr[:1], A, s)
+    assert (full[:1].cpu() - ref).abs().max() <= TOL_FP32
+
+
 def test_profile_and_launch_count():
     A, s = 5, 4
     eng = _engine(A, s, synth.synth_state_dict(A, s, 0))
