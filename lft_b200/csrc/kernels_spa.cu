@@ -435,11 +435,15 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
                                 tmem + dcol, fresh);
     };
     auto done = [&]() { umma_commit_elected(mma_done); LFT_TL(tl); ++tl; };
-    wait_a(); gemm(g_o, 0, true); done();                                  // D[0,128)   = O Wo^T
-    wait_a(); gemm(g_1a, 0, true); gemm(g_1b, 128, true); done();          // D[0,256)   = Y1 W'1^T  (both halves)
-    wait_a(); gemm(g_2a, 0, true); done();                                 // D[0,128)   = relu(.)[:, :128] W2[:, :128]^T
-    wait_a(); gemm(g_2b, 0, false); done();                                // D[0,128)  += relu(.)[:, 128:] W2[:, 128:]^T
-    wait_a(); gemm(g_l, 128, true); done();                                // D[128,192) = Y2 Wlin^T
+    // TS form (A operand in TMEM columns [128,192) hi | [192,256) lo) wherever those columns are free
+    auto gemm_ts = [&](const GemmPhase& g, uint32_t dcol, bool fresh) {
+      ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g, passes, tmem + 128, tmem + 192, tmem + dcol, fresh);
+    };
+    wait_a(); gemm_ts(g_o, 0, true); done();                               // D[0,128)   = O Wo^T                    (TS)
+    wait_a(); gemm(g_1a, 0, true); gemm(g_1b, 128, true); done();          // D[0,256)   = Y1 W'1^T  (both halves)   (SS)
+    wait_a(); gemm(g_2a, 0, true); done();                                 // D[0,128)   = relu(.)[:, :128] W2a^T    (SS)
+    wait_a(); gemm_ts(g_2b, 0, false); done();                             // D[0,128)  += relu(.)[:, 128:] W2b^T    (TS)
+    wait_a(); gemm_ts(g_l, 0, true); done();                               // D[0,64)    = Y2 Wlin^T                 (TS)
   } else {
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     const long long t = (long long)blockIdx.x * 128 + m;
@@ -466,6 +470,13 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
       tc_fence_after();
       LFT_TL(tl); ++tl;
     };
+    auto publish_tmem = [&]() {  // A operand written with tcgen05.st
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+      LFT_TL(tl); ++tl;
+    };
+    const bool fp32m = passes == 3;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     LFT_TL(0);
 
@@ -479,9 +490,10 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j) f[4 * c + j] = ok ? __ldg(reinterpret_cast<const float4*>(ob + c * hs + j * js)) : zero4;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, reinterpret_cast<const float*>(&f[4 * c]), passes == 3);
+      for (int c = 0; c < 4; ++c)
+        a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, reinterpret_cast<const float*>(&f[4 * c]), fp32m);
     }
-    publish();
+    publish_tmem();
 
     // phase 1: Y1 = tok + D (own half) -> global spill + raw A operand; LN2 statistics (folded into FFN1's epilogue)
     float mean, rstd;
@@ -530,12 +542,16 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
     }
     publish();
 
-    // phase 3: hidden[:, 128:] is computed from D[128,256) while the FFN2a MMAs run; stored once A is free
+    // phase 3: hidden[:, 128:] from D[128,256) -> TMEM A operand (the same columns, once both partner threads have
+    // read their halves); it does not touch the smem operand FFN2a is still reading, so no wait is needed here
     {
       float hb[64];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 128 + 64 * q + 16 * c, hb + 16 * c);
       tmem_wait_ld();
+      tc_fence_before();
+      pair_bar_sync(warp & 3);
+      tc_fence_after();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float4 uv = u1[32 + 16 * q + j], cv = c1[32 + 16 * q + j];
@@ -544,11 +560,11 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
         hb[4 * j + 2] = fmaxf(fmaf(rstd, hb[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
         hb[4 * j + 3] = fmaxf(fmaf(rstd, hb[4 * j + 3], fmaf(-mr, uv.w, cv.w)), 0.f);
       }
-      await();  // FFN2a done: A is free
 #pragma unroll
-      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, hb + 16 * c, passes == 3);
+      for (int c = 0; c < 4; ++c) a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, hb + 16 * c, fp32m);
     }
-    publish();
+    publish_tmem();
+    await();  // FFN2a done (keeps the mma_done phases in step)
 
     // phase 4: Y2 = Y1 (spilled row, prefetched) + D[0,128) -> A
     {
@@ -565,12 +581,12 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
           d[4 * j] += y1[4 * c + j].x; d[4 * j + 1] += y1[4 * c + j].y;
           d[4 * j + 2] += y1[4 * c + j].z; d[4 * j + 3] += y1[4 * c + j].w;
         }
-        a_store16(A, 8 * q + 2 * c, m, d, passes == 3);
+        a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, d, fp32m);
       }
     }
-    publish();
+    publish_tmem();
 
-    // phase 5: out = D[128,192) (+ global residual), own 32 columns
+    // phase 5: out = D[0,64) (+ global residual), own 32 columns
     float4 r4[8];
     if (final_res) {
 #pragma unroll
@@ -580,8 +596,8 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
     await();
     {
       float d[32];
-      tmem_ld16_nowait(trow + 128 + 32 * q, d);
-      tmem_ld16_nowait(trow + 128 + 32 * q + 16, d + 16);
+      tmem_ld16_nowait(trow + 32 * q, d);
+      tmem_ld16_nowait(trow + 32 * q + 16, d + 16);
       tmem_wait_ld();
       if (ok) {
 #pragma unroll

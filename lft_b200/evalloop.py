@@ -1,0 +1,41 @@
+"""test.py-compatible evaluation loop: the body of `test(test_loader, device, net)`
+(test.py:73-111) with the per-patch Python loop replaced by the batched device path.
+
+    for Lr_SAI_y, Hr_SAI_y in loader:             # [1, A*h0, A*w0] / [1, A*h0*s, A*w0*s] like TestSetDataLoader
+        Sr_SAI_y = sr(Lr_SAI_y.squeeze().cuda())   # LFdivide -> forward(all patches) -> LFintegrate on the GPU
+
+Metrics are not part of the hot path (skimage PSNR/SSIM, out of scope); a per-view PSNR with the
+reference's definition (utils.py:79,85: 10 log10(1/MSE) on [0,1] images, mean over views) is provided because the
+bf16 gate is stated in PSNR.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+
+from .lightfield import LightFieldSR
+
+
+def psnr_per_view(sr_sai: torch.Tensor, hr_sai: torch.Tensor, angRes: int) -> torch.Tensor:
+    """[A, A] PSNR of every view of two SAI mosaics [A*H, A*W] (utils.py:56-88 without SSIM)."""
+    A = angRes
+    H, W = sr_sai.shape[0] // A, sr_sai.shape[1] // A
+    d = (sr_sai.double() - hr_sai.double().to(sr_sai.device)).view(A, H, A, W).permute(0, 2, 1, 3)
+    mse = (d * d).mean(dim=(2, 3)).clamp_min(1e-20)
+    return 10.0 * torch.log10(1.0 / mse)
+
+
+@torch.no_grad()
+def test(test_loader: Iterable, device, net, angRes: Optional[int] = None) -> Tuple[float, List[torch.Tensor]]:
+    """Mirror of test.py:73-111: returns (mean PSNR over the loader, list of SR SAI mosaics on the CPU)."""
+    A = angRes if angRes is not None else net.angRes
+    sr = LightFieldSR(net)
+    psnrs, outs = [], []
+    for Lr_SAI_y, Hr_SAI_y in test_loader:
+        lr = Lr_SAI_y.squeeze().to(device, torch.float32).contiguous()   # test.py:77
+        Sr_SAI_y = sr(lr)                                                 # test.py:83-101
+        outs.append(Sr_SAI_y.cpu())
+        if Hr_SAI_y is not None:
+            psnrs.append(float(psnr_per_view(Sr_SAI_y, Hr_SAI_y.squeeze(), A).mean()))
+    return (sum(psnrs) / len(psnrs) if psnrs else float("nan")), outs

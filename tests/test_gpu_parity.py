@@ -231,6 +231,25 @@ def test_config5_angres9_batch_chunked():
     assert (full[:1].cpu() - ref).abs().max() <= TOL_FP32
 
 
+def test_eval_loop_dropin(tmp_path):
+    """test.py-compatible loop: same SR and same mean PSNR as the oracle's per-patch loop."""
+    from lft_b200.evalloop import test as run_test, psnr_per_view
+    from lft_b200.model import get_model
+    A, s, h0, w0 = 5, 2, 32, 40
+    sd = synth.synth_state_dict(A, s, 8)
+    net = get_model(types.SimpleNamespace(channels=64, angRes=A, scale_factor=s))
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    lr = torch.from_numpy(synth.synth_light_field(A, h0, w0, 8))
+    hr = torch.from_numpy(synth.synth_light_field(A, h0 * s, w0 * s, 9))
+    loader = [(lr[None], hr[None])]
+    mean_psnr, outs = run_test(loader, torch.device("cuda"), net)
+    want, _ = O.infer_light_field(sd, lr, A, s, mode="window", batch=4)
+    assert (outs[0] - want).abs().max() <= TOL_FP32
+    ref_psnr = float(psnr_per_view(want, hr, A).mean())
+    assert abs(mean_psnr - ref_psnr) <= 1e-3
+
+
 def test_profile_and_launch_count():
     A, s = 5, 4
     eng = _engine(A, s, synth.synth_state_dict(A, s, 0))
