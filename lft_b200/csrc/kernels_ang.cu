@@ -27,6 +27,123 @@ LFT_DEVINL float dot8(const f32x2* q, const ulonglong2& k0, const ulonglong2& k1
   return hsum2(add2(a, b));
 }
 
+// Attention of ONE head for NQ queries of the same pixel held by one thread (A=5 path): the 25 keys/values of that
+// pixel and head are read ONCE from shared memory for all NQ queries.  Softmax is evaluated online in chunks of 5
+// keys (scores of one chunk live in registers; the accumulators are rescaled once per chunk).  q is pre-scaled by
+// log2(e)/sqrt(hd).  kb/vb: this pixel's first key in the [head][half][kv row][4 floats] planes (kv row = t*5 + pixel).
+template <int NQ>
+LFT_DEVINL void ang_attn_head25(const f32x2 (*q)[4], const ulonglong2* __restrict__ kb, const ulonglong2* __restrict__ vb,
+                                float (*o)[8]) {
+  float mx[NQ], l[NQ];
+  f32x2 acc[NQ][4];
+#pragma unroll
+  for (int x = 0; x < NQ; ++x) {
+    mx[x] = -INFINITY;
+    l[x] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[x][e] = 0ull;
+  }
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    float sc[NQ][5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const ulonglong2 k0 = kb[5 * (5 * c + j)], k1 = kb[5 * (5 * c + j) + 128];
+#pragma unroll
+      for (int x = 0; x < NQ; ++x) sc[x][j] = dot8(q[x], k0, k1);
+    }
+#pragma unroll
+    for (int x = 0; x < NQ; ++x) {
+      const float cm = fmaxf(fmaxf(fmaxf(sc[x][0], sc[x][1]), fmaxf(sc[x][2], sc[x][3])), sc[x][4]);
+      const float mn = fmaxf(mx[x], cm);
+      const float corr = fast_exp2(mx[x] - mn);  // first chunk: exp2(-inf) = 0 on zero accumulators
+      mx[x] = mn;
+      l[x] *= corr;
+      const f32x2 c2 = pack2(corr, corr);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[x][e] = mul2(acc[x][e], c2);
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const ulonglong2 v0 = vb[5 * (5 * c + j)], v1 = vb[5 * (5 * c + j) + 128];
+#pragma unroll
+      for (int x = 0; x < NQ; ++x) {
+        const float pw = fast_exp2(sc[x][j] - mx[x]);
+        l[x] += pw;
+        const f32x2 pp = pack2(pw, pw);
+        acc[x][0] = fma2(pp, v0.x, acc[x][0]); acc[x][1] = fma2(pp, v0.y, acc[x][1]);
+        acc[x][2] = fma2(pp, v1.x, acc[x][2]); acc[x][3] = fma2(pp, v1.y, acc[x][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < NQ; ++x) {
+    const float inv = 1.f / l[x];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a, b;
+      unpack2(acc[x][e], a, b);
+      o[x][2 * e] = a * inv;
+      o[x][2 * e + 1] = b * inv;
+    }
+  }
+}
+
+// One head pair (relative heads h2 and 2+h2 of this thread's channel half) of the A=5 attention for a lane pair:
+// the lower lane (of l, l+16) computes head h2, the upper lane head 2+h2, each for its own query, its partner's and (NQ == 3) a
+// third query of the same pixel; queries and results travel by warp shuffles.  Q is read from the fp32 stash in
+// TMEM columns [tq, tq+32); results are written as the bf16 hi/lo TS-form A operand of the output projection.
+template <int NQ>
+LFT_DEVINL void ang_pair_heads25(uint32_t tq, uint32_t to_hi, uint32_t to_lo, int h2, bool up, int partner, int tsrc,
+                                 bool single, int hlo, int hup, const uint8_t* ks_q, const uint8_t* vs_q, int pl,
+                                 bool fp32_mode) {
+  float qa[8], qb[8];
+  tmem_ld8(tq + 8 * h2, qa);
+  tmem_ld8(tq + 16 + 8 * h2, qb);
+  f32x2 qq[NQ][4];
+  {
+    float mine[8], part[8], third[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mine[i] = up ? qb[i] : qa[i];
+      part[i] = __shfl_sync(0xffffffffu, up ? qa[i] : qb[i], partner);  // the partner's query, MY head
+      if (NQ == 3) {
+        const float tl = __shfl_sync(0xffffffffu, qa[i], tsrc), tu = __shfl_sync(0xffffffffu, qb[i], tsrc);
+        third[i] = up ? tu : tl;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      qq[0][e] = pack2(mine[2 * e], mine[2 * e + 1]);
+      qq[1][e] = pack2(part[2 * e], part[2 * e + 1]);
+      if (NQ == 3) qq[NQ - 1][e] = pack2(third[2 * e], third[2 * e + 1]);
+    }
+  }
+  const int head = (up ? 2 : 0) + h2;
+  const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(ks_q + head * 4096) + pl;
+  const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(vs_q + head * 4096) + pl;
+  float o[NQ][8];
+  ang_attn_head25<NQ>(qq, kb, vb, o);
+  float oa[8], ob[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float recv = __shfl_sync(0xffffffffu, o[1][i], partner);  // my query, the partner's head
+    oa[i] = up ? recv : o[0][i];
+    ob[i] = up ? o[0][i] : recv;
+    if (NQ == 3) {
+      const float rl = __shfl_sync(0xffffffffu, o[NQ - 1][i], hlo), ru = __shfl_sync(0xffffffffu, o[NQ - 1][i], hup);
+      if (single) { oa[i] = rl; ob[i] = ru; }
+    }
+  }
+  uint4 hi, lo;
+  split8(oa, hi, lo, fp32_mode);
+  tmem_st4u(to_hi + 4 * h2, hi);
+  if (fp32_mode) tmem_st4u(to_lo + 4 * h2, lo);
+  split8(ob, hi, lo, fp32_mode);
+  tmem_st4u(to_hi + 8 + 4 * h2, hi);
+  if (fp32_mode) tmem_st4u(to_lo + 8 + 4 * h2, lo);
+}
+
 // NV > 0: compile-time number of views (scores kept in registers, single QK pass); NV == 0: runtime N.
 template <int NV>
 __global__ void __launch_bounds__(kThreads2, 2)
@@ -73,8 +190,11 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     umma_commit_elected(mma_done);
     mbar_wait(a_ready, 1);
     tc_fence_after();
-    ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes, R1, R1 + 16384, LBO, 0, NoShift{},
-                              tmem + 0, true);
+    if constexpr (NV == 25)  // O operand in TMEM columns [64,96) hi | [96,128) lo (TS form)
+      ring_consume_mma_ts<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes, tmem + 64, tmem + 96, tmem + 0, true);
+    else
+      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes, R1, R1 + 16384, LBO, 0, NoShift{},
+                                tmem + 0, true);
     umma_commit_elected(mma_done);
     mbar_wait(a_ready, 0);
     tc_fence_after();
@@ -92,7 +212,30 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     // rows are view-major inside the tile (m = a*PPT + pl): consecutive lanes = consecutive pixels of one view,
     // so one 16-byte request of a warp touches ~7 cache lines of the T32 layout instead of 25
     const int PPT = NV > 0 ? 128 / NV : 128 / N;
-    const int a = m / PPT, pl = m - a * PPT;
+    int a, pl, kvrow;
+    if constexpr (NV == 25) {
+      // paired rows: lanes l and l+16 of a warp hold views (2v, 2v+1) of ONE pixel, so that the attention can share every
+      // K/V read between two queries (partner = lane ^ 16; a quarter-warp always reads one head: no bank conflicts).
+      // Pair k = 16*(warp&3) + (lane&15) < 60: view pair k/5, pixel k%5.  The 8 remaining lanes of the last row warp
+      // hold the 5 rows of view 24 (slots 0..4) and 3 idle rows.
+      {
+        const int k = 16 * (warp & 3) + (lane & 15), upper = lane >> 4;
+        if (k < 60) {
+          const int vp = k / 5;
+          pl = k - 5 * vp;
+          a = 2 * vp + upper;
+        } else {
+          const int slot = (k - 60) + 4 * upper;
+          a = slot < 5 ? 24 : 25;
+          pl = slot < 5 ? slot : slot - 5;
+        }
+      }
+      kvrow = a < 25 ? a * 5 + pl : m;  // K/V planes stay view-major: one wavefront per key read
+    } else {
+      a = m / PPT;
+      pl = m - a * PPT;
+      kvrow = m;
+    }
     const long long gp = (long long)blockIdx.x * PPT + pl;
     const bool rowok = (a < N) && (gp < npix);
     long long tok = 0;
@@ -161,7 +304,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)  // [head][half][row][4 floats]: head = 4q + 2c + j/2, half = j%2 (conflict-free)
-          *reinterpret_cast<float4*>(ks_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + m * 16) =
+          *reinterpret_cast<float4*>(ks_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) =
               make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
       }
 #pragma unroll
@@ -169,7 +312,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
         tmem_ld16(trow + 128 + 32 * q + 16 * c, kv);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(vs_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + m * 16) =
+          *reinterpret_cast<float4*>(vs_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) =
               make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
       }
       float qv[32];
@@ -177,6 +320,52 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       tmem_ld16_nowait(trow + 32 * q + 16, qv + 16);
       tmem_wait_ld();
       const float scale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e)/sqrt(8), folded into Q (softmax via exp2)
+      if constexpr (NV == 25) {
+        // corrected, pre-scaled Q back into its own TMEM columns (fp32 stash); the pair kernels re-read one head pair at a time
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 pv = __ldg(pq4 + (8 * q + j) * N);
+          const float4 uv = tab4[8 * q + j], cv = tab4[32 + 8 * q + j];
+          qv[4 * j] = scale * fmaf(rstd, qv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
+          qv[4 * j + 1] = scale * fmaf(rstd, qv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
+          qv[4 * j + 2] = scale * fmaf(rstd, qv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
+          qv[4 * j + 3] = scale * fmaf(rstd, qv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+        }
+        tmem_st16(trow + 32 * q, qv);
+        tmem_st16(trow + 32 * q + 16, qv + 16);
+        tmem_wait_st();
+        rows_bar_sync256();  // K/V planes complete; every K/V accumulator column has been consumed
+        LFT_TL(3);
+        const int wq = warp & 3;
+        const bool up = lane >= 16;
+        int partner = lane ^ 16, tsrc = lane, hlo = lane, hup = lane;
+        bool single = false;
+        if (wq == 3) {  // pairs 48..59 in lanes 0..11 / 16..27; view 24 of pixel s in lane 12+s (s < 4) or 28 (s = 4)
+          const int l15 = lane & 15;
+          if (l15 >= 12) {
+            partner = lane;
+            single = a == 24;
+            if (single) { hlo = (pl + 2) % 5; hup = hlo + 16; }  // the pair holding views 18/19 or 20/21 of the same pixel
+          } else if (l15 < 5) {
+            const int px = (3 + l15) % 5;  // pixel of pair 48 + l15
+            tsrc = px < 4 ? 12 + px : 28;
+          }
+        }
+        const uint8_t* ks_q = ks_ptr + (4 * q) * 4096;
+        const uint8_t* vs_q = vs_ptr + (4 * q) * 4096;
+        const uint32_t tq = trow + 32 * q, to_hi = trow + 64 + 16 * q, to_lo = trow + 96 + 16 * q;
+#pragma unroll 1
+        for (int h2 = 0; h2 < 2; ++h2) {
+          if (wq == 3)
+            ang_pair_heads25<3>(tq, to_hi, to_lo, h2, up, partner, tsrc, single, hlo, hup, ks_q, vs_q, pl, passes == 3);
+          else
+            ang_pair_heads25<2>(tq, to_hi, to_lo, h2, up, partner, tsrc, single, hlo, hup, ks_q, vs_q, pl, passes == 3);
+        }
+        LFT_TL(4);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+      } else {
       f32x2 q2[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -255,6 +444,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(a_ready);
+      }  // NV != 25
     }
 
     LFT_TL(5);

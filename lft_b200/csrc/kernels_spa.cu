@@ -67,6 +67,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
   const long long VS = (long long)P1 * P1;
   const long long G = (long long)V * VS;
   const long long g0 = (long long)blockIdx.x * 128;
+  LFT_TL2(20);
   cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
   const GemmPhase g_c{wmlp, 128, 9}, g_q{wq, 128, 2}, g_k{wk, 128, 2}, g_v{wv, 128, 2};
@@ -83,24 +84,32 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     RingState<kSpaNST> rs;
     mbar_wait(a_ready, 0);
     tc_fence_after();
+    LFT_TL2(10);
     auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
     ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
                               c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
     umma_commit_elected(mma_done);
+    LFT_TL2(11);
     // Q, K, V: A operand z = tok + PE_s lives in TMEM columns [128,256) (hi | lo), written by the row owners (TS form)
     const uint32_t ta_hi = tmem + 128, ta_lo = tmem + 192;
     mbar_wait(a_ready, 1);
     tc_fence_after();
+    LFT_TL2(12);
     ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, ta_hi, ta_lo, tmem + 0, true);
     umma_commit_elected(mma_done);
+    LFT_TL2(13);
     mbar_wait(a_ready, 0);
     tc_fence_after();
+    LFT_TL2(14);
     ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, ta_hi, ta_lo, tmem + 0, true);
     umma_commit_elected(mma_done);
+    LFT_TL2(15);
     mbar_wait(a_ready, 1);
     tc_fence_after();
+    LFT_TL2(16);
     ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, ta_hi, ta_lo, tmem + 0, true);
     umma_commit_elected(mma_done);
+    LFT_TL2(17);
   } else {
     LFT_TL2(0);
     conv_stage_window(feat, c_hi, c_lo, g0, G, VS, P, tid, passes == 3);
@@ -230,6 +239,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     tc_fence_before();
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
+  LFT_TL2(21);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -180,7 +180,7 @@ def spa_trans(x: torch.Tensor, sd: Dict[str, torch.Tensor], pre: str, pe_hw: tor
     tn = _ln(tok + pe, sd[pre + "norm.weight"], sd[pre + "norm.bias"])
     w_in, w_out = sd[pre + "attention.in_proj_weight"], sd[pre + "attention.out_proj.weight"]
     if mode == "dense":
-        mask = gen_mask_loop(h, w, 5).to(tok.dtype)
+        mask = gen_mask_loop(h, w, 5).to(tok)                             # built on the host like LFT.py:147-162, then moved
         att = _mha(tn, tok, w_in, w_out, mask)
     else:
         hd = S // HEADS
@@ -188,7 +188,7 @@ def spa_trans(x: torch.Tensor, sd: Dict[str, torch.Tensor], pre: str, pe_hw: tor
         q = (tn @ w_in[:S].t()).view(V_, h * w, HEADS, hd)
         k = (tn @ w_in[S:2 * S].t()).view(V_, h * w, HEADS, hd)
         v = (tok @ w_in[2 * S:].t()).view(V_, h * w, HEADS, hd)
-        idx, valid = window_index(h, w, 5)
+        idx, valid = (t.to(tok.device) for t in window_index(h, w, 5))
         kg = k[:, idx]                                                     # [V, hw, 25, H, hd]
         vg = v[:, idx]
         s = torch.einsum("vqhd,vqkhd->vqhk", q, kg) / math.sqrt(hd)
@@ -219,12 +219,12 @@ def bicubic_views(v: torch.Tensor, s: int) -> torch.Tensor:
     4 taps at floor(src)-1..+2 with indices clamped to the view, no output clamp. v:[V,h,w]->[V,hs,ws]."""
     V, h, w = v.shape
     def axis(n):
-        dst = torch.arange(n * s, dtype=v.dtype)
+        dst = torch.arange(n * s, dtype=v.dtype, device=v.device)
         src = (dst + 0.5) / s - 0.5
         i0 = torch.floor(src)
         t = src - i0
         ws_ = torch.stack(_cubic_w(t), dim=1)                               # [n*s, 4]
-        ii = (i0.long()[:, None] + torch.arange(-1, 3)[None]).clamp(0, n - 1)
+        ii = (i0.long()[:, None] + torch.arange(-1, 3, device=v.device)[None]).clamp(0, n - 1)
         return ii, ws_
     iy, wy = axis(h)
     ix, wx = axis(w)
@@ -250,7 +250,7 @@ def forward(sd: Dict[str, torch.Tensor], lr: torch.Tensor, angRes: int, scale: i
     """get_model.forward (LFT.py:52-83). lr: [B,1,A*h,A*w] SAI mosaic -> [B,1,A*h*s,A*w*s].
     `stages`, if given, is filled with channels-last intermediates for stage-level tests."""
     A, s = angRes, scale
-    sd = {k: v.to(dtype) for k, v in sd.items()}
+    sd = {k: v.to(device=lr.device, dtype=dtype) for k, v in sd.items()}
     lr = lr.to(dtype)
     B, _, H, W = lr.shape
     h, w = H // A, W // A
@@ -263,8 +263,8 @@ def forward(sd: Dict[str, torch.Tensor], lr: torch.Tensor, angRes: int, scale: i
     buf = buf.view(B, A * A, C, h, w).permute(0, 1, 3, 4, 2).contiguous()   # [B,N,h,w,C]
     if stages is not None:
         stages["conv_init"] = buf.clone()
-    pe_a = ang_position(A, C, dtype)
-    pe_s = spa_position(h, w, C, dtype)
+    pe_a = ang_position(A, C, dtype).to(lr.device)                          # LFT.py:103 (.to(device) per forward)
+    pe_s = spa_position(h, w, C, dtype).to(lr.device)
     x = buf
     for i in range(layers):
         x = ang_trans(x, sd, f"altblock.{i}.ang_trans.", pe_a)

@@ -5,14 +5,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lft_b200 import capi, synth
 from lft_b200.engine import Engine
 A, s = 5, 4
-eng = Engine(A, s); eng.load_state_dict(synth.synth_state_dict(A, s, 0))
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+eng = Engine(A, s, precision=prec); eng.load_state_dict(synth.synth_state_dict(A, s, 0))
 lr = torch.from_numpy(synth.synth_lr_mosaic(64, A, 32, 32, 0)).cuda()
 for _ in range(2): eng.forward(lr)
 torch.cuda.synchronize()
 for which, name in ((0, "k_spa_ffn"), (1, "k_ang"), (2, "k_spa_embed_qkv")):
     buf = (C.c_int64 * 64)()
     capi.check(eng.lib.lft_debug_timeline(which, buf))
-    row = [buf[i] for i in range(30)]; mma = [buf[32 + i] for i in range(30)]
+    row = [buf[i] for i in range(32)]; mma = [buf[32 + i] for i in range(32)]
     t0 = min(x for x in row + mma if x > 0)
-    print(name, "row :", [x - t0 for x in row if x > 0])
-    print(name, "mma :", [x - t0 for x in mma if x > 0])
+    print(prec, name, "row :", {i: x - t0 for i, x in enumerate(row) if x > 0})
+    print(prec, name, "mma :", {i: x - t0 for i, x in enumerate(mma) if x > 0})
