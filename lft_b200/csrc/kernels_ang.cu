@@ -483,11 +483,14 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     LFT_TL(8);
     {
       const float mr = mean * rstd;
-#pragma unroll 1
+      float dd[64];  // all four accumulator loads in flight, one wait
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dd + 16 * c);
+      tmem_wait_ld();
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float d[16];
+        float* d = dd + 16 * c;
         const int col = 64 * q + 16 * c;
-        tmem_ld16(trow + col, d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 uv = reinterpret_cast<const float4*>(tab.v + 256 + col)[j];

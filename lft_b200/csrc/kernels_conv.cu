@@ -4,6 +4,8 @@
 #include "host.h"
 #include "kernels.cuh"
 
+#include <cstring>
+
 namespace lft {
 
 // ------------------------------------------------------------------------------------------------
@@ -85,10 +87,86 @@ int launch_layout(Handle* h, const float* in, float* out, long long T, int C, in
 // VS=(P+1)^2.  In this linear space every tap (dy,dx) is the constant row shift dy*(P+1)+dx, so the
 // nine taps are nine descriptor offsets into ONE staged copy of the inputs (no im2col).
 // A CTA computes 128 consecutive positions; pad positions are computed and discarded (6% at P=32).
+//
+// Fusion of conv_init0 (LFT.py:23-25,65): with `lr` set, the input window of the FIRST conv of the stack is
+// conv_init0(lr) evaluated on the fly (9 taps x 64 channels per staged position, same fma order as k_conv0), and the
+// residual of the LAST conv (`buffer = conv_init(buffer) + buffer`, LFT.py:66) is recomputed the same way instead of
+// being read back -- the [T,64] conv_init0 tensor never exists in HBM.
+struct W0Tab { float w[64 * 9]; };  // conv_init0.0.weight [c][tap] (constant bank)
+
+// the 9 taps of view `v` (= b*A*A + u*A + vv) at (y, x), zero padded per view
+LFT_DEVINL void conv0_taps(const float* __restrict__ lr, int A, int P, unsigned v, int y, int x, float* t) {
+  const unsigned NA = (unsigned)(A * A);
+  const unsigned b = v / NA, a = v - b * NA;
+  const int u = (int)a / A, vv = (int)a - u * A;
+  const int W = A * P;
+  const float* img = lr + (long long)b * W * W + (long long)(u * P) * W + vv * P;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      t[ky * 3 + kx] = (yy >= 0 && yy < P && xx >= 0 && xx < P) ? __ldg(img + (long long)yy * W + xx) : 0.f;
+    }
+}
+template <int C0, int NC>
+LFT_DEVINL void conv0_channels(const W0Tab& w0, const float* t, float* o) {  // channels C0 .. C0+NC-1 (compile-time indices)
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s = fmaf(w0.w[(C0 + j) * 9 + k], t[k], s);
+    o[j] = s;
+  }
+}
+
+// conv_stage_window with conv_init0 computed in place of the loads
+LFT_DEVINL void conv_stage_window_lr(const float* __restrict__ lr, const W0Tab& w0, int A, uint32_t a_hi, uint32_t a_lo,
+                                     long long g0, long long G, long long VS, int P, int tid, bool fp32_mode) {
+  const int P1 = P + 1;
+  for (int r = tid; r < kConvRows; r += kRowThreads2) {
+    const long long g = g0 - kConvOff + r;
+    bool inside = false;
+    unsigned v = 0;
+    int y = 0, x = 0;
+    if (g >= 0 && g < G) {
+      const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
+      v = gu / vsu;
+      const int qq = (int)(gu - v * vsu);
+      y = qq / P1;
+      x = qq - y * P1;
+      inside = (y < P && x < P);
+    }
+    float t[9];
+    if (inside) {
+      conv0_taps(lr, A, P, v, y, x, t);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) t[k] = 0.f;  // pad positions: zero feature vector
+    }
+    auto put = [&](int kc, const float* f) {
+      uint4 hi, lo;
+      split8(f, hi, lo, fp32_mode);
+      st_shared_v4(a_hi + kc * (kConvRows * 16) + r * 16, hi);
+      if (fp32_mode) st_shared_v4(a_lo + kc * (kConvRows * 16) + r * 16, lo);
+    };
+    float f[8];
+    conv0_channels<0, 8>(w0, t, f);  put(0, f);
+    conv0_channels<8, 8>(w0, t, f);  put(1, f);
+    conv0_channels<16, 8>(w0, t, f); put(2, f);
+    conv0_channels<24, 8>(w0, t, f); put(3, f);
+    conv0_channels<32, 8>(w0, t, f); put(4, f);
+    conv0_channels<40, 8>(w0, t, f); put(5, f);
+    conv0_channels<48, 8>(w0, t, f); put(6, f);
+    conv0_channels<56, 8>(w0, t, f); put(7, f);
+  }
+}
+
 template <int N>
 __global__ void __launch_bounds__(kThreads2, 2)
 k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* __restrict__ out,
-          const float* __restrict__ res, int V, int P, int passes, int epi) {
+          const float* __restrict__ res, int V, int P, int passes, int epi, const float* __restrict__ lr,
+          const __grid_constant__ W0Tab w0, int A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NST = 3;
   constexpr uint32_t STAGE = N * 128;
@@ -124,7 +202,10 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
     umma_commit_elected(mma_done);
   } else {
     // ---- stage the input window: rows r <-> positions g0 - kConvOff + r, lanes <-> rows
-    conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
+    if (N == 64 && in == nullptr)
+      conv_stage_window_lr(lr, w0, A, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
+    else
+      conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
     fence_proxy_async_smem();
     mbar_arrive(a_ready);
 
@@ -133,15 +214,22 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
     constexpr int HC = N / 2;  // own columns
     const long long g = g0 + m;
     long long tok = -1;
+    float4 r4[HC / 4];
     if (g < G) {
       const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
       const unsigned v = gu / vsu;
       const int qq = (int)(gu - v * vsu);
       const int y = qq / P1, x = qq - y * P1;
       if (y < P && x < P) tok = (long long)((v * P + y) * P + x);
+      if (N == 64 && (epi & 2) && res == nullptr && tok >= 0) {  // residual = conv_init0(lr), own 32 channels
+        float t[9];
+        conv0_taps(lr, A, P, v, y, x, t);
+        float* rr = reinterpret_cast<float*>(r4);
+        if (q == 0) conv0_channels<0, 32>(w0, t, rr);
+        else conv0_channels<32, 32>(w0, t, rr);
+      }
     }
-    float4 r4[HC / 4];
-    if ((epi & 2) && tok >= 0) {
+    if ((epi & 2) && res != nullptr && tok >= 0) {
 #pragma unroll
       for (int i = 0; i < HC / 4; ++i)
         r4[i] = __ldg(reinterpret_cast<const float4*>(res + t32_off(tok, q * (HC / 4) + i, N / 4)));
@@ -361,15 +449,21 @@ int launch_conv0(Handle* h, const float* lr, float* out, int B, int P, cudaStrea
   return sc.finish();
 }
 
+// in == nullptr: the input is conv_init0(lr) computed on the fly; (epi & 2) with res == nullptr: so is the residual.
 int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* out, const float* res, int V, int P,
-                   int epi, cudaStream_t st) {
+                   int epi, const float* lr, cudaStream_t st) {
   const long long G = (long long)V * (P + 1) * (P + 1);
   const unsigned grid = (unsigned)((G + 127) / 128);
+  if ((in == nullptr || ((epi & 2) && res == nullptr)) && (N != 64 || lr == nullptr))
+    return fail(LFT_ERR_ARG, "launch_conv3x3: fused conv_init0 needs N == 64 and the LR mosaic");
+  W0Tab w0;
+  memcpy(w0.w, h->w_conv0_host.data(), sizeof(w0.w));
   Scope sc(h, N == 64 ? K_CONV64 : K_CONV128, st);
   if (N == 64)
-    k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi);
+    k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res);
   else
-    k_conv3x3<128><<<grid, kThreads2, kSmemConv128, st>>>(in, wp, out, res, V, P, h->passes(), epi);
+    k_conv3x3<128><<<grid, kThreads2, kSmemConv128, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0,
+                                                           h->cfg.ang_res);
   return sc.finish();
 }
 

@@ -177,40 +177,50 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     mbar_wait(mma_done, 1);
     tc_fence_after();
     LFT_TL2(4);
-#pragma unroll 2
-    for (int c = 0; c < 4; ++c) {
-      float d[16];
-      const int col = 64 * q + 16 * c;
-      tmem_ld16(trow + col, d);
+    {
+      float dd[64];  // all four accumulator loads in flight, one wait
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 uv = tab4[col / 4 + j], cv = tab4[64 + col / 4 + j];
-        d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
-        d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
-        d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
-        d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dd + 16 * c);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float* d = dd + 16 * c;
+        const int col = 64 * q + 16 * c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 uv = tab4[col / 4 + j], cv = tab4[64 + col / 4 + j];
+          d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
+          d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
+          d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
+          d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
+        }
+        if (ok) planar_store16(Q, v, 4 * q + c, y, x, P, d);
       }
-      if (ok) planar_store16(Q, v, 4 * q + c, y, x, P, d);
     }
     tc_fence_before();
     mbar_arrive(a_ready);
     LFT_TL2(5);
     mbar_wait(mma_done, 0);
     tc_fence_after();
-#pragma unroll 2
-    for (int c = 0; c < 4; ++c) {
-      float d[16];
-      const int col = 64 * q + 16 * c;
-      tmem_ld16(trow + col, d);
+    {
+      float dd[64];  // all four accumulator loads in flight, one wait
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 uv = tab4[32 + col / 4 + j], cv = tab4[96 + col / 4 + j];
-        d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
-        d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
-        d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
-        d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dd + 16 * c);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float* d = dd + 16 * c;
+        const int col = 64 * q + 16 * c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 uv = tab4[32 + col / 4 + j], cv = tab4[96 + col / 4 + j];
+          d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
+          d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
+          d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
+          d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
+        }
+        if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
       }
-      if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
     }
     tc_fence_before();
     mbar_arrive(a_ready);
@@ -536,10 +546,13 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
 
     // phase 2: hidden[:, :128] (own 64 columns of D[0,128)) -> A
     await();
-#pragma unroll 2
+    float dh[64];  // all four accumulator loads in flight, one wait
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dh + 16 * c);
+    tmem_wait_ld();
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
-      float d[16];
-      tmem_ld16(trow + 64 * q + 16 * c, d);
+      float* d = dh + 16 * c;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 uv = u1[16 * q + 4 * c + j], cv = c1[16 * q + 4 * c + j];

@@ -45,10 +45,10 @@ int run_conv_init(Handle* h, const float* lr, float* out, float* tmp0, float* tm
   const long long T = (long long)V * P * P;
   (void)T;
   int rc;
-  if ((rc = launch_conv0(h, lr, tmp0, B, P, st))) return rc;
-  if ((rc = launch_conv3x3(h, 64, tmp0, h->w_conv[0], tmp1, nullptr, V, P, 1, st))) return rc;
-  if ((rc = launch_conv3x3(h, 64, tmp1, h->w_conv[1], tmp2, nullptr, V, P, 1, st))) return rc;
-  if ((rc = launch_conv3x3(h, 64, tmp2, h->w_conv[2], out, tmp0, V, P, 3, st))) return rc;
+  (void)tmp0;  // conv_init0 is fused into the first conv's loader and the last conv's residual (never materialised)
+  if ((rc = launch_conv3x3(h, 64, nullptr, h->w_conv[0], tmp1, nullptr, V, P, 1, lr, st))) return rc;
+  if ((rc = launch_conv3x3(h, 64, tmp1, h->w_conv[1], tmp2, nullptr, V, P, 1, lr, st))) return rc;
+  if ((rc = launch_conv3x3(h, 64, tmp2, h->w_conv[2], out, nullptr, V, P, 3, lr, st))) return rc;
   return 0;
 }
 

@@ -260,5 +260,5 @@ def test_profile_and_launch_count():
     torch.cuda.synchronize()
     prof = eng.profile_read()
     eng.profile_enable(False)
-    assert eng.launch_count() - n0 == 4 + 4 * 4 + 2   # conv0 + 3 conv, 4 x (ang, embed+qkv, attn, ffn), up gemm + gather
+    assert eng.launch_count() - n0 == 3 + 4 * 4 + 2   # 3 conv (conv_init0 fused), 4 x (ang, embed+qkv, attn, ffn), up gemm + gather
     assert prof["ang_fused"]["launches"] == 4 and prof["spa_ffn"]["ms"] > 0
