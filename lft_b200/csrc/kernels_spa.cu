@@ -423,6 +423,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
   const uint32_t ring = A + 65536;
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
+  const uint32_t hb_ready = smem_u32(&ctl->aux[0]);  // 256 arrivals, used once per CTA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   LFT_TL(30);
   cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
@@ -461,8 +462,14 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
     };
     wait_a(); gemm_ts(g_o, 0, true); done();                               // D[0,128)   = O Wo^T                    (TS)
     wait_a(); gemm(g_1a, 0, true); gemm(g_1b, 128, true); done();          // D[0,256)   = Y1 W'1^T  (both halves)   (SS)
-    wait_a(); gemm(g_2a, 0, true); done();                                 // D[0,128)   = relu(.)[:, :128] W2a^T    (SS)
-    wait_a(); gemm_ts(g_2b, 0, false); done();                             // D[0,128)  += relu(.)[:, 128:] W2b^T    (TS)
+    wait_a(); gemm(g_2a, 0, true);                                         // D[0,128)   = relu(.)[:, :128] W2a^T    (SS)
+    // hidden[:, 128:] is published on its OWN barrier: the row owners reach that arrival without an intervening wait, so on
+    // a_ready a fast warp's second arrival would be counted into the phase slower warps have not finished (FFN2a would
+    // start on a half-written operand)
+    mbar_wait(hb_ready, 0);
+    tc_fence_after();
+    LFT_TL(tl); ++tl;
+    gemm_ts(g_2b, 0, false); done();                                       // D[0,128)  += relu(.)[:, 128:] W2b^T    (TS); ONE commit for FFN2a+b
     wait_a(); gemm_ts(g_l, 0, true); done();                               // D[0,64)    = Y2 Wlin^T                 (TS)
   } else {
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
@@ -586,8 +593,10 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
 #pragma unroll
       for (int c = 0; c < 4; ++c) a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, hb + 16 * c, fp32m);
     }
-    publish_tmem();
-    await();  // FFN2a done (keeps the mma_done phases in step)
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(hb_ready);  // NOT a_ready: no wait separates this arrival from the previous one (see the MMA warp)
+    LFT_TL(tl); ++tl;
 
     // phase 4: Y2 = Y1 (spilled row, prefetched) + D[0,128) -> A
     {

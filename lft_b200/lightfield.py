@@ -90,3 +90,66 @@ class LightFieldSR:
         sr = torch.empty(A * h0 * s, A * w0 * s, dtype=torch.float32, device=lr_sai.device)
         eng.integrate(allc, h0, w0, 0, nu * nv, sr)
         return sr
+
+
+class HostPipeline:
+    """Streams light fields pinned host -> device -> SR -> pinned host with the copies overlapped with compute:
+    the H2D of light field i+1 and the D2H of light field i run on a side stream while the kernels of the other one
+    run on the caller's stream (`depth` device slots).  What test.py's loop does per scene with `.to(device)` /
+    `.cpu()` (test.py:94-95), without the stalls.
+
+        pipe = HostPipeline(net)                       # net = lft_b200.model.get_model(args) or an Engine
+        for lr_host, sr_host in zip(inputs, outputs):  # pinned CPU tensors [A*h0, A*w0] / [A*h0*s, A*w0*s]
+            pipe.submit(lr_host, sr_host)
+        pipe.drain()                                   # the current stream now waits for every output copy
+    """
+
+    def __init__(self, net_or_engine, depth: int = 2, max_ws_bytes: Optional[int] = None):
+        self._sr = LightFieldSR(net_or_engine, max_ws_bytes)
+        self._depth = depth
+        self._slots: List[dict] = []
+        self._copy: Optional[torch.cuda.Stream] = None
+        self._i = 0
+
+    def _slot(self, device) -> dict:
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(device=device)
+            self._slots = [dict(lr=None, sr=None, h2d=torch.cuda.Event(), done=None, d2h=None) for _ in range(self._depth)]
+        s = self._slots[self._i % self._depth]
+        self._i += 1
+        return s
+
+    @torch.no_grad()
+    def submit(self, lr_host: torch.Tensor, sr_host: torch.Tensor, device=None) -> torch.cuda.Event:
+        if lr_host.is_cuda or sr_host.is_cuda or not (lr_host.is_pinned() and sr_host.is_pinned()):
+            raise ValueError("HostPipeline.submit expects pinned host tensors")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        slot = self._slot(device)
+        main = torch.cuda.current_stream(device)
+        if slot["lr"] is None or slot["lr"].shape != lr_host.shape:
+            slot["lr"] = torch.empty(lr_host.shape, dtype=torch.float32, device=device)
+        with torch.cuda.stream(self._copy):
+            if slot["done"] is not None:
+                self._copy.wait_event(slot["done"])     # the kernels that read this slot's LR buffer have finished
+            else:
+                self._copy.wait_stream(main)            # first use: the buffer allocation is ordered on `main`
+            slot["lr"].copy_(lr_host, non_blocking=True)
+            slot["h2d"].record(self._copy)
+        main.wait_event(slot["h2d"])
+        if slot["d2h"] is not None:
+            main.wait_event(slot["d2h"])                # the slot's previous result has left the device
+        sr = self._sr(slot["lr"])
+        slot["sr"] = sr                                  # keep alive until the slot is reused
+        slot["done"] = torch.cuda.Event()
+        slot["done"].record(main)
+        with torch.cuda.stream(self._copy):
+            self._copy.wait_event(slot["done"])
+            sr_host.copy_(sr, non_blocking=True)
+            slot["d2h"] = torch.cuda.Event()
+            slot["d2h"].record(self._copy)
+        return slot["d2h"]
+
+    def drain(self) -> None:
+        """Make the current stream wait for every outstanding device->host copy."""
+        if self._copy is not None:
+            torch.cuda.current_stream(self._copy.device).wait_stream(self._copy)
