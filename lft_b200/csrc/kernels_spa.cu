@@ -69,6 +69,12 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
   const long long g0 = (long long)blockIdx.x * 128;
   LFT_TL2(20);
   cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
+  const uint32_t k_done = smem_u32(&ctl->aux[1]);  // completed by one tcgen05.commit (K accumulator full)
+  if (tid == 0) {
+    mbar_init(k_done, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
   const uint32_t tmem = ctl->tmem;
   const GemmPhase g_c{wmlp, 128, 9}, g_q{wq, 128, 2}, g_k{wk, 128, 2}, g_v{wv, 128, 2};
 
@@ -90,24 +96,25 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
                               c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
     umma_commit_elected(mma_done);
     LFT_TL2(11);
-    // Q, K, V: A operand z = tok + PE_s lives in TMEM columns [128,256) (hi | lo), written by the row owners (TS form)
-    const uint32_t ta_hi = tmem + 128, ta_lo = tmem + 192;
+    // Q, K, V: SS form from the smem operand z = tok + PE_s (the conv staging area is dead by now), two accumulators:
+    // Q -> D0 [0,128), K -> D1 [128,256) issued back to back, V -> D0 once the row owners have drained Q.  The Q and K
+    // epilogues run under the K and V MMAs.
     mbar_wait(a_ready, 1);
     tc_fence_after();
     LFT_TL2(12);
-    ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, ta_hi, ta_lo, tmem + 0, true);
+    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
+                              tmem + 0, true);
     umma_commit_elected(mma_done);
     LFT_TL2(13);
-    mbar_wait(a_ready, 0);
-    tc_fence_after();
-    LFT_TL2(14);
-    ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, ta_hi, ta_lo, tmem + 0, true);
-    umma_commit_elected(mma_done);
+    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
+                              tmem + 128, true);
+    umma_commit_elected(k_done);
     LFT_TL2(15);
-    mbar_wait(a_ready, 1);
+    mbar_wait(a_ready, 0);  // D0 drained
     tc_fence_after();
     LFT_TL2(16);
-    ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, ta_hi, ta_lo, tmem + 0, true);
+    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
+                              tmem + 0, true);
     umma_commit_elected(mma_done);
     LFT_TL2(17);
   } else {
@@ -161,12 +168,12 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) z[16 * c + i] += t[i];
-        a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, z + 16 * c, passes == 3);
+        a_store16(A, 8 * q + 2 * c, m, z + 16 * c, passes == 3);
       }
       // mailbox in this thread's own (already consumed) accumulator columns
       pair_ln_stats<64>(z, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
     }
-    tmem_wait_st();
+    fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(a_ready);
     LFT_TL2(3);
@@ -198,14 +205,14 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       }
     }
     tc_fence_before();
-    mbar_arrive(a_ready);
+    mbar_arrive(a_ready);  // D0 drained: V may overwrite it
     LFT_TL2(5);
-    mbar_wait(mma_done, 0);
+    mbar_wait(k_done, 0);
     tc_fence_after();
     {
       float dd[64];  // all four accumulator loads in flight, one wait
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dd + 16 * c);
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 128 + 64 * q + 16 * c, dd + 16 * c);
       tmem_wait_ld();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -222,15 +229,13 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
         if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
       }
     }
-    tc_fence_before();
-    mbar_arrive(a_ready);
     // ---- phase 3: V = D - PE_s Wv^T  (table prefetched before the wait)
     {
       float4 pv[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) pv[i] = __ldg(reinterpret_cast<const float4*>(pev) + (long long)(16 * q + i) * PP + p);
       LFT_TL2(6);
-      mbar_wait(mma_done, 1);
+      mbar_wait(mma_done, 0);
       tc_fence_after();
       LFT_TL2(7);
 #pragma unroll
