@@ -268,19 +268,39 @@ struct GemmPhase {
 
 // Producer side of one GEMM phase (called by ALL lanes of the producer warp). `passes` = 3 (fp32 via hi/lo) or 1
 // (bf16: hi slabs only).
+#ifdef LFT_TIMELINE
+// producer timeline of the middle CTA (debug): [kind][slab][0: before the empty wait, 1: after it, 2: after the copy issue]
+static __device__ long long g_ring_tl[4][40][3];
+static __device__ int g_ring_tl_n[4];
+#endif
 template <int NST>
 LFT_DEVINL void ring_produce(RingState<NST>& rs, uint32_t ring_base, uint32_t stage_bytes, uint32_t full0,
-                             uint32_t empty0, const GemmPhase& g, int passes) {
+                             uint32_t empty0, const GemmPhase& g, int passes, int tlk = -1, int* tln = nullptr) {
   const uint32_t slab = g.N * 128u;
   for (uint32_t ks = 0; ks < g.kslabs; ++ks) {
     const int nparts = passes == 3 ? 2 : 1;
     for (int part = 0; part < nparts; ++part) {
+#ifdef LFT_TIMELINE
+      const bool rec = tlk >= 0 && tln && blockIdx.x == gridDim.x / 2 && (threadIdx.x & 31) == 0 && *tln < 40;
+      if (rec) g_ring_tl[tlk][*tln][0] = clock64();
+#endif
       mbar_wait(empty0 + 8u * rs.stage, rs.phase ^ 1u);
+#ifdef LFT_TIMELINE
+      if (rec) g_ring_tl[tlk][*tln][1] = clock64();
+#endif
       if (elect_one()) {
+#ifdef LFT_EXPERIMENT_NOSTREAM  // timing experiment only (wrong results): how much does weight streaming cost?
+        mbar_arrive(full0 + 8u * rs.stage);
+#else
         mbar_arrive_expect_tx(full0 + 8u * rs.stage, slab);
         bulk_g2s(ring_base + rs.stage * stage_bytes, g.w + (size_t)(ks * 2 + part) * slab, slab, full0 + 8u * rs.stage);
+#endif
       }
       __syncwarp();
+#ifdef LFT_TIMELINE
+      if (rec) { g_ring_tl[tlk][*tln][2] = clock64(); g_ring_tl_n[tlk] = *tln + 1; }
+      if (tln) ++*tln;
+#endif
       rs.advance();
     }
   }
@@ -313,37 +333,43 @@ LFT_DEVINL void ring_consume_mma(RingState<NST>& rs, uint32_t ring_base, uint32_
     // field (callers keep >= kConvOff rows of headroom, so it never borrows from the LBO field)
     const uint32_t a_off = (uint32_t)((int)((ks * a_kslab_stride) >> 4) + sh);
     const uint32_t ah = ahi0 + a_off, al = alo0 + a_off;
-    // hi weights: A_hi*W_hi (+ A_lo*W_hi)
-    mbar_wait(full0 + 8u * rs.stage, rs.phase);
-    tc_fence_after();
-    uint32_t b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
-    if (elect_one()) {
-#pragma unroll
-      for (uint32_t j = 0; j < 4; ++j)
-        umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), idesc, j ? 1u : acc);
-      if (passes == 3) {
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j)
-          umma_bf16(d_tmem, umma_desc_from(al + j * a_step), umma_desc_from(b0 + j * b_step), idesc, 1u);
-      }
-      umma_commit(empty0 + 8u * rs.stage);
-    }
-    __syncwarp();
-    acc = 1u;
+    // The issuing thread pays ~250 cycles of bookkeeping per wait / elect / commit round (measured), as much as 4 MMAs:
+    // in fp32 mode the hi and the lo slab of a k block are therefore waited for together and their 12 MMAs
+    // (A_hi*W_hi, A_lo*W_hi | A_hi*W_lo) go out in ONE elected region, each stage still released by its own commit.
+    const uint32_t st_hi = rs.stage, ph_hi = rs.phase;
     rs.advance();
-    if (passes == 3) {  // lo weights: A_hi*W_lo
-      mbar_wait(full0 + 8u * rs.stage, rs.phase);
+    mbar_wait(full0 + 8u * st_hi, ph_hi);
+    const uint32_t bh = umma_desc_lo(ring_base + st_hi * stage_bytes, b_lbo);
+    if (passes == 3) {
+      const uint32_t st_lo = rs.stage, ph_lo = rs.phase;
+      rs.advance();
+      mbar_wait(full0 + 8u * st_lo, ph_lo);
       tc_fence_after();
-      b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
+      const uint32_t bl = umma_desc_lo(ring_base + st_lo * stage_bytes, b_lbo);
       if (elect_one()) {
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j)
-          umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), idesc, 1u);
-        umma_commit(empty0 + 8u * rs.stage);
+          umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(bh + j * b_step), idesc, j ? 1u : acc);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16(d_tmem, umma_desc_from(al + j * a_step), umma_desc_from(bh + j * b_step), idesc, 1u);
+        umma_commit(empty0 + 8u * st_hi);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(bl + j * b_step), idesc, 1u);
+        umma_commit(empty0 + 8u * st_lo);
       }
-      __syncwarp();
-      rs.advance();
+    } else {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16(d_tmem, umma_desc_from(ah + j * a_step), umma_desc_from(bh + j * b_step), idesc, j ? 1u : acc);
+        umma_commit(empty0 + 8u * st_hi);
+      }
     }
+    __syncwarp();
+    acc = 1u;
   }
 }
 
@@ -392,36 +418,40 @@ LFT_DEVINL void ring_consume_mma_ts(RingState<NST>& rs, uint32_t ring_base, uint
   const uint32_t b_lbo = g.N * 16u, b_step = (2u * b_lbo) >> 4;
   uint32_t acc = fresh ? 0u : 1u;
   for (uint32_t ks = 0; ks < g.kslabs; ++ks) {
-    mbar_wait(full0 + 8u * rs.stage, rs.phase);
-    tc_fence_after();
-    uint32_t b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
-    if (elect_one()) {
-#pragma unroll
-      for (uint32_t j = 0; j < 4; ++j)
-        umma_bf16_ts(d_tmem, ta_hi + ks * 32 + j * 8, umma_desc_from(b0 + j * b_step), idesc, j ? 1u : acc);
-      if (passes == 3) {
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j)
-          umma_bf16_ts(d_tmem, ta_lo + ks * 32 + j * 8, umma_desc_from(b0 + j * b_step), idesc, 1u);
-      }
-      umma_commit(empty0 + 8u * rs.stage);
-    }
-    __syncwarp();
-    acc = 1u;
+    const uint32_t st_hi = rs.stage, ph_hi = rs.phase;  // hi and lo slab in one round, see ring_consume_mma
     rs.advance();
+    mbar_wait(full0 + 8u * st_hi, ph_hi);
+    const uint32_t bh = umma_desc_lo(ring_base + st_hi * stage_bytes, b_lbo);
     if (passes == 3) {
-      mbar_wait(full0 + 8u * rs.stage, rs.phase);
+      const uint32_t st_lo = rs.stage, ph_lo = rs.phase;
+      rs.advance();
+      mbar_wait(full0 + 8u * st_lo, ph_lo);
       tc_fence_after();
-      b0 = umma_desc_lo(ring_base + rs.stage * stage_bytes, b_lbo);
+      const uint32_t bl = umma_desc_lo(ring_base + st_lo * stage_bytes, b_lbo);
       if (elect_one()) {
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j)
-          umma_bf16_ts(d_tmem, ta_hi + ks * 32 + j * 8, umma_desc_from(b0 + j * b_step), idesc, 1u);
-        umma_commit(empty0 + 8u * rs.stage);
+          umma_bf16_ts(d_tmem, ta_hi + ks * 32 + j * 8, umma_desc_from(bh + j * b_step), idesc, j ? 1u : acc);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16_ts(d_tmem, ta_lo + ks * 32 + j * 8, umma_desc_from(bh + j * b_step), idesc, 1u);
+        umma_commit(empty0 + 8u * st_hi);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16_ts(d_tmem, ta_hi + ks * 32 + j * 8, umma_desc_from(bl + j * b_step), idesc, 1u);
+        umma_commit(empty0 + 8u * st_lo);
       }
-      __syncwarp();
-      rs.advance();
+    } else {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          umma_bf16_ts(d_tmem, ta_hi + ks * 32 + j * 8, umma_desc_from(bh + j * b_step), idesc, j ? 1u : acc);
+        umma_commit(empty0 + 8u * st_hi);
+      }
     }
+    __syncwarp();
+    acc = 1u;
   }
 }
 

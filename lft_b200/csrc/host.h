@@ -119,6 +119,7 @@ int configure_up();
 int debug_timeline_spa(long long* out);
 int debug_timeline_ang(long long* out);
 int debug_timeline_embed(long long* out);
+int debug_timeline_ring_embed(long long* out);
 int launch_conv0(Handle* h, const float* lr, float* out, int B, int P, cudaStream_t st);
 int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* out, const float* res, int V, int P,
                    int epi, const float* lr, cudaStream_t st);

@@ -15,8 +15,8 @@ constexpr int kConvRows = 201;  // odd: k-chunk planes start in different banks
 constexpr int kConvOff = 36;
 
 struct Ctl {
-  uint64_t full[4];
-  uint64_t empty[4];
+  uint64_t full[8];
+  uint64_t empty[8];
   uint64_t a_ready;
   uint64_t mma_done;
   uint64_t aux[4];

@@ -377,12 +377,13 @@ k_gemm_selftest(const float* __restrict__ A, int K, const uint8_t* __restrict__ 
 
 // Micro-benchmark: issue `reps` x (K/16) MMAs of shape 128 x N x 16 back to back on resident operands (no ring, no
 // row owners) and report clock64 cycles per MMA.  mode 0: A and B from shared memory; mode 1: A from TMEM.
-__global__ void __launch_bounds__(64, 2) k_mma_bench(int N, int K, int reps, int mode, long long* out, int pad_smem) {
+template <int mode>
+__global__ void __launch_bounds__(64, 2) k_mma_bench(int N, int K, int reps, long long* out, int pad_smem) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tslot;
   const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); mbar_fence_init(); }
   if (warp == 1) tmem_alloc(smem_u32(&tslot), 256);
   for (int i = threadIdx.x; i < (128 * K * 2 + N * K * 2) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   fence_proxy_async_smem();
@@ -394,16 +395,51 @@ __global__ void __launch_bounds__(64, 2) k_mma_bench(int N, int K, int reps, int
     const uint32_t a_lbo = 128 * 16, b_lbo = N * 16;
     const uint32_t a0 = umma_desc_lo(smem_u32(smem), a_lbo), b0 = umma_desc_lo(smem_u32(smem) + 128 * K * 2, b_lbo);
     const uint32_t idesc = umma_idesc_bf16(N);
+    const uint32_t sw0 = smem_u32(smem) >> 4;
+    (void)sw0;
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
+      if constexpr (mode >= 5) {
+        // the 3x3 conv issue pattern on resident operands: per tap 4 x (A_hi, W_hi), 4 x (A_lo, W_hi), 4 x (A_hi, W_lo); A rows
+        // shifted per tap; mode 5: k-chunk stride 201 rows (3216 B), mode 6: 208 rows (3328 B = 26 x 128), mode 7: no shifts
+        constexpr uint32_t rows = mode == 6 ? 208u : 201u;
+        const uint32_t lbo = rows * 16u, astep = (2u * lbo) >> 4, bstep = (2u * b_lbo) >> 4;
+        const uint32_t ahi = umma_desc_lo(smem_u32(smem) + 36 * 16, lbo), alo = umma_desc_lo(smem_u32(smem) + rows * 128 + 36 * 16, lbo);
+        const uint32_t bb = umma_desc_lo(smem_u32(smem) + 2 * rows * 128, b_lbo);
+        if (elect_one()) {
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            const int sh = mode == 7 ? 0 : (t / 3 - 1) * 33 + (t % 3 - 1);
+            const uint32_t ah = ahi + (uint32_t)sh, al = alo + (uint32_t)sh;
+            const uint32_t bh = bb + (uint32_t)((2 * t) % 3) * (N * 128u >> 4), bl = bb + (uint32_t)((2 * t + 1) % 3) * (N * 128u >> 4);
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) umma_bf16(tmem, umma_desc_from(ah + j * astep), umma_desc_from(bh + j * bstep), idesc, 1u);
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) umma_bf16(tmem, umma_desc_from(al + j * astep), umma_desc_from(bh + j * bstep), idesc, 1u);
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) umma_bf16(tmem, umma_desc_from(ah + j * astep), umma_desc_from(bl + j * bstep), idesc, 1u);
+          }
+        }
+        __syncwarp();
+        continue;
+      }
       if (elect_one()) {
         for (int j = 0; j < K / 16; ++j) {
           if (mode == 0)
             umma_bf16(tmem, umma_desc_from(a0 + j * ((2 * a_lbo) >> 4)), umma_desc_from(b0 + j * ((2 * b_lbo) >> 4)), idesc, 1u);
-          else
+          else if (mode == 1)
             umma_bf16_ts(tmem, tmem + 256 - K / 2 + j * 8, umma_desc_from(b0 + j * ((2 * b_lbo) >> 4)), idesc, 1u);
+          else if (mode == 2)  // SS, A start shifted by one 16-byte row (a conv tap with dx = +-1): core matrices straddle 128 B
+            umma_bf16(tmem, umma_desc_from(a0 + 1 + j * ((2 * a_lbo) >> 4)), umma_desc_from(b0 + j * ((2 * b_lbo) >> 4)), idesc, 1u);
+          else {               // SS, A in the SWIZZLE_128B K-major layout (rows of 128 B, 64-wide k slabs); mode 4: shifted by one row
+            constexpr uint32_t sh = mode == 4 ? 1u : 0u;
+            const uint32_t a_lo32 = ((sw0 + sh * 8u + (uint32_t)(j >> 2) * 1024u + (uint32_t)(j & 3) * 2u) & 0x3FFFu) | (1u << 16);
+            constexpr uint32_t a_hi32 = (1024u >> 4) | (1u << 14) | (sh << 17) | (2u << 29);
+            umma_bf16(tmem, ((uint64_t)a_hi32 << 32) | a_lo32, umma_desc_from(b0 + j * ((2 * b_lbo) >> 4)), idesc, 1u);
+          }
         }
       }
+      if (pad_smem > 0 && (r % pad_smem) == pad_smem - 1 && elect_one()) umma_commit(smem_u32(&bar2));  // extra commits
       __syncwarp();
     }
     umma_commit_elected(smem_u32(&bar));
@@ -418,10 +454,21 @@ __global__ void __launch_bounds__(64, 2) k_mma_bench(int N, int K, int reps, int
 }
 
 int launch_mma_bench(int N, int K, int reps, int mode, int grid, int smem_bytes, long long* host_out) {
+  const int commit_every = mode / 16;  // mode = base + 16 * (commit after every n-th group of K/16 MMAs)
+  mode %= 16;
   long long* d = nullptr;
   CUDA_TRY(cudaMalloc(&d, sizeof(long long) * grid));
-  CUDA_TRY(cudaFuncSetAttribute(k_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  k_mma_bench<<<grid, 64, smem_bytes>>>(N, K, reps, mode, d, 0);
+#define LFT_MMA_BENCH(M)                                                                                  \
+  case M:                                                                                                 \
+    CUDA_TRY(cudaFuncSetAttribute(k_mma_bench<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+    k_mma_bench<M><<<grid, 64, smem_bytes>>>(N, K, reps, d, commit_every);                                          \
+    break;
+  switch (mode) {
+    LFT_MMA_BENCH(0) LFT_MMA_BENCH(1) LFT_MMA_BENCH(2) LFT_MMA_BENCH(3) LFT_MMA_BENCH(4) LFT_MMA_BENCH(5) LFT_MMA_BENCH(6)
+    LFT_MMA_BENCH(7)
+    default: cudaFree(d); return fail(LFT_ERR_ARG, "mma bench mode 0..7");
+  }
+#undef LFT_MMA_BENCH
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(host_out, d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));

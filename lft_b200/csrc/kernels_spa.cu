@@ -81,10 +81,11 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
   if (warp == kWarpProducer2) {
 
     RingState<kSpaNST> rs;
-    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes);
-    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes);
-    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes);
-    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes);
+    int tln = 0;
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, 0, &tln);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, 0, &tln);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, 0, &tln);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, 0, &tln);
   } else if (warp == kWarpMma2) {
 
     RingState<kSpaNST> rs;
@@ -649,6 +650,16 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
   LFT_TL(31);
+}
+
+int debug_timeline_ring_embed(long long* out) {  // out[40*3]
+#ifdef LFT_TIMELINE
+  CUDA_TRY(cudaMemcpyFromSymbol(out, g_ring_tl, sizeof(long long) * 120));
+  return 0;
+#else
+  (void)out;
+  return fail(LFT_ERR_STATE, "library built without -DLFT_TIMELINE");
+#endif
 }
 
 int debug_timeline_embed(long long* out) {

@@ -263,6 +263,7 @@ int lft_forward_lf(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, i
 
 int lft_debug_timeline(int32_t which, int64_t* out64) {
   long long* o = reinterpret_cast<long long*>(out64);
+  if (which == 4) return debug_timeline_ring_embed(o);  // needs out64[120]
   return which == 0 ? debug_timeline_spa(o) : (which == 1 ? debug_timeline_ang(o) : debug_timeline_embed(o));
 }
 

@@ -6,7 +6,7 @@ from lft_b200 import capi
 lib = capi.load()
 reps = 200
 for ctas_per_sm, smem in ((1, 150 * 1024), (2, 100 * 1024)):
-    for mode in (0, 1):
+    for mode in (0, 1, 2, 3, 4):
         for N in (64, 128, 256):
             K = 128
             grid = 148 * ctas_per_sm
@@ -14,5 +14,5 @@ for ctas_per_sm, smem in ((1, 150 * 1024), (2, 100 * 1024)):
             capi.check(lib.lft_mma_bench(N, K, reps, mode, grid, smem, buf))
             cyc = np.array(list(buf), dtype=np.float64)
             n_mma = reps * K // 16
-            print(f"ctas/SM {ctas_per_sm} mode {'SS' if mode == 0 else 'TS'} N={N:3d}: {cyc.mean() / n_mma:7.1f} cycles/MMA per CTA "
+            print(f"ctas/SM {ctas_per_sm} mode {('SS', 'TS', 'SS+1row', 'SS sw128', 'SS sw128+1row')[mode]} N={N:3d}: {cyc.mean() / n_mma:7.1f} cycles/MMA per CTA "
                   f"(math floor {128 * N / 256:.0f}) -> per-SM {cyc.mean() / n_mma / ctas_per_sm:6.1f}", flush=True)
