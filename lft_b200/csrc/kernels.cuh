@@ -77,9 +77,16 @@ static __device__ long long g_tl2[2][32];
     if (blockIdx.x == gridDim.x / 2 && (threadIdx.x == 0 || threadIdx.x == 32 * kWarpMma2))          \
       g_tl2[threadIdx.x == 0 ? 0 : 1][s] = clock64();                                               \
   } while (0)
+// per-row-warp marks (lane 0 of every row warp): which = 0/1 selects the table half, slot 22 + warp
+#define LFT_TL2W(which, warp)                                                                       \
+  do {                                                                                              \
+    if (blockIdx.x == gridDim.x / 2 && (threadIdx.x & 31) == 0 && (warp) < 8)                       \
+      g_tl2[which][22 + (warp)] = clock64();                                                        \
+  } while (0)
 #else
 #define LFT_TL(s) do {} while (0)
 #define LFT_TL2(s) do {} while (0)
+#define LFT_TL2W(which, warp) do {} while (0)
 #endif
 
 // "T32" activation layout for [T, C] fp32 tensors: blocks of 32 consecutive tokens, inside a block the

@@ -178,6 +178,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     tc_fence_before();
     mbar_arrive(a_ready);
     LFT_TL2(3);
+    LFT_TL2W(1, warp);
 
     // ---- phase 2: Q then K (one accumulator, TS-form MMAs): affine LN correction in the epilogue
     const float4* tab4 = reinterpret_cast<const float4*>(tab.v);  // [u_q | u_k | c_q | c_k] x 128 (constant bank)
@@ -252,6 +253,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       }
     }
     LFT_TL2(8);
+    LFT_TL2W(0, warp);
     tc_fence_before();
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
