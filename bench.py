@@ -136,10 +136,29 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, ...) write to fd 1 from C, so fd 1 is
+    pointed at stderr for the rest of the process and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -290,7 +309,7 @@ def main():
             v, dt, n, th = cpu_baseline(sd, lf_host.clone(), args.cpu_patches)
             line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": th, "kind": "port",
                                     "sample": f"{n} of 64 patches of the same light field, B=1 per call, {dt:.1f} s (oracle port of test.py:83-99, dense masked attention)"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
