@@ -32,12 +32,13 @@ MP_PER_LF = A * A * H0 * S * W0 * S / 1e6          # 6.5536
 TOKENS_PER_LF = PATCHES * A * A * 32 * 32          # 1,638,400
 # algorithmic FLOP per LR token and launch (window attention at its mean 23.16 keys)
 FLOP_PER_TOKEN = {
-    "conv0": 1152, "conv3x3_64": 73728, "conv3x3_128": 147456, "ang_fused": 71936, "spa_embed_qkv": 147456 + 98304,
+    "conv3x3_64": 73728,   # + conv_init0 (1,152) fused into the first launch
+    "conv3x3_128": 147456, "ang_fused": 71936, "spa_embed_qkv": 147456 + 98304,
     "spa_attn": 11858, "spa_ffn": 180224, "up_gemm": 131072 + 18432, "up_gather": 32 * S * S,
 }
 FLOP_PER_LF = 2411464 * TOKENS_PER_LF              # 3.951 TFLOP
 # algorithmic HBM bytes per token for the bandwidth-bound kernels (fp32 in/out, once each)
-BYTES_PER_TOKEN = {"spa_attn": 4 * 128 * 4, "up_gather": (9 * 16 + 16) * 4, "conv0": 4 + 256}
+BYTES_PER_TOKEN = {"spa_attn": 4 * 128 * 4, "up_gather": (9 * 16 + 16) * 4}
 TENSOR_KINDS = {"conv3x3_64", "conv3x3_128", "ang_fused", "spa_embed_qkv", "spa_ffn", "up_gemm"}
 
 

@@ -134,8 +134,7 @@ static int finalize(Handle* h) {
   {
     const float* w = W("conv_init0.0.weight");
     std::vector<float> v(w, w + 576);
-    if ((rc = upload_f32(h, v, &h->w_conv0))) return rc;
-    h->w_conv0_host = v;
+    h->w_conv0_host = v;  // kernel parameter (constant bank) of the first / last conv of the stack
   }
   // conv weights [N][C][ky][kx] -> tap-major K: k = tap*64 + c
   auto conv_pack = [&](const float* w, int N, const uint8_t** dst) {

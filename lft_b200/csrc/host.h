@@ -65,7 +65,6 @@ struct Handle {
   std::map<std::string, std::vector<float>> host_w;
   bool finalized = false;
   std::vector<void*> allocs;
-  const float* w_conv0 = nullptr;
   std::vector<float> w_conv0_host;  // conv_init0 weight [64][9] (kernel parameter of the fused first/last conv)
   const uint8_t* w_conv[3] = {nullptr, nullptr, nullptr};
   Layer layer[kLayers];
@@ -120,7 +119,6 @@ int debug_timeline_spa(long long* out);
 int debug_timeline_ang(long long* out);
 int debug_timeline_embed(long long* out);
 int debug_timeline_ring_embed(long long* out);
-int launch_conv0(Handle* h, const float* lr, float* out, int B, int P, cudaStream_t st);
 int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* out, const float* res, int V, int P,
                    int epi, const float* lr, cudaStream_t st);
 int launch_layout(Handle* h, const float* in, float* out, long long T, int C, int to_t32, cudaStream_t st);

@@ -1,4 +1,5 @@
-// conv_init0 (CUDA cores), the 3x3 implicit-GEMM convolution (tcgen05) and the GEMM self-test kernel.
+// The 3x3 implicit-GEMM convolution (tcgen05) with conv_init0 fused in (CUDA cores), the layout converter and the
+// GEMM self-test / MMA micro-benchmark kernels.
 // Reference semantics: model/LFT.py:23-33,65-66 (conv stack) and LFT.py:164-169 (SpaTrans.SAI2Token:
 // unfold 3x3 + Linear == zero-padded 3x3 conv 64->128).
 #include "host.h"
@@ -7,49 +8,6 @@
 #include <cstring>
 
 namespace lft {
-
-// ------------------------------------------------------------------------------------------------
-// conv_init0: Conv3d(1->64,(1,3,3),pad(0,1,1)) on the LR SAI mosaic, zero padded PER VIEW.
-// in : lr [B,1,A*P,A*P] fp32 (view (u,v) at rows u*P.., cols v*P..)   out: feat [T,64] fp32, T32 layout
-// One thread = one token x 4 channels; consecutive threads = consecutive tokens (512 B coalesced stores).
-__global__ void __launch_bounds__(256) k_conv0(const float* __restrict__ lr, const float* __restrict__ w0,
-                                              float* __restrict__ out, int B, int A, int P) {
-  __shared__ float sw[64 * 9];
-  for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i] = w0[i];
-  __syncthreads();
-  const long long T = (long long)B * A * A * P * P;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long tok = ((gid >> 9) << 5) + (gid & 31);  // 512 threads per 32-token block
-  const int cg = (int)((gid >> 5) & 15);
-  if (tok >= T) return;
-  const unsigned tu = (unsigned)tok, Pu = (unsigned)P, PPu = Pu * Pu, NAu = (unsigned)(A * A);  // T < 2^31
-  const int x = (int)(tu % Pu);
-  const int y = (int)((tu / Pu) % Pu);
-  const int a = (int)((tu / PPu) % NAu);
-  const int b = (int)(tu / (PPu * NAu));
-  const int u = a / A, v = a % A;
-  const int W = A * P;
-  const float* img = lr + (long long)b * W * W + (long long)(u * P) * W + v * P;
-  float t[9];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int yy = y + ky - 1, xx = x + kx - 1;
-      t[ky * 3 + kx] = (yy >= 0 && yy < P && xx >= 0 && xx < P) ? __ldg(img + (long long)yy * W + xx) : 0.f;
-    }
-  float4 o;
-  float* op = reinterpret_cast<float*>(&o);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float* w = sw + (cg * 4 + j) * 9;
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s = fmaf(w[k], t[k], s);
-    op[j] = s;
-  }
-  *reinterpret_cast<float4*>(out + t32_off(tok, cg, 16)) = o;
-}
 
 // ------------------------------------------------------------------------------------------------
 // Layout conversion for the stage-level entry points: channels-last [T][C] <-> T32.
@@ -89,7 +47,7 @@ int launch_layout(Handle* h, const float* in, float* out, long long T, int C, in
 // A CTA computes 128 consecutive positions; pad positions are computed and discarded (6% at P=32).
 //
 // Fusion of conv_init0 (LFT.py:23-25,65): with `lr` set, the input window of the FIRST conv of the stack is
-// conv_init0(lr) evaluated on the fly (9 taps x 64 channels per staged position, same fma order as k_conv0), and the
+// conv_init0(lr) evaluated on the fly (9 taps x 64 channels per staged position, fp32 fma chain over the 9 taps per channel), and the
 // residual of the LAST conv (`buffer = conv_init(buffer) + buffer`, LFT.py:66) is recomputed the same way instead of
 // being read back -- the [T,64] conv_init0 tensor never exists in HBM.
 struct W0Tab { float w[64 * 9]; };  // conv_init0.0.weight [c][tap] (constant bank)
@@ -485,15 +443,6 @@ int configure_conv() {
   CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemConv128));
   CUDA_TRY(cudaFuncSetAttribute(k_gemm_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return 0;
-}
-
-int launch_conv0(Handle* h, const float* lr, float* out, int B, int P, cudaStream_t st) {
-  const int A = h->cfg.ang_res;
-  const long long T = (long long)B * A * A * P * P;
-  Scope sc(h, K_CONV0, st);
-  const long long Tp = (T + 31) / 32 * 32;
-  k_conv0<<<(unsigned)((Tp * 16 + 255) / 256), 256, 0, st>>>(lr, h->w_conv0, out, B, A, P);
-  return sc.finish();
 }
 
 // in == nullptr: the input is conv_init0(lr) computed on the fly; (epi & 2) with res == nullptr: so is the residual.
