@@ -19,6 +19,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 if os.environ.get("LFT_TIMELINE"):
     FLAGS.append("-DLFT_TIMELINE")
+if os.environ.get("LFT_EXPERIMENT_NOSTORE"):    # timing experiment (wrong results): k_spa_embed_qkv* never store
+    FLAGS.append("-DLFT_EXPERIMENT_NOSTORE")
 if os.environ.get("LFT_EXPERIMENT_NOSTREAM"):   # timing experiment (wrong results): weight slabs are never copied
     FLAGS.append("-DLFT_EXPERIMENT_NOSTREAM")
 

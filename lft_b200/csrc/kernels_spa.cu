@@ -49,215 +49,205 @@ LFT_DEVINL void a_store16(uint32_t A, int kc0, int m, const float* x, bool fp32_
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_spa_embed_qkv is persistent: a CTA (two per SM) walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ... keeping
+// its TMEM / barriers, and the row owners stage the NEXT tile's conv window into shared memory while the tensor core works
+// on Q of the current one (z = tok + PE_s lives in TMEM, TS form - no smem operand reads for A - so the staging area is
+// free as soon as the conv MMAs are done).  Accumulators are drained into registers and released before the epilogue
+// arithmetic and stores, which then run under the next MMA.  Set-up / tear-down / window fill leave the per-tile chain.  Barriers: F = aux[0] (256) window of the next tile staged; a_ready (256): z ready, Q / K / V drained
+// (4 arrivals per tile, each separated from the next by a wait on an MMA that needed the previous phase complete);
+// mma_done: conv, Q, K, V (4 commits per tile).
 __global__ void __launch_bounds__(kThreads2, 2)
 k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp, const float* __restrict__ pe,
-                const float* __restrict__ pev, const __grid_constant__ Tab512 tab, const uint8_t* __restrict__ wq,
-                const uint8_t* __restrict__ wk, const uint8_t* __restrict__ wv, float* __restrict__ tok,
-                float* __restrict__ Q, float* __restrict__ K, float* __restrict__ Vv, int V, int P, int passes) {
+                  const float* __restrict__ pev, const __grid_constant__ Tab512 tab, const uint8_t* __restrict__ wq,
+                  const uint8_t* __restrict__ wk, const uint8_t* __restrict__ wv, float* __restrict__ tok,
+                  float* __restrict__ Q, float* __restrict__ K, float* __restrict__ Vv, int V, int P, int passes,
+                  int ntiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t U = smem_u32(smem) + kCtlBytes;
-  const uint32_t c_hi = U, c_lo = U + kConvRows * 128;  // conv staging (51.5 KB), dead after the conv MMAs
-  const uint32_t A = U;                                  // K=128 operand: hi [0,32K), lo [32K,64K)
+  const uint32_t c_hi = U, c_lo = U + kConvRows * 128;
   const uint32_t ring = U + 65536;
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
+  const uint32_t f_ready = smem_u32(&ctl->aux[0]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P1 = P + 1;
   const long long VS = (long long)P1 * P1;
   const long long G = (long long)V * VS;
-  const long long g0 = (long long)blockIdx.x * 128;
-  LFT_TL2(20);
   cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
-  const uint32_t k_done = smem_u32(&ctl->aux[1]);  // completed by one tcgen05.commit (K accumulator full)
-  if (tid == 0) {
-    mbar_init(k_done, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
   const uint32_t tmem = ctl->tmem;
   const GemmPhase g_c{wmlp, 128, 9}, g_q{wq, 128, 2}, g_k{wk, 128, 2}, g_v{wv, 128, 2};
+  const int first = blockIdx.x, step = gridDim.x;
+  const int ntl = first < ntiles ? (ntiles - first + step - 1) / step : 0;
 
   if (warp == kWarpProducer2) {
-
     RingState<kSpaNST> rs;
-    int tln = 0;
-    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, 0, &tln);
-    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, 0, &tln);
-    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, 0, &tln);
-    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, 0, &tln);
+    for (int k = 0; k < ntl; ++k) {
+      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes);
+      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes);
+      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes);
+      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes);
+    }
   } else if (warp == kWarpMma2) {
-
     RingState<kSpaNST> rs;
-    mbar_wait(a_ready, 0);
-    tc_fence_after();
-    LFT_TL2(10);
+    uint32_t rpar = 0;
     auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
-    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
-                              c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
-    umma_commit_elected(mma_done);
-    LFT_TL2(11);
-    // Q, K, V: SS form from the smem operand z = tok + PE_s (the conv staging area is dead by now), two accumulators:
-    // Q -> D0 [0,128), K -> D1 [128,256) issued back to back, V -> D0 once the row owners have drained Q.  The Q and K
-    // epilogues run under the K and V MMAs.
-    mbar_wait(a_ready, 1);
-    tc_fence_after();
-    LFT_TL2(12);
-    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                              tmem + 0, true);
-    umma_commit_elected(mma_done);
-    LFT_TL2(13);
-    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                              tmem + 128, true);
-    umma_commit_elected(k_done);
-    LFT_TL2(15);
-    mbar_wait(a_ready, 0);  // D0 drained
-    tc_fence_after();
-    LFT_TL2(16);
-    ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
-                              tmem + 0, true);
-    umma_commit_elected(mma_done);
-    LFT_TL2(17);
+    const uint32_t ta_hi = tmem + 128, ta_lo = tmem + 192;
+    for (int k = 0; k < ntl; ++k) {
+      mbar_wait(f_ready, k & 1);
+      if (k > 0) { mbar_wait(a_ready, rpar); rpar ^= 1; }  // V of the previous tile drained: D[0,128) is free
+      tc_fence_after();
+      ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
+                                c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
+      umma_commit_elected(mma_done);
+      mbar_wait(a_ready, rpar); rpar ^= 1;
+      tc_fence_after();
+      ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, ta_hi, ta_lo, tmem + 0, true);
+      umma_commit_elected(mma_done);
+      mbar_wait(a_ready, rpar); rpar ^= 1;
+      tc_fence_after();
+      ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, ta_hi, ta_lo, tmem + 0, true);
+      umma_commit_elected(mma_done);
+      mbar_wait(a_ready, rpar); rpar ^= 1;
+      tc_fence_after();
+      ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, ta_hi, ta_lo, tmem + 0, true);
+      umma_commit_elected(mma_done);
+    }
   } else {
-    LFT_TL2(0);
-    conv_stage_window(feat, c_hi, c_lo, g0, G, VS, P, tid, passes == 3);
-    fence_proxy_async_smem();
-    mbar_arrive(a_ready);
-    LFT_TL2(1);
-
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
-    const long long g = g0 + m;
-    bool ok = false;
-    long long v = 0;
-    int y = 0, x = 0;
-    if (g < G) {
-      const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
-      v = gu / vsu;
-      const int qq = (int)(gu - (unsigned)v * vsu);
-      y = qq / P1;
-      x = qq - y * P1;
-      ok = (y < P && x < P);
-    }
-    if (!ok) { v = 0; y = 0; x = 0; }
-    const int PP = P * P;
-    const int p = y * P + x;
-    const long long token = (v * P + y) * P + x;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-
-    // ---- phase 1: tok (own 64 columns) -> global; z = tok + PE_s -> A operand and LN statistics.
-    // (Q, K = LN(z) W^T via the folded epilogue; V = tok Wv^T = z Wv^T - PE_s Wv^T.)  PE is fetched before the wait.
-    float mean, rstd;
-    {
-      float z[64];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(pe) + (long long)(16 * q + i) * PP + p);  // [chunk][p][4]
-        z[4 * i] = b.x; z[4 * i + 1] = b.y; z[4 * i + 2] = b.z; z[4 * i + 3] = b.w;
-      }
-      mbar_wait(mma_done, 0);
-      tc_fence_after();
-      LFT_TL2(2);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float t[16];
-        tmem_ld16(trow + 64 * q + 16 * c, t);
-        if (ok) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(tok + t32_off(token, 16 * q + 4 * c + i, 32)) =
-                make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) z[16 * c + i] += t[i];
-        a_store16(A, 8 * q + 2 * c, m, z + 16 * c, passes == 3);
-      }
-      // mailbox in this thread's own (already consumed) accumulator columns
-      pair_ln_stats<64>(z, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(a_ready);
-    LFT_TL2(3);
-    LFT_TL2W(1, warp);
-
-    // ---- phase 2: Q then K (one accumulator, TS-form MMAs): affine LN correction in the epilogue
+    const int PP = P * P;
     const float4* tab4 = reinterpret_cast<const float4*>(tab.v);  // [u_q | u_k | c_q | c_k] x 128 (constant bank)
-    const float mr = mean * rstd;
-    mbar_wait(mma_done, 1);
-    tc_fence_after();
-    LFT_TL2(4);
-    {
-      float dd[64];  // all four accumulator loads in flight, one wait
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dd + 16 * c);
-      tmem_wait_ld();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float* d = dd + 16 * c;
-        const int col = 64 * q + 16 * c;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 uv = tab4[col / 4 + j], cv = tab4[64 + col / 4 + j];
-          d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
-          d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
-          d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
-          d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
-        }
-        if (ok) planar_store16(Q, v, 4 * q + c, y, x, P, d);
-      }
-    }
-    tc_fence_before();
-    mbar_arrive(a_ready);  // D0 drained: V may overwrite it
-    LFT_TL2(5);
-    mbar_wait(k_done, 0);
-    tc_fence_after();
-    {
-      float dd[64];  // all four accumulator loads in flight, one wait
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 128 + 64 * q + 16 * c, dd + 16 * c);
-      tmem_wait_ld();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float* d = dd + 16 * c;
-        const int col = 64 * q + 16 * c;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 uv = tab4[32 + col / 4 + j], cv = tab4[96 + col / 4 + j];
-          d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
-          d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
-          d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
-          d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
-        }
-        if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
-      }
-    }
-    // ---- phase 3: V = D - PE_s Wv^T  (table prefetched before the wait)
-    {
-      float4 pv[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pv[i] = __ldg(reinterpret_cast<const float4*>(pev) + (long long)(16 * q + i) * PP + p);
-      LFT_TL2(6);
-      mbar_wait(mma_done, 0);
+    uint32_t mpar = 0;
+    auto await = [&]() {
+      mbar_wait(mma_done, mpar);
+      mpar ^= 1;
       tc_fence_after();
-      LFT_TL2(7);
+    };
+    auto stage = [&](int k) {
+      conv_stage_window(feat, c_hi, c_lo, (long long)(first + k * step) * 128, G, VS, P, tid, passes == 3);
+      fence_proxy_async_smem();
+      mbar_arrive(f_ready);
+    };
+    if (ntl > 0) stage(0);
+    for (int k = 0; k < ntl; ++k) {
+      const long long g = (long long)(first + k * step) * 128 + m;
+      bool ok = false;
+      long long v = 0;
+      int y = 0, x = 0;
+      if (g < G) {
+        const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
+        v = gu / vsu;
+        const int qq = (int)(gu - (unsigned)v * vsu);
+        y = qq / P1;
+        x = qq - y * P1;
+        ok = (y < P && x < P);
+      }
+      if (!ok) { v = 0; y = 0; x = 0; }
+#ifdef LFT_EXPERIMENT_NOSTORE
+      ok = false;  // timing experiment: no global stores at all
+#endif
+      const int p = y * P + x;
+      const long long token = (v * P + y) * P + x;
+      float mean, rstd;
+      {
+        float z[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float d[16];
-        tmem_ld16(trow + 64 * q + 16 * c, d);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          d[4 * j] -= pv[4 * c + j].x; d[4 * j + 1] -= pv[4 * c + j].y;
-          d[4 * j + 2] -= pv[4 * c + j].z; d[4 * j + 3] -= pv[4 * c + j].w;
+        for (int i = 0; i < 16; ++i) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(pe) + (long long)(16 * q + i) * PP + p);
+          z[4 * i] = b.x; z[4 * i + 1] = b.y; z[4 * i + 2] = b.z; z[4 * i + 3] = b.w;
         }
-        if (ok) planar_store16(Vv, v, 4 * q + c, y, x, P, d);
+        await();  // conv
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t[16];
+          tmem_ld16(trow + 64 * q + 16 * c, t);
+          if (ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<float4*>(tok + t32_off(token, 16 * q + 4 * c + i, 32)) =
+                  make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) z[16 * c + i] += t[i];
+          a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, z + 16 * c, passes == 3);
+        }
+        pair_ln_stats<64>(z, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(a_ready);             // z ready
+      if (k + 1 < ntl) stage(k + 1);    // the staging area is free (conv MMAs of this tile are complete)
+      const float mr = mean * rstd;
+      await();  // Q
+      {
+        float dd[64];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dd + 16 * c);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(a_ready);           // Q drained (values are in registers)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float* d = dd + 16 * c;
+          const int col = 64 * q + 16 * c;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 uv = tab4[col / 4 + j], cv = tab4[64 + col / 4 + j];
+            d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
+            d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
+            d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
+            d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
+          }
+          if (ok) planar_store16(Q, v, 4 * q + c, y, x, P, d);
+        }
+      }
+      await();  // K
+      {
+        float dd[64];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dd + 16 * c);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(a_ready);           // K drained
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float* d = dd + 16 * c;
+          const int col = 64 * q + 16 * c;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 uv = tab4[32 + col / 4 + j], cv = tab4[96 + col / 4 + j];
+            d[4 * j] = fmaf(rstd, d[4 * j], fmaf(-mr, uv.x, cv.x));
+            d[4 * j + 1] = fmaf(rstd, d[4 * j + 1], fmaf(-mr, uv.y, cv.y));
+            d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
+            d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
+          }
+          if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
+        }
+      }
+      await();  // V
+      {
+        float dd[64];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dd + 16 * c);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(a_ready);           // V drained: the next tile's conv may overwrite D
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float* d = dd + 16 * c;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 pv = __ldg(reinterpret_cast<const float4*>(pev) + (long long)(16 * q + 4 * c + j) * PP + p);
+            d[4 * j] -= pv.x; d[4 * j + 1] -= pv.y; d[4 * j + 2] -= pv.z; d[4 * j + 3] -= pv.w;
+          }
+          if (ok) planar_store16(Vv, v, 4 * q + c, y, x, P, d);
+        }
       }
     }
-    LFT_TL2(8);
-    LFT_TL2W(0, warp);
     tc_fence_before();
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
-  LFT_TL2(21);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -704,8 +694,10 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     Tab512 tq;
     memcpy(tq.v, L.s_tab.data(), sizeof(tq.v));  // [u_q | u_k | c_q | c_k]
     Scope sc(h, K_SPA_QKV, st);
-    k_spa_embed_qkv<<<(unsigned)((G + 127) / 128), kThreads2, kSmemSpa, st>>>(
-        in, L.s_wmlp, L.s_pe, L.s_pev, tq, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes());
+    const unsigned ntiles = (unsigned)((G + 127) / 128);
+    const unsigned pg = ntiles < 2u * h->num_sms ? ntiles : 2u * h->num_sms;  // persistent: two CTAs per SM
+    k_spa_embed_qkv<<<pg, kThreads2, kSmemSpa, st>>>(in, L.s_wmlp, L.s_pe, L.s_pev, tq, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q,
+                                                     w.k, w.v, (int)V, P, h->passes(), (int)ntiles);
     if ((rc = sc.finish())) return rc;
   }
   {

@@ -94,7 +94,7 @@ class LightFieldSR:
 
 class HostPipeline:
     """Streams light fields pinned host -> device -> SR -> pinned host with the copies overlapped with compute:
-    the H2D of light field i+1 and the D2H of light field i run on a side stream while the kernels of the other one
+    the H2D of light field i+1 and the D2H of light field i run on two side streams while the kernels of the other one
     run on the caller's stream (`depth` device slots).  What test.py's loop does per scene with `.to(device)` /
     `.cpu()` (test.py:94-95), without the stalls.
 
@@ -108,12 +108,14 @@ class HostPipeline:
         self._sr = LightFieldSR(net_or_engine, max_ws_bytes)
         self._depth = depth
         self._slots: List[dict] = []
-        self._copy: Optional[torch.cuda.Stream] = None
+        self._copy: Optional[torch.cuda.Stream] = None   # device -> host
+        self._up: Optional[torch.cuda.Stream] = None     # host -> device (own stream: an upload never queues behind a download)
         self._i = 0
 
     def _slot(self, device) -> dict:
         if self._copy is None:
             self._copy = torch.cuda.Stream(device=device)
+            self._up = torch.cuda.Stream(device=device)
             self._slots = [dict(lr=None, sr=None, h2d=torch.cuda.Event(), done=None, d2h=None) for _ in range(self._depth)]
         s = self._slots[self._i % self._depth]
         self._i += 1
@@ -128,13 +130,13 @@ class HostPipeline:
         main = torch.cuda.current_stream(device)
         if slot["lr"] is None or slot["lr"].shape != lr_host.shape:
             slot["lr"] = torch.empty(lr_host.shape, dtype=torch.float32, device=device)
-        with torch.cuda.stream(self._copy):
+        with torch.cuda.stream(self._up):
             if slot["done"] is not None:
-                self._copy.wait_event(slot["done"])     # the kernels that read this slot's LR buffer have finished
+                self._up.wait_event(slot["done"])       # the kernels that read this slot's LR buffer have finished
             else:
-                self._copy.wait_stream(main)            # first use: the buffer allocation is ordered on `main`
+                self._up.wait_stream(main)              # first use: the buffer allocation is ordered on `main`
             slot["lr"].copy_(lr_host, non_blocking=True)
-            slot["h2d"].record(self._copy)
+            slot["h2d"].record(self._up)
         main.wait_event(slot["h2d"])
         if slot["d2h"] is not None:
             main.wait_event(slot["d2h"])                # the slot's previous result has left the device

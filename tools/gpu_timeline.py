@@ -14,6 +14,8 @@ for which, name in ((0, "k_spa_ffn"), (1, "k_ang"), (2, "k_spa_embed_qkv")):
     buf = (C.c_int64 * 64)()
     capi.check(eng.lib.lft_debug_timeline(which, buf))
     row = [buf[i] for i in range(32)]; mma = [buf[32 + i] for i in range(32)]
+    if not any(x > 0 for x in row + mma):
+        print(prec, name, ": no marks in this build"); continue
     t0 = min(x for x in row + mma if x > 0)
     print(prec, name, "row :", {i: x - t0 for i, x in enumerate(row) if x > 0})
     print(prec, name, "mma :", {i: x - t0 for i, x in enumerate(mma) if x > 0})
@@ -22,7 +24,7 @@ buf = (C.c_int64 * 120)()
 capi.check(eng.lib.lft_debug_timeline(4, buf))
 v = [buf[i] for i in range(120)]
 t0 = v[0]
-print("embed producer (middle CTA): per slab [before empty-wait, after wait, after copy issue] relative cycles")
+if t0: print("embed producer (middle CTA): per slab [before empty-wait, after wait, after copy issue] relative cycles")
 for i in range(26):
     a, b, c = v[3 * i:3 * i + 3]
     if a: print(f"  slab {i:2d}: {a - t0:7d} {b - t0:7d} {c - t0:7d}   wait {b - a:6d}  issue {c - b:5d}")
