@@ -31,9 +31,11 @@ LFT_DEVINL float dot8(const f32x2* q, const ulonglong2& k0, const ulonglong2& k1
 // pixel and head are read ONCE from shared memory for all NQ queries.  Softmax is evaluated online in chunks of 5
 // keys (scores of one chunk live in registers; the accumulators are rescaled once per chunk).  q is pre-scaled by
 // log2(e)/sqrt(hd).  kb/vb: this pixel's first key in the [head][half][kv row][4 floats] planes (kv row = t*5 + pixel).
-template <int NQ>
-LFT_DEVINL void ang_attn_head25(const f32x2 (*q)[4], const ulonglong2* __restrict__ kb, const ulonglong2* __restrict__ vb,
-                                float (*o)[8]) {
+// Generalised: NK keys in chunks of CH (NK % CH == 0), key t at kv row t*KS + pixel (KS = pixels per tile).
+template <int NQ, int NK, int KS, int CH>
+LFT_DEVINL void ang_attn_head(const f32x2 (*q)[4], const ulonglong2* __restrict__ kb, const ulonglong2* __restrict__ vb,
+                              float (*o)[8]) {
+  static_assert(NK % CH == 0, "chunking");
   float mx[NQ], l[NQ];
   f32x2 acc[NQ][4];
 #pragma unroll
@@ -43,18 +45,22 @@ LFT_DEVINL void ang_attn_head25(const f32x2 (*q)[4], const ulonglong2* __restric
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[x][e] = 0ull;
   }
+#pragma unroll(NK / CH <= 5 ? NK / CH : 1)
+  for (int c = 0; c < NK / CH; ++c) {
+    float sc[NQ][CH];
+    const ulonglong2* kc = kb + KS * CH * c;
+    const ulonglong2* vc = vb + KS * CH * c;
 #pragma unroll
-  for (int c = 0; c < 5; ++c) {
-    float sc[NQ][5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const ulonglong2 k0 = kb[5 * (5 * c + j)], k1 = kb[5 * (5 * c + j) + 128];
+    for (int j = 0; j < CH; ++j) {
+      const ulonglong2 k0 = kc[KS * j], k1 = kc[KS * j + 128];
 #pragma unroll
       for (int x = 0; x < NQ; ++x) sc[x][j] = dot8(q[x], k0, k1);
     }
 #pragma unroll
     for (int x = 0; x < NQ; ++x) {
-      const float cm = fmaxf(fmaxf(fmaxf(sc[x][0], sc[x][1]), fmaxf(sc[x][2], sc[x][3])), sc[x][4]);
+      float cm = sc[x][0];
+#pragma unroll
+      for (int j = 1; j < CH; ++j) cm = fmaxf(cm, sc[x][j]);
       const float mn = fmaxf(mx[x], cm);
       const float corr = fast_exp2(mx[x] - mn);  // first chunk: exp2(-inf) = 0 on zero accumulators
       mx[x] = mn;
@@ -64,8 +70,8 @@ LFT_DEVINL void ang_attn_head25(const f32x2 (*q)[4], const ulonglong2* __restric
       for (int e = 0; e < 4; ++e) acc[x][e] = mul2(acc[x][e], c2);
     }
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const ulonglong2 v0 = vb[5 * (5 * c + j)], v1 = vb[5 * (5 * c + j) + 128];
+    for (int j = 0; j < CH; ++j) {
+      const ulonglong2 v0 = vc[KS * j], v1 = vc[KS * j + 128];
 #pragma unroll
       for (int x = 0; x < NQ; ++x) {
         const float pw = fast_exp2(sc[x][j] - mx[x]);
@@ -93,8 +99,8 @@ LFT_DEVINL void ang_attn_head25(const f32x2 (*q)[4], const ulonglong2* __restric
 // the lower lane (of l, l+16) computes head h2, the upper lane head 2+h2, each for its own query, its partner's and (NQ == 3) a
 // third query of the same pixel; queries and results travel by warp shuffles.  Q is read from the fp32 stash in
 // TMEM columns [tq, tq+32); results are written as the bf16 hi/lo TS-form A operand of the output projection.
-template <int NQ>
-LFT_DEVINL void ang_pair_heads25(uint32_t tq, uint32_t to_hi, uint32_t to_lo, int h2, bool up, int partner, int tsrc,
+template <int NQ, int NK, int KS, int CH>
+LFT_DEVINL void ang_pair_heads(uint32_t tq, uint32_t to_hi, uint32_t to_lo, int h2, bool up, int partner, int tsrc,
                                  bool single, int hlo, int hup, const uint8_t* ks_q, const uint8_t* vs_q, int pl,
                                  bool fp32_mode) {
   float qa[8], qb[8];
@@ -123,7 +129,7 @@ LFT_DEVINL void ang_pair_heads25(uint32_t tq, uint32_t to_hi, uint32_t to_lo, in
   const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(ks_q + head * 4096) + pl;
   const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(vs_q + head * 4096) + pl;
   float o[NQ][8];
-  ang_attn_head25<NQ>(qq, kb, vb, o);
+  ang_attn_head<NQ, NK, KS, CH>(qq, kb, vb, o);
   float oa[8], ob[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -152,6 +158,11 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       const uint8_t* __restrict__ w2, const __grid_constant__ Tab512 tab, const float* __restrict__ peqk,
       const float* __restrict__ pe, int Nrt, int PP, long long npix, int passes) {
   const int N = NV > 0 ? NV : Nrt;
+  // Specialised views-per-pixel counts (A = 3, 5, 7, 9) pair two views of one pixel in lanes l / l+16 and share every K/V read
+  // between them (kPair); pixels per tile: 12 / 5 / 2 / 1, softmax chunk = A keys.
+  constexpr bool kPair = NV == 9 || NV == 25 || NV == 49 || NV == 81;
+  constexpr int kPPT = NV == 9 ? 12 : NV == 25 ? 5 : NV == 49 ? 2 : NV == 81 ? 1 : 0;
+  constexpr int kCH = NV == 9 ? 9 : NV == 25 ? 5 : NV == 49 ? 7 : NV == 81 ? 9 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t s_base = smem_u32(smem);
@@ -190,7 +201,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     umma_commit_elected(mma_done);
     mbar_wait(a_ready, 1);
     tc_fence_after();
-    if constexpr (NV == 25)  // O operand in TMEM columns [64,96) hi | [96,128) lo (TS form)
+    if constexpr (kPair)  // O operand in TMEM columns [64,96) hi | [96,128) lo (TS form)
       ring_consume_mma_ts<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes, tmem + 64, tmem + 96, tmem + 0, true);
     else
       ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes, R1, R1 + 16384, LBO, 0, NoShift{},
@@ -211,9 +222,17 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     // rows are view-major inside the tile (m = a*PPT + pl): consecutive lanes = consecutive pixels of one view,
     // so one 16-byte request of a warp touches ~7 cache lines of the T32 layout instead of 25
-    const int PPT = NV > 0 ? 128 / NV : 128 / N;
+    const int PPT = kPair ? kPPT : (NV > 0 ? 128 / NV : 128 / N);
     int a, pl, kvrow;
-    if constexpr (NV == 25) {
+    if constexpr (kPair && NV != 25) {
+      // pair k = 16*(warp&3) + (lane&15): view pair k / PPT, pixel k % PPT; lower lane = even view, upper lane = odd view
+      // (an odd view count leaves the last even view paired with an idle row)
+      const int k = 16 * (warp & 3) + (lane & 15), upper = lane >> 4;
+      const int vp = k / kPPT;
+      pl = k - kPPT * vp;
+      a = 2 * vp + upper;
+      kvrow = a < NV ? a * kPPT + pl : -1;  // idle rows stage nothing
+    } else if constexpr (NV == 25) {
       // paired rows: lanes l and l+16 of a warp hold views (2v, 2v+1) of ONE pixel, so that the attention can share every
       // K/V read between two queries (partner = lane ^ 16; a quarter-warp always reads one head: no bank conflicts).
       // Pair k = 16*(warp&3) + (lane&15) < 60: view pair k/5, pixel k%5.  The 8 remaining lanes of the last row warp
@@ -302,25 +321,29 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
           kv[4 * j + 2] = fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
           kv[4 * j + 3] = fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
         }
+        if (kvrow >= 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)  // [head][half][row][4 floats]: head = 4q + 2c + j/2, half = j%2 (conflict-free)
-          *reinterpret_cast<float4*>(ks_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) =
-              make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)  // [head][half][row][4 floats]: head = 4q + 2c + j/2, half = j%2 (conflict-free)
+            *reinterpret_cast<float4*>(ks_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) =
+                make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+        }
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {  // V columns 128 + 32q + 16c (raw)
         tmem_ld16(trow + 128 + 32 * q + 16 * c, kv);
+        if (kvrow >= 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(vs_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) =
-              make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(vs_ptr + ((4 * q + 2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) =
+                make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+        }
       }
       float qv[32];
       tmem_ld16_nowait(trow + 32 * q, qv);
       tmem_ld16_nowait(trow + 32 * q + 16, qv + 16);
       tmem_wait_ld();
       const float scale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e)/sqrt(8), folded into Q (softmax via exp2)
-      if constexpr (NV == 25) {
+      if constexpr (kPair) {
         // corrected, pre-scaled Q back into its own TMEM columns (fp32 stash); the pair kernels re-read one head pair at a time
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -340,7 +363,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
         const bool up = lane >= 16;
         int partner = lane ^ 16, tsrc = lane, hlo = lane, hup = lane;
         bool single = false;
-        if (wq == 3) {  // pairs 48..59 in lanes 0..11 / 16..27; view 24 of pixel s in lane 12+s (s < 4) or 28 (s = 4)
+        if (NV == 25 && wq == 3) {  // pairs 48..59 in lanes 0..11 / 16..27; view 24 of pixel s in lane 12+s (s < 4) or 28 (s = 4)
           const int l15 = lane & 15;
           if (l15 >= 12) {
             partner = lane;
@@ -356,10 +379,12 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
         const uint32_t tq = trow + 32 * q, to_hi = trow + 64 + 16 * q, to_lo = trow + 96 + 16 * q;
 #pragma unroll 1
         for (int h2 = 0; h2 < 2; ++h2) {
-          if (wq == 3)
-            ang_pair_heads25<3>(tq, to_hi, to_lo, h2, up, partner, tsrc, single, hlo, hup, ks_q, vs_q, pl, passes == 3);
+          if (NV == 25 && wq == 3)
+            ang_pair_heads<3, NV, kPPT, kCH>(tq, to_hi, to_lo, h2, up, partner, tsrc, single, hlo, hup, ks_q, vs_q, pl,
+                                             passes == 3);
           else
-            ang_pair_heads25<2>(tq, to_hi, to_lo, h2, up, partner, tsrc, single, hlo, hup, ks_q, vs_q, pl, passes == 3);
+            ang_pair_heads<2, NV, kPPT, kCH>(tq, to_hi, to_lo, h2, up, partner, tsrc, single, hlo, hup, ks_q, vs_q, pl,
+                                             passes == 3);
         }
         LFT_TL(4);
         tmem_wait_st();
@@ -552,6 +577,8 @@ int debug_timeline_ang(long long* out) {
 int configure_ang() {
   CUDA_TRY(cudaFuncSetAttribute(k_ang<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAng));
   CUDA_TRY(cudaFuncSetAttribute(k_ang<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAng));
+  CUDA_TRY(cudaFuncSetAttribute(k_ang<49>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAng));
+  CUDA_TRY(cudaFuncSetAttribute(k_ang<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAng));
   CUDA_TRY(cudaFuncSetAttribute(k_ang<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAng));
   return 0;
 }
@@ -559,7 +586,7 @@ int configure_ang() {
 int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cudaStream_t st) {
   const int N = h->cfg.ang_res * h->cfg.ang_res;
   const long long npix = (long long)B * P * P;
-  const int PPT = 128 / N;
+  const int PPT = N == 9 ? 12 : N == 25 ? 5 : N == 49 ? 2 : N == 81 ? 1 : 128 / N;  // keep in step with kPPT in k_ang
   const unsigned grid = (unsigned)((npix + PPT - 1) / PPT);
   const Layer& L = h->layer[layer];
   Tab512 ta;
@@ -570,6 +597,8 @@ int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cud
                                                h->pe_ang, N, P * P, npix, h->passes())
   if (N == 25) LFT_ANG_LAUNCH(25);
   else if (N == 9) LFT_ANG_LAUNCH(9);
+  else if (N == 49) LFT_ANG_LAUNCH(49);
+  else if (N == 81) LFT_ANG_LAUNCH(81);
   else LFT_ANG_LAUNCH(0);
 #undef LFT_ANG_LAUNCH
   return sc.finish();

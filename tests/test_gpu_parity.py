@@ -94,6 +94,17 @@ def test_angres9_81_tokens_vs_oracle():
     assert (out - ref).abs().max() <= TOL_FP32
 
 
+@pytest.mark.parametrize("A,s,h,B", [(7, 2, 8, 2), (7, 4, 5, 1), (3, 4, 9, 3), (4, 2, 8, 1), (2, 4, 8, 2), (6, 2, 6, 1)])
+def test_other_angular_resolutions_vs_oracle(A, s, h, B):
+    """A = 3, 7 run the paired-view attention specialisations (9 / 49 tokens per pixel), A = 2, 4, 6 the run-time-N path;
+    odd patch sizes make the last tile ragged."""
+    sd = synth.synth_state_dict(A, s, 10 + A)
+    lr = torch.from_numpy(synth.synth_lr_mosaic(B, A, h, h, 10 + A))
+    ref = O.forward(sd, lr, A, s)
+    out = _engine(A, s, sd).forward(lr.cuda()).cpu()
+    assert (out - ref).abs().max() <= TOL_FP32
+
+
 def _psnr(a, b):
     return 10.0 * np.log10(1.0 / max(float(((a - b) ** 2).mean()), 1e-20))
 
