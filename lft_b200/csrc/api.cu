@@ -253,8 +253,8 @@ static int finalize(Handle* h) {
     void* d;
     if ((rc = upload(h, all.data(), all.size() * 2, &d))) return rc;
     h->w_up = (const uint8_t*)d;
-    const float* w3 = W("upsampling.3.weight");  // [1][64][3][3]: contracted on CUDA cores inside k_up_gemm
-    h->w_up3_host.assign(w3, w3 + 576);
+    const float* w3 = W("upsampling.3.weight");  // [1][64][3][3] -> B operand of the tap GEMM: row = tap (9 of 16), k = channel
+    if ((rc = upload_packed(h, 9, 16, 64, [=](int n, int k) { return w3[(size_t)k * 9 + n]; }, &h->w_up3))) return rc;
   }
   // angular position table, chunk-planar [c/4][A*A][4]
   {

@@ -69,7 +69,7 @@ struct Handle {
   const uint8_t* w_conv[3] = {nullptr, nullptr, nullptr};
   Layer layer[kLayers];
   const uint8_t* w_up = nullptr;
-  std::vector<float> w_up3_host;  // upsampling.3.weight [1][64][3][3] (kernel parameter of k_up_gemm)
+  const uint8_t* w_up3 = nullptr;  // upsampling.3.weight packed as a [16 x 64] bf16 hi/lo B operand (rows 9..15 zero)
   const float* pe_ang = nullptr;
   int pe_P = -1;
   bool profiling = false;

@@ -17,32 +17,35 @@ namespace lft {
 
 constexpr int kUpNST = 4;
 constexpr uint32_t kUpStage = 64 * 128;
-constexpr size_t kSmemUp = kCtlBytes + 32768 + kUpNST * kUpStage;
+constexpr size_t kSmemUp = kCtlBytes + 32768 + 4096 + kUpNST * kUpStage;
 constexpr uint32_t kLbo64 = 128 * 16;
 
-struct W3Tab { float w[10 * 64]; };  // upsampling.3.weight as [tap][c] (constant bank); tap 9 = zero padding
-
-// The 1x1 conv (64 -> 64 s^2, one [64 x 64] GEMM per sub-pixel ij, PixelShuffle order) runs on tcgen05 with a
-// double-buffered TMEM accumulator; the row owners turn accumulator ij into LeakyReLU'd values and contract
-// them with the nine 3x3 taps on CUDA cores (64 -> 9, fp32 FFMA with constant-bank weights) while the tensor
-// core already computes sub-pixel ij+1.  Thread (row, q) reads the whole 64-column row and owns taps
-// 0..4 (q = 0) or 5..8 (q = 1); one completed HR row (s sub-pixels) is stored per tap as one 16-byte vector.
-//   barriers: aux[0] A1 ready (256) | aux[2], aux[3] accumulator full (commit) | a_ready / mma_done are reused as
-//   accumulator-free barriers of buffers 0 / 1 (256 arrivals each).
+// The 1x1 conv (64 -> 64 s^2, one [64 x 64] GEMM per sub-pixel ij, PixelShuffle order) and the 64 -> 9 tap contraction of
+// the final 3x3 conv are TWO chained tcgen05 GEMMs per sub-pixel:
+//   G1(ij): D1[b] = A1 (feat tile, smem)  x  W_up[ij]^T          (N = 64, weights through the ring, double-buffered D1)
+//   G2(ij): D2    = lrelu(D1[b]) (TMEM A operand, TS form)  x  W3^T   (N = 16: taps 0..8 + 7 zero rows, W3 resident in smem)
+// The row owners only convert: D1 -> LeakyReLU -> bf16 hi/lo -> TMEM, and read the 9 per-tap partial sums back (the CUDA-core
+// 64 x 9 FFMA contraction this replaces made the kernel issue-bound at 82 %).  One completed HR row (s sub-pixels) is stored
+// per tap as one 16-byte vector; thread (row, q) owns taps 0..4 (q = 0) or 5..8 (q = 1).
+//   TMEM: D1[0] [0,64) | D1[1] [64,128) | A2 hi [128,160) lo [160,192) | D2 [192,208)
+//   barriers: aux[0] A1 + W3 staged (256) | aux[2], aux[3] D1[b] full (commit) | a_ready: A2 ready = D1[b] drained (256) |
+//   mma_done: D2 full (commit) | aux[1]: D2 drained (256).  Re-arrivals are separated by waits on the MMA in between.
 __global__ void __launch_bounds__(kThreads2, 2)
-k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const __grid_constant__ W3Tab w3,
+k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const uint8_t* __restrict__ w3p,
           float* __restrict__ Pp, long long T, int A, int P, int s, int passes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t A1 = smem_u32(smem) + kCtlBytes;
-  const uint32_t ring = A1 + 32768;
+  const uint32_t W3 = A1 + 32768;              // [hi: kc 8][16 rows][16 B] 2 KB | lo 2 KB
+  const uint32_t ring = W3 + 4096;
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a1_ready = smem_u32(&ctl->aux[0]);
   const uint32_t d1_full0 = smem_u32(&ctl->aux[2]);  // aux[2], aux[3]
-  const uint32_t d1_free0 = smem_u32(&ctl->aux[1]);  // buffer 0
-  const uint32_t d1_free1 = smem_u32(&ctl->a_ready); // buffer 1
+  const uint32_t a2_ready = smem_u32(&ctl->a_ready);
+  const uint32_t d2_full = smem_u32(&ctl->mma_done);
+  const uint32_t d2_free = smem_u32(&ctl->aux[1]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  cta_setup<kUpNST>(ctl, warp, lane, kRowThreads2, 128, kWarpMma2);
+  cta_setup<kUpNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   if (tid == 0) {  // accumulator-full barriers are completed by one tcgen05.commit each
     mbar_init(d1_full0, 1);
     mbar_init(d1_full0 + 8, 1);
@@ -64,16 +67,34 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
     RingState<kUpNST> rs;
     mbar_wait(a1_ready, 0);
     tc_fence_after();
+    auto g1 = [&](int ij) {
+      const GemmPhase g{wup + (size_t)ij * 2 * kUpStage, 64, 1};
+      ring_consume_mma<kUpNST>(rs, ring, kUpStage, full0, empty0, g, passes, A1, A1 + 16384, kLbo64, 0, NoShift{},
+                               tmem + 64u * (ij & 1), true);
+      umma_commit_elected(d1_full0 + 8u * (ij & 1));
+    };
+    g1(0);
+    if (s2 > 1) g1(1);
+    const uint32_t idesc = umma_idesc_bf16(16);
+    const uint32_t bh = umma_desc_lo(W3, 256), bl = umma_desc_lo(W3 + 2048, 256);  // LBO = 16 rows x 16 B
+    const uint32_t a_hi = tmem + 128, a_lo = tmem + 160, d2 = tmem + 192;
     for (int ij = 0; ij < s2; ++ij) {
-      const int b = ij & 1;
-      if (ij >= 2) {  // accumulator b was drained by the row owners (its (ij/2 - 1)-th release)
-        mbar_wait(b ? d1_free1 : d1_free0, ((ij >> 1) - 1) & 1);
-        tc_fence_after();
+      mbar_wait(a2_ready, ij & 1);
+      if (ij > 0) mbar_wait(d2_free, (ij - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) umma_bf16_ts(d2, a_hi + j * 8, umma_desc_from(bh + j * 32), idesc, j ? 1u : 0u);
+        if (passes == 3) {
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) umma_bf16_ts(d2, a_lo + j * 8, umma_desc_from(bh + j * 32), idesc, 1u);
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) umma_bf16_ts(d2, a_hi + j * 8, umma_desc_from(bl + j * 32), idesc, 1u);
+        }
+        umma_commit(d2_full);
       }
-      const GemmPhase g1{wup + (size_t)ij * 2 * kUpStage, 64, 1};
-      ring_consume_mma<kUpNST>(rs, ring, kUpStage, full0, empty0, g1, passes, A1, A1 + 16384, kLbo64, 0, NoShift{},
-                               tmem + 64u * b, true);
-      umma_commit_elected(d1_full0 + 8u * b);
+      __syncwarp();
+      if (ij + 2 < s2) g1(ij + 2);  // D1[ij & 1] was drained before the row owners arrived on a2_ready
     }
   } else {
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
@@ -88,7 +109,7 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
     const int H = A * P * s;
     const long long Y0 = (long long)(u * P + y) * s, X0 = (long long)(v * P + x) * s;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    {  // A1 <- feat row (own 32 channels)
+    {  // A1 <- feat row (own 32 channels); W3 <- packed tap weights (one 16-byte piece per thread)
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
         float z[8];
@@ -100,40 +121,46 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
         st_shared_v4(A1 + (4 * q + kc) * kLbo64 + m * 16, hi);
         st_shared_v4(A1 + 16384 + (4 * q + kc) * kLbo64 + m * 16, lo);
       }
+      st_shared_v4(W3 + tid * 16, __ldg(reinterpret_cast<const uint4*>(w3p) + tid));
       fence_proxy_async_smem();
       mbar_arrive(a1_ready);
     }
     float pj[4][5];                             // [sub-pixel column j][own tap]
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+      for (int tp = 0; tp < 5; ++tp) pj[jj][tp] = 0.f;
     for (int ij = 0; ij < s2; ++ij) {
       const int bsel = ij & 1;
       mbar_wait(d1_full0 + 8u * bsel, (ij >> 1) & 1);
       tc_fence_after();
-      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      // taps are compile-time per branch so the weights are immediate constant-bank operands of the FFMAs
-      auto taps = [&](auto tap0, auto ntaps) {
-        constexpr int T0 = decltype(tap0)::value, NT = decltype(ntaps)::value;
-        float d[64];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * bsel + 16 * c, d + 16 * c);
+      {  // own 32 columns of D1 -> LeakyReLU -> A2 (the previous G2 is complete: its D2 was read below)
+        float d[32];
+        tmem_ld16_nowait(trow + 64 * bsel + 32 * q, d);
+        tmem_ld16_nowait(trow + 64 * bsel + 32 * q + 16, d + 16);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const float hv = lrelu02(d[i]);
-#pragma unroll
-          for (int tp = 0; tp < NT; ++tp) acc[tp] = fmaf(hv, w3.w[(T0 + tp) * 64 + i], acc[tp]);
-        }
-      };
-      if (q == 0) taps(std::integral_constant<int, 0>{}, std::integral_constant<int, 5>{});
-      else taps(std::integral_constant<int, 5>{}, std::integral_constant<int, 4>{});
+        for (int i = 0; i < 32; ++i) d[i] = lrelu02(d[i]);
+        a_tmem_store16(trow + 128, trow + 160, 32 * q, d, passes == 3);
+        a_tmem_store16(trow + 128, trow + 160, 32 * q + 16, d + 16, passes == 3);
+      }
+      tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(bsel ? d1_free1 : d1_free0);
+      mbar_arrive(a2_ready);
+      mbar_wait(d2_full, ij & 1);
+      tc_fence_after();
+      float acc[16];
+      tmem_ld16(trow + 192, acc);
+      tc_fence_before();
+      mbar_arrive(d2_free);
       const int j = ij % s;
+      float own[5];
+#pragma unroll
+      for (int tp = 0; tp < 5; ++tp) own[tp] = q ? acc[5 + (tp < 4 ? tp : 3)] : acc[tp];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj)
-        if (jj == j) {
 #pragma unroll
-          for (int tp = 0; tp < 5; ++tp) pj[jj][tp] = acc[tp];
-        }
+        for (int tp = 0; tp < 5; ++tp) pj[jj][tp] = (jj == j) ? own[tp] : pj[jj][tp];
       if (j == s - 1 && ok) {  // one HR row i = ij / s of this LR pixel is complete
         const int i = ij / s;
         const int ntap = q ? 4 : 5;
@@ -149,8 +176,9 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
         }
       }
     }
+    tc_fence_before();
   }
-  cta_teardown(ctl, warp, 128, kWarpMma2);
+  cta_teardown(ctl, warp, 256, kWarpMma2);
 }
 
 // PyTorch upsample_bicubic2d coefficients (A = -0.75)
@@ -281,12 +309,8 @@ int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float
   const long long T = (long long)B * A * A * P * P;
   int rc;
   {
-    W3Tab w3t;
-    memset(&w3t, 0, sizeof(w3t));
-    for (int tp = 0; tp < 9; ++tp)
-      for (int c = 0; c < 64; ++c) w3t.w[tp * 64 + c] = h->w_up3_host[(size_t)c * 9 + tp];  // [1][64][3][3] -> [tap][c]
     Scope sc(h, K_UP_GEMM, st);
-    k_up_gemm<<<(unsigned)((T + 127) / 128), kThreads2, kSmemUp, st>>>(feat, h->w_up, w3t, pp, T, A, P, s, h->passes());
+    k_up_gemm<<<(unsigned)((T + 127) / 128), kThreads2, kSmemUp, st>>>(feat, h->w_up, h->w_up3, pp, T, A, P, s, h->passes());
     if ((rc = sc.finish())) return rc;
   }
   {
