@@ -101,6 +101,30 @@ class Engine:
         capi.check(self.lib.lft_forward(self._h, _ptr(lr), _ptr(out), B, P, _ptr(ws), ws.numel(), _stream()))
         return out
 
+    def forward_graphed(self, lr: torch.Tensor) -> torch.Tensor:
+        """forward() replayed from a CUDA graph (one per input shape): the 21 launches of a forward cost one graph launch,
+        which matters for the reference's own usage pattern - one 32x32 patch per call (test.py:88-95), where the kernels
+        take ~15 us each.  The result lives in a buffer owned by the graph: it is overwritten by the next call with the
+        same shape (clone it to keep it)."""
+        self._check_in(lr, "lr")
+        key = tuple(lr.shape)
+        g = getattr(self, "_graphs", None)
+        if g is None:
+            g = self._graphs = {}
+        if key not in g:
+            static_in = torch.empty_like(lr)
+            static_in.copy_(lr)
+            self.forward(static_in)                      # warm-up outside capture: builds the per-patch-size tables
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self.forward(static_in)
+            g[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = g[key]
+        static_in.copy_(lr)
+        graph.replay()
+        return static_out
+
     def stage_conv_init(self, lr: torch.Tensor) -> torch.Tensor:
         self._check_in(lr, "lr")
         B, _, H, W = lr.shape

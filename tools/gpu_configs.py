@@ -17,10 +17,10 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 rows = []
-def run(name, A, s, B, prec, reps):
+def run(name, A, s, B, prec, reps, graphed=False):
     eng = Engine(A, s, precision=prec); eng.load_state_dict(synth.synth_state_dict(A, s, 4))
     lr = torch.rand(B, 1, A * 32, A * 32, device="cuda", generator=torch.Generator("cuda").manual_seed(B))
-    ms = timed(lambda: eng.forward(lr, max_ws_bytes=WS), reps)
+    ms = timed((lambda: eng.forward_graphed(lr)) if graphed else (lambda: eng.forward(lr, max_ws_bytes=WS)), reps)
     raw_mp = B * (A * 32 * s) ** 2 / 1e6
     flop = {(5, 4): 61.733e9, (5, 2): 58.853e9, (9, 4): 204.773e9}[(A, s)] * B
     rows.append(f"| {name} | {A}x{A} | {s}x | {B} | {prec} | {ms:.3f} | {B / ms * 1e3:.1f} | {raw_mp / ms * 1e3:.0f} | {flop / ms / 1e9:.0f} |")
@@ -29,6 +29,7 @@ def run(name, A, s, B, prec, reps):
 
 print("| config | angRes | scale | patches B | path | ms / forward | patches/s | raw SR MP/s | algorithmic TFLOP/s |\n|---|---|---|---|---|---|---|---|---|")
 run("1: one 32x32 patch", 5, 4, 1, "fp32", 50)
+run("1: one 32x32 patch, CUDA graph replay", 5, 4, 1, "fp32", 50, graphed=True)
 run("2: batch of 64", 5, 2, 64, "fp32", 10)
 run("2: batch of 64", 5, 2, 64, "bf16", 10)
 for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512):
