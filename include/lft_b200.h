@@ -126,7 +126,10 @@ int lft_gemm_selftest(const float* A, const float* W, float* D, float* aux, int3
                       int32_t precision, int32_t variant);
 
 /* Micro-benchmark of the tcgen05 issue/operand path: every CTA issues reps*(K/16) MMAs (128 x N x 16, bf16) on resident
- * operands; cycles[grid] = clock64 cycles from first issue to completion.  mode 0: A,B from smem (SS); 1: A from TMEM (TS).
+ * operands; cycles[grid] = clock64 cycles from first issue to completion.  mode % 16: 0 A,B from smem (SS); 1 A from TMEM (TS);
+ * 2 SS with the A start shifted by one 16-byte row; 3 / 4 A in the SWIZZLE_128B layout (4: shifted by one row); 5 / 6 / 7 the
+ * 3x3-conv issue pattern (108 MMAs per rep; k-chunk planes of 201 rows / 208 rows / 201 rows without tap shifts).
+ * mode / 16 = n > 0: an extra tcgen05.commit after every n-th group of K/16 MMAs (commit cost).
  * smem_bytes sets the dynamic shared memory per CTA (and thereby how many CTAs share an SM). */
 int lft_mma_bench(int32_t N, int32_t K, int32_t reps, int32_t mode, int32_t grid, int32_t smem_bytes, int64_t* cycles);
 
