@@ -292,7 +292,10 @@ def main():
                      "traffic": ncu_traffic(top), "traffic_unit": "bytes/launch (dram read+write, ncu --set full, profiles/)",
                      "peak_source": pk["src"],
                      "note": ("fp32 path issues 3 bf16 MMAs per product (hi*hi+lo*hi+hi*lo): attainable frac <= 1/3"
-                              if args.precision == "fp32" else "single bf16 MMA per product")})
+                              if args.precision == "fp32" else "single bf16 MMA per product")
+                             + ("; ang_fused and spa_embed_qkv share the top spot within run-to-run noise - ang_fused spends 13 % of "
+                                "its time in GEMMs, the rest in the per-pixel 25x25 (head dim 8) attention on CUDA cores, which is "
+                                "shared-memory bound (DESIGN.md section 6)" if top == "ang_fused" else "")})
         whole = FLOP_PER_LF * world * args.steps / (total_ms * 1e-3) / 1e12
         line = {
             "metric": "SR output megapixels/sec (5x5 4x full LF)", "value": value, "unit": "MP/s", "n_gpus": world,
