@@ -209,13 +209,19 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     umma_commit_elected(mma_done);
     mbar_wait(a_ready, 0);
     tc_fence_after();
-    ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes, R1, R1 + 16384, LBO, 0, NoShift{},
-                              tmem + 0, true);
+    if constexpr (kPair)  // X1 operand in TMEM columns [128,160) hi | [160,192) lo (the V accumulator is dead)
+      ring_consume_mma_ts<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes, tmem + 128, tmem + 160, tmem + 0, true);
+    else
+      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes, R1, R1 + 16384, LBO, 0, NoShift{},
+                                tmem + 0, true);
     umma_commit_elected(mma_done);
     mbar_wait(a_ready, 1);
     tc_fence_after();
-    ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes, R1, R2, LBO, 8 * LBO, NoShift{},
-                              tmem + 128, true);
+    if constexpr (kPair)  // hidden operand written in place over the FFN1 accumulator: [0,64) hi | [64,128) lo
+      ring_consume_mma_ts<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes, tmem + 0, tmem + 64, tmem + 128, true);
+    else
+      ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes, R1, R2, LBO, 8 * LBO, NoShift{},
+                                tmem + 128, true);
     umma_commit_elected(mma_done);
   } else {
     // ------------------------------------------------------------ row owner: row m, channel half q
@@ -488,14 +494,19 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       for (int i = 0; i < 32; ++i) x[i] += d[i];
       tmem_st16(trow + 192 + 32 * q, x);
       tmem_st16(trow + 192 + 32 * q + 16, x + 16);
+      if constexpr (kPair) {  // TS form: the operand never touches shared memory
+        a_tmem_store16(trow + 128, trow + 160, 32 * q, x, passes == 3);
+        a_tmem_store16(trow + 128, trow + 160, 32 * q + 16, x + 16, passes == 3);
+      } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 hi, lo;
-        split8(x + 8 * c, hi, lo, passes == 3);
-        st_shared_v4(R1 + (4 * q + c) * LBO + m * 16, hi);
-        st_shared_v4(R1 + 16384 + (4 * q + c) * LBO + m * 16, lo);
+        for (int c = 0; c < 4; ++c) {
+          uint4 hi, lo;
+          split8(x + 8 * c, hi, lo, passes == 3);
+          st_shared_v4(R1 + (4 * q + c) * LBO + m * 16, hi);
+          st_shared_v4(R1 + 16384 + (4 * q + c) * LBO + m * 16, lo);
+        }
       }
-      pair_ln_stats<32>(x, trow + 64 + 4 * q, trow + 64 + 4 * (1 - q), bar_id, mean, rstd);
+      pair_ln_stats<32>(x, trow + 64 + 4 * q, trow + 64 + 4 * (1 - q), bar_id, mean, rstd);  // includes tcgen05.wait::st
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(a_ready);
@@ -512,6 +523,11 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, dd + 16 * c);
       tmem_wait_ld();
+      if constexpr (kPair) {  // the operand goes back into the same columns: both threads of the row must have read first
+        tc_fence_before();
+        pair_bar_sync(warp & 3);
+        tc_fence_after();
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float* d = dd + 16 * c;
@@ -525,14 +541,19 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
           d[4 * j + 2] = fmaxf(fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
           d[4 * j + 3] = fmaxf(fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w)), 0.f);
         }
+        if constexpr (kPair) {  // TS form: hidden hi -> columns [0,64), lo -> [64,128)
+          a_tmem_store16(trow + 0, trow + 64, 64 * q + 16 * c, d, passes == 3);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint4 hi, lo;
-          split8(d + 8 * j, hi, lo, passes == 3);
-          st_shared_v4(R1 + (8 * q + 2 * c + j) * LBO + m * 16, hi);
-          st_shared_v4(R2 + (8 * q + 2 * c + j) * LBO + m * 16, lo);
+          for (int j = 0; j < 2; ++j) {
+            uint4 hi, lo;
+            split8(d + 8 * j, hi, lo, passes == 3);
+            st_shared_v4(R1 + (8 * q + 2 * c + j) * LBO + m * 16, hi);
+            st_shared_v4(R2 + (8 * q + 2 * c + j) * LBO + m * 16, lo);
+          }
         }
       }
+      if constexpr (kPair) tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(a_ready);
