@@ -95,51 +95,41 @@ LFT_DEVINL void ang_attn_head(const f32x2 (*q)[4], const ulonglong2* __restrict_
   }
 }
 
-// One head pair (relative heads h2 and 2+h2 of this thread's channel half) of the A=5 attention for a lane pair:
-// the lower lane (of l, l+16) computes head h2, the upper lane head 2+h2, each for its own query, its partner's and (NQ == 3) a
-// third query of the same pixel; queries and results travel by warp shuffles.  Q is read from the fp32 stash in
-// TMEM columns [tq, tq+32); results are written as the bf16 hi/lo TS-form A operand of the output projection.
-template <int NQ, int NK, int KS, int CH>
-LFT_DEVINL void ang_pair_heads(uint32_t tq, uint32_t to_hi, uint32_t to_lo, int h2, bool up, int partner, int tsrc,
-                                 bool single, int hlo, int hup, const uint8_t* ks_q, const uint8_t* vs_q, int pl,
-                                 bool fp32_mode) {
+// One head pair (relative heads h2 and 2+h2 of this thread's channel half) of the paired-view attention for a lane pair:
+// the lower lane (of l, l+16) computes head h2, the upper lane head 2+h2, each for its own query and its partner's; queries and
+// results travel by warp shuffles.  Q is read from the fp32 stash in TMEM columns [tq, tq+32); results are written as the bf16
+// hi/lo TS-form A operand of the output projection.
+template <int NK, int KS, int CH>
+LFT_DEVINL void ang_pair_heads(uint32_t tq, uint32_t to_hi, uint32_t to_lo, int h2, bool up, int partner,
+                               const uint8_t* ks_q, const uint8_t* vs_q, int pl, bool fp32_mode) {
   float qa[8], qb[8];
   tmem_ld8(tq + 8 * h2, qa);
   tmem_ld8(tq + 16 + 8 * h2, qb);
-  f32x2 qq[NQ][4];
+  f32x2 qq[2][4];
   {
-    float mine[8], part[8], third[8];
+    float mine[8], part[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       mine[i] = up ? qb[i] : qa[i];
       part[i] = __shfl_sync(0xffffffffu, up ? qa[i] : qb[i], partner);  // the partner's query, MY head
-      if (NQ == 3) {
-        const float tl = __shfl_sync(0xffffffffu, qa[i], tsrc), tu = __shfl_sync(0xffffffffu, qb[i], tsrc);
-        third[i] = up ? tu : tl;
-      }
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       qq[0][e] = pack2(mine[2 * e], mine[2 * e + 1]);
       qq[1][e] = pack2(part[2 * e], part[2 * e + 1]);
-      if (NQ == 3) qq[NQ - 1][e] = pack2(third[2 * e], third[2 * e + 1]);
     }
   }
   const int head = (up ? 2 : 0) + h2;
   const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(ks_q + head * 4096) + pl;
   const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(vs_q + head * 4096) + pl;
-  float o[NQ][8];
-  ang_attn_head<NQ, NK, KS, CH>(qq, kb, vb, o);
+  float o[2][8];
+  ang_attn_head<2, NK, KS, CH>(qq, kb, vb, o);
   float oa[8], ob[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float recv = __shfl_sync(0xffffffffu, o[1][i], partner);  // my query, the partner's head
     oa[i] = up ? recv : o[0][i];
     ob[i] = up ? o[0][i] : recv;
-    if (NQ == 3) {
-      const float rl = __shfl_sync(0xffffffffu, o[NQ - 1][i], hlo), ru = __shfl_sync(0xffffffffu, o[NQ - 1][i], hup);
-      if (single) { oa[i] = rl; ob[i] = ru; }
-    }
   }
   uint4 hi, lo;
   split8(oa, hi, lo, fp32_mode);
@@ -148,6 +138,56 @@ LFT_DEVINL void ang_pair_heads(uint32_t tq, uint32_t to_hi, uint32_t to_lo, int 
   split8(ob, hi, lo, fp32_mode);
   tmem_st4u(to_hi + 8 + 4 * h2, hi);
   if (fp32_mode) tmem_st4u(to_lo + 8 + 4 * h2, lo);
+}
+
+// A = 5: the five rows of view 24 (one per pixel) have no partner view.  After the pair pass the last row warp of each
+// channel half runs this pass: unit (pixel s, relative head hh) goes to lane 8*hh + s (a quarter-warp reads one head: no bank
+// conflicts), the query comes from the row's own lane by shuffle (lane 12+s, or 28 for s = 4), the result goes back the
+// same way and overwrites the place-holder the pair pass wrote.  One head x one query per lane: ~1/4 of the pair pass.
+LFT_DEVINL void ang_singles25(uint32_t tq, uint32_t to_hi, uint32_t to_lo, int lane, const uint8_t* ks_q, const uint8_t* vs_q,
+                              bool fp32_mode) {
+  const int hh = lane >> 3, s = lane & 7;                 // unit of this lane (valid for s < 5)
+  const int sv = s < 5 ? s : 0;
+  const int qsrc = sv < 4 ? 12 + sv : 28;                 // lane that owns the row of pixel sv
+  const int my_s = lane == 28 ? 4 : lane - 12;            // pixel of the row this lane owns (meaningful on lanes 12..15, 28)
+  const bool owner = (lane >= 12 && lane < 16) || lane == 28;
+  f32x2 qq[1][4];
+  {
+    float mine[8];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {                         // every lane reads ITS row's Q of head h; the owners' values are picked up
+      float qh[8];
+      tmem_ld8(tq + 8 * h, qh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v = __shfl_sync(0xffffffffu, qh[i], qsrc);
+        if (h == hh) mine[i] = v;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) qq[0][e] = pack2(mine[2 * e], mine[2 * e + 1]);
+  }
+  const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(ks_q + hh * 4096) + sv;
+  const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(vs_q + hh * 4096) + sv;
+  float o[1][8];
+  ang_attn_head<1, 25, 5, 5>(qq, kb, vb, o);
+  tmem_wait_st();                                         // the pair pass's operand stores, re-read below
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {                           // owners collect head h from lane 8*h + their pixel
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __shfl_sync(0xffffffffu, o[0][i], 8 * h + (owner ? my_s : 0));
+    // tcgen05.ld/st are warp-collective (.sync.aligned): every lane executes them; the other lanes write their own
+    // (pair-pass) operand words back unchanged
+    uint4 hi, lo;
+    split8(r, hi, lo, fp32_mode);
+    const uint4 oh = tmem_ld4u(to_hi + 4 * h);
+    tmem_st4u(to_hi + 4 * h, owner ? hi : oh);
+    if (fp32_mode) {
+      const uint4 ol = tmem_ld4u(to_lo + 4 * h);
+      tmem_st4u(to_lo + 4 * h, owner ? lo : ol);
+    }
+  }
 }
 
 // NV > 0: compile-time number of views (scores kept in registers, single QK pass); NV == 0: runtime N.
@@ -367,31 +407,15 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
         LFT_TL(3);
         const int wq = warp & 3;
         const bool up = lane >= 16;
-        int partner = lane ^ 16, tsrc = lane, hlo = lane, hup = lane;
-        bool single = false;
-        if (NV == 25 && wq == 3) {  // pairs 48..59 in lanes 0..11 / 16..27; view 24 of pixel s in lane 12+s (s < 4) or 28 (s = 4)
-          const int l15 = lane & 15;
-          if (l15 >= 12) {
-            partner = lane;
-            single = a == 24;
-            if (single) { hlo = (pl + 2) % 5; hup = hlo + 16; }  // the pair holding views 18/19 or 20/21 of the same pixel
-          } else if (l15 < 5) {
-            const int px = (3 + l15) % 5;  // pixel of pair 48 + l15
-            tsrc = px < 4 ? 12 + px : 28;
-          }
-        }
+        int partner = lane ^ 16;
+        if (NV == 25 && wq == 3 && (lane & 15) >= 12) partner = lane;  // rows of view 24 / idle rows: no partner view
         const uint8_t* ks_q = ks_ptr + (4 * q) * 4096;
         const uint8_t* vs_q = vs_ptr + (4 * q) * 4096;
         const uint32_t tq = trow + 32 * q, to_hi = trow + 64 + 16 * q, to_lo = trow + 96 + 16 * q;
 #pragma unroll 1
-        for (int h2 = 0; h2 < 2; ++h2) {
-          if (NV == 25 && wq == 3)
-            ang_pair_heads<3, NV, kPPT, kCH>(tq, to_hi, to_lo, h2, up, partner, tsrc, single, hlo, hup, ks_q, vs_q, pl,
-                                             passes == 3);
-          else
-            ang_pair_heads<2, NV, kPPT, kCH>(tq, to_hi, to_lo, h2, up, partner, tsrc, single, hlo, hup, ks_q, vs_q, pl,
-                                             passes == 3);
-        }
+        for (int h2 = 0; h2 < 2; ++h2)
+          ang_pair_heads<NV, kPPT, kCH>(tq, to_hi, to_lo, h2, up, partner, ks_q, vs_q, pl, passes == 3);
+        if (NV == 25 && wq == 3) ang_singles25(tq, to_hi, to_lo, lane, ks_q, vs_q, passes == 3);
         LFT_TL(4);
         tmem_wait_st();
         tc_fence_before();
