@@ -436,11 +436,9 @@ int launch_mma_bench(int N, int K, int reps, int mode, int grid, int smem_bytes,
 
 // ------------------------------------------------------------------------------------------------ host
 constexpr size_t kSmemConv64 = kCtlBytes + 2 * kConvRows * 128 + 3 * 64 * 128;
-constexpr size_t kSmemConv128 = kCtlBytes + 2 * kConvRows * 128 + 3 * 128 * 128;
 
 int configure_conv() {
   CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemConv64));
-  CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemConv128));
   CUDA_TRY(cudaFuncSetAttribute(k_gemm_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return 0;
 }
@@ -454,12 +452,9 @@ int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* 
     return fail(LFT_ERR_ARG, "launch_conv3x3: fused conv_init0 needs N == 64 and the LR mosaic");
   W0Tab w0;
   memcpy(w0.w, h->w_conv0_host.data(), sizeof(w0.w));
-  Scope sc(h, N == 64 ? K_CONV64 : K_CONV128, st);
-  if (N == 64)
-    k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res);
-  else
-    k_conv3x3<128><<<grid, kThreads2, kSmemConv128, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0,
-                                                           h->cfg.ang_res);
+  Scope sc(h, K_CONV64, st);
+  if (N != 64) return fail(LFT_ERR_ARG, "launch_conv3x3: only the 64 -> 64 conv stack uses this kernel (the 64 -> 128 token embedding is part of k_spa_embed_qkv)");
+  k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res);
   return sc.finish();
 }
 
