@@ -140,8 +140,25 @@ static int finalize(Handle* h) {
   auto conv_pack = [&](const float* w, int N, const uint8_t** dst) {
     return upload_packed(h, N, N, 576, [=](int n, int k) { return w[((size_t)n * 64 + (k % 64)) * 9 + (k / 64)]; }, dst);
   };
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 3; ++i) {
     if ((rc = conv_pack(W("conv_init." + std::to_string(2 * i) + ".weight"), 64, &h->w_conv[i]))) return rc;
+    {  // stacked slabs for the fp32 path: per tap [k-chunk 8][rows 0..63 = bf16 hi | rows 64..127 = bf16 lo][8]
+      const float* w = W("conv_init." + std::to_string(2 * i) + ".weight");
+      std::vector<uint16_t> st((size_t)9 * 128 * 64);
+      for (int t = 0; t < 9; ++t)
+        for (int kc = 0; kc < 8; ++kc)
+          for (int n = 0; n < 64; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const float x = w[((size_t)n * 64 + kc * 8 + e) * 9 + t];
+              const uint16_t hi = f2bf(x), lo = f2bf(x - bf2f(hi));
+              st[(size_t)t * 128 * 64 + ((size_t)kc * 128 + n) * 8 + e] = hi;
+              st[(size_t)t * 128 * 64 + ((size_t)kc * 128 + 64 + n) * 8 + e] = lo;
+            }
+      void* d;
+      if ((rc = upload(h, st.data(), st.size() * 2, &d))) return rc;
+      h->w_conv_st[i] = (const uint8_t*)d;
+    }
+  }
   auto lin_pack = [&](const float* w, int row0, int N, int ldk, int col0, int K, const uint8_t** dst) {
     return upload_packed(h, N, N, K, [=](int n, int k) { return w[(size_t)(row0 + n) * ldk + col0 + k]; }, dst);
   };

@@ -67,6 +67,7 @@ struct Handle {
   std::vector<void*> allocs;
   std::vector<float> w_conv0_host;  // conv_init0 weight [64][9] (kernel parameter of the fused first/last conv)
   const uint8_t* w_conv[3] = {nullptr, nullptr, nullptr};
+  const uint8_t* w_conv_st[3] = {nullptr, nullptr, nullptr};  // fp32 mode: hi and lo rows stacked to one [128 x 64] slab per tap
   Layer layer[kLayers];
   const uint8_t* w_up = nullptr;
   const uint8_t* w_up3 = nullptr;  // upsampling.3.weight packed as a [16 x 64] bf16 hi/lo B operand (rows 9..15 zero)
@@ -119,8 +120,8 @@ int debug_timeline_spa(long long* out);
 int debug_timeline_ang(long long* out);
 int debug_timeline_embed(long long* out);
 int debug_timeline_ring_embed(long long* out);
-int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* out, const float* res, int V, int P,
-                   int epi, const float* lr, cudaStream_t st);
+int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, const uint8_t* wst, float* out, const float* res,
+                   int V, int P, int epi, const float* lr, cudaStream_t st);
 int launch_layout(Handle* h, const float* in, float* out, long long T, int C, int to_t32, cudaStream_t st);
 int launch_mma_bench(int N, int K, int reps, int mode, int grid, int smem_bytes, long long* host_out);
 int launch_selftest(const float* dA, int K, const uint8_t* dW, int N, float* dD, float* dX, int M, int passes,

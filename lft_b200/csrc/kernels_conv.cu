@@ -124,10 +124,13 @@ template <int N>
 __global__ void __launch_bounds__(kThreads2, 2)
 k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* __restrict__ out,
           const float* __restrict__ res, int V, int P, int passes, int epi, const float* __restrict__ lr,
-          const __grid_constant__ W0Tab w0, int A) {
+          const __grid_constant__ W0Tab w0, int A, const uint8_t* __restrict__ wst) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NST = 3;
-  constexpr uint32_t STAGE = N * 128;
+  // fp32 mode streams STACKED slabs: per tap one [128 x 64] B operand (rows 0..63 hi, 64..127 lo), so that A_hi is read once
+  // for A_hi*W_hi and A_hi*W_lo (one N = 128 MMA per k step, accumulator columns [0,64) | [64,128)) and A_lo*W_hi adds into
+  // [0,64) with an N = 64 MMA on the same slab: 14 KB instead of 18 KB of operands and 112 instead of 144 pipe cycles per k step.
+  constexpr uint32_t STAGE = 2 * N * 128;
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t s_base = smem_u32(smem);
   const uint32_t a_hi = s_base + kCtlBytes;
@@ -141,22 +144,59 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
   const long long G = (long long)V * VS;
   const long long g0 = (long long)blockIdx.x * 128;
 
-  cta_setup<NST>(ctl, warp, lane, kRowThreads2, N <= 64 ? 64 : 128, kWarpMma2);
+  cta_setup<NST>(ctl, warp, lane, kRowThreads2, 128, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
+  const bool stacked = passes == 3;
 
   GemmPhase ph{wp, (uint32_t)N, 9};
   if (warp == kWarpProducer2) {
 
     RingState<NST> rs;
-    ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
+    if (stacked) {  // one 16 KB slab per tap, consecutive in memory
+      for (uint32_t t = 0; t < 9; ++t) {
+        mbar_wait(empty0 + 8u * rs.stage, rs.phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full0 + 8u * rs.stage, STAGE);
+          bulk_g2s(ring + rs.stage * STAGE, wst + (size_t)t * STAGE, STAGE, full0 + 8u * rs.stage);
+        }
+        __syncwarp();
+        rs.advance();
+      }
+    } else {
+      ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
+    }
   } else if (warp == kWarpMma2) {
 
     RingState<NST> rs;
     mbar_wait(a_ready, 0);
     tc_fence_after();
     auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
-    ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi + kConvOff * 16, a_lo + kConvOff * 16,
-                          kConvRows * 16, 0, shift, tmem, true);
+    if (stacked) {
+      const uint32_t id_wide = umma_idesc_bf16(2 * N), id_half = umma_idesc_bf16(N);
+      const uint32_t a_lbo = kConvRows * 16, b_lbo = 2 * N * 16;
+      const uint32_t a_step = (2u * a_lbo) >> 4, b_step = (2u * b_lbo) >> 4;
+      const uint32_t ahi0 = umma_desc_lo(a_hi + kConvOff * 16, a_lbo), alo0 = umma_desc_lo(a_lo + kConvOff * 16, a_lbo);
+      for (uint32_t t = 0; t < 9; ++t) {
+        const uint32_t ah = ahi0 + (uint32_t)shift(t), al = alo0 + (uint32_t)shift(t);
+        mbar_wait(full0 + 8u * rs.stage, rs.phase);
+        tc_fence_after();
+        const uint32_t b0 = umma_desc_lo(ring + rs.stage * STAGE, b_lbo);
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j)   // A_hi x [W_hi; W_lo] -> columns [0,64) | [64,128)
+            umma_bf16(tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), id_wide, (t | j) ? 1u : 0u);
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j)   // A_lo x W_hi (rows 0..63 of the same slab) -> columns [0,64)
+            umma_bf16(tmem, umma_desc_from(al + j * a_step), umma_desc_from(b0 + j * b_step), id_half, 1u);
+          umma_commit(empty0 + 8u * rs.stage);
+        }
+        __syncwarp();
+        rs.advance();
+      }
+    } else {
+      ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi + kConvOff * 16, a_lo + kConvOff * 16,
+                            kConvRows * 16, 0, shift, tmem, true);
+    }
     umma_commit_elected(mma_done);
   } else {
     // ---- stage the input window: rows r <-> positions g0 - kConvOff + r, lanes <-> rows
@@ -198,7 +238,16 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
     float v[HC];
 #pragma unroll
     for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(trow + HC * q + 16 * c, v + 16 * c);
-    tmem_wait_ld();
+    if (stacked) {  // + A_hi*W_lo from columns [64,128)
+      float u[HC];
+#pragma unroll
+      for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(trow + N + HC * q + 16 * c, u + 16 * c);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < HC; ++i) v[i] += u[i];
+    } else {
+      tmem_wait_ld();
+    }
     if (tok >= 0) {
       if (epi & 1) {
 #pragma unroll
@@ -213,7 +262,7 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
     }
     tc_fence_before();
   }
-  cta_teardown(ctl, warp, N <= 64 ? 64 : 128, kWarpMma2);
+  cta_teardown(ctl, warp, 128, kWarpMma2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -435,7 +484,7 @@ int launch_mma_bench(int N, int K, int reps, int mode, int grid, int smem_bytes,
 }
 
 // ------------------------------------------------------------------------------------------------ host
-constexpr size_t kSmemConv64 = kCtlBytes + 2 * kConvRows * 128 + 3 * 64 * 128;
+constexpr size_t kSmemConv64 = kCtlBytes + 2 * kConvRows * 128 + 3 * 128 * 128;
 
 int configure_conv() {
   CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemConv64));
@@ -444,8 +493,8 @@ int configure_conv() {
 }
 
 // in == nullptr: the input is conv_init0(lr) computed on the fly; (epi & 2) with res == nullptr: so is the residual.
-int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* out, const float* res, int V, int P,
-                   int epi, const float* lr, cudaStream_t st) {
+int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, const uint8_t* wst, float* out, const float* res,
+                   int V, int P, int epi, const float* lr, cudaStream_t st) {
   const long long G = (long long)V * (P + 1) * (P + 1);
   const unsigned grid = (unsigned)((G + 127) / 128);
   if ((in == nullptr || ((epi & 2) && res == nullptr)) && (N != 64 || lr == nullptr))
@@ -454,7 +503,7 @@ int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, float* 
   memcpy(w0.w, h->w_conv0_host.data(), sizeof(w0.w));
   Scope sc(h, K_CONV64, st);
   if (N != 64) return fail(LFT_ERR_ARG, "launch_conv3x3: only the 64 -> 64 conv stack uses this kernel (the 64 -> 128 token embedding is part of k_spa_embed_qkv)");
-  k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res);
+  k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst);
   return sc.finish();
 }
 

@@ -46,9 +46,9 @@ int run_conv_init(Handle* h, const float* lr, float* out, float* tmp0, float* tm
   (void)T;
   int rc;
   (void)tmp0;  // conv_init0 is fused into the first conv's loader and the last conv's residual (never materialised)
-  if ((rc = launch_conv3x3(h, 64, nullptr, h->w_conv[0], tmp1, nullptr, V, P, 1, lr, st))) return rc;
-  if ((rc = launch_conv3x3(h, 64, tmp1, h->w_conv[1], tmp2, nullptr, V, P, 1, lr, st))) return rc;
-  if ((rc = launch_conv3x3(h, 64, tmp2, h->w_conv[2], out, nullptr, V, P, 3, lr, st))) return rc;
+  if ((rc = launch_conv3x3(h, 64, nullptr, h->w_conv[0], h->w_conv_st[0], tmp1, nullptr, V, P, 1, lr, st))) return rc;
+  if ((rc = launch_conv3x3(h, 64, tmp1, h->w_conv[1], h->w_conv_st[1], tmp2, nullptr, V, P, 1, lr, st))) return rc;
+  if ((rc = launch_conv3x3(h, 64, tmp2, h->w_conv[2], h->w_conv_st[2], out, nullptr, V, P, 3, lr, st))) return rc;
   return 0;
 }
 
