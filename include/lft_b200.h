@@ -92,6 +92,21 @@ int lft_integrate(lft_handle* h, const float* sr_crops, int32_t h0, int32_t w0, 
 int lft_divide(lft_handle* h, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch_begin, int32_t patch_end,
                float* patches, void* stream);
 
+/* The same four entry points for test.py's `--patch_size_for_test` / `--stride_for_test` (option.py:16-17; test.py:83-96
+ * passes them to LFdivide / LFintegrate; the entry points above are these with patch = 32, stride = 16):
+ *   patch  : 4..32 (the kernels' patch-size range), stride : 1..patch, bdr = (patch - stride) / 2 (utils.py:95)
+ *   patches  [n, 1, A*patch, A*patch];  sr_crops [n, A, A, stride*s, stride*s] = the block
+ *   [c0, c0 + stride*s)^2 of every SR patch view with c0 = ((patch - stride)*s) / 2 (utils.py:145,152).
+ * Views smaller than the mirror border, or tilings the reference would return empty, are LFT_ERR_ARG. */
+int lft_lf_num_patches_ex(int32_t h0, int32_t w0, int32_t patch, int32_t stride, int32_t* numU, int32_t* numV);
+int lft_divide_ex(lft_handle* h, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
+                  int32_t patch_begin, int32_t patch_end, float* patches, void* stream);
+int lft_forward_lf_ex(lft_handle* h, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
+                      int32_t patch_begin, int32_t patch_end, float* sr_crops, void* workspace, size_t ws_bytes,
+                      void* stream);
+int lft_integrate_ex(lft_handle* h, const float* sr_crops, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
+                     int32_t patch_begin, int32_t patch_end, float* sr_lf, void* stream);
+
 /* Stage-level entry points (device pointers, channels-last tokens [B, A*A, P, P, C]) for parity tests
  * against the reference's own sub-modules:
  *   conv_init : conv_init0 + conv_init + residual           LFT.py:65-66   lr [B,1,A*P,A*P] -> [T,64]

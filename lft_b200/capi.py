@@ -51,6 +51,13 @@ SIGNATURES = {
                                 C.c_void_p]),
     "lft_divide": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                              C.c_void_p]),
+    "lft_lf_num_patches_ex": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32_p, c_i32_p]),
+    "lft_forward_lf_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lft_integrate_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_void_p, C.c_void_p]),
+    "lft_divide_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_void_p, C.c_void_p]),
     "lft_stage_conv_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_size_t, C.c_void_p]),
     "lft_stage_ang": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,

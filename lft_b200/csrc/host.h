@@ -139,10 +139,11 @@ int run_conv_init(Handle* h, const float* lr, float* out, float* tmp0, float* tm
 int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cudaStream_t st);
 int run_spa(Handle* h, int layer, const float* in, float* out, const float* final_res, Workspace& w, int B, int P,
             cudaStream_t st);
-int launch_divide(Handle* h, const float* lf, float* patches, int h0, int w0, int numV, int p0, int n, cudaStream_t st);
-int launch_integrate(Handle* h, const float* crops, float* sr, int h0, int w0, int numV, int p0, int n,
+int launch_divide(Handle* h, const float* lf, float* patches, int h0, int w0, int numV, int p0, int n, int P, int S,
+                  cudaStream_t st);
+int launch_integrate(Handle* h, const float* crops, float* sr, int h0, int w0, int numV, int p0, int n, int S,
                      cudaStream_t st);
-int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float* pp, int B, int P, int crop_mode,
+int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float* pp, int B, int P, int crop_stride,
                  cudaStream_t st);
 
 }  // namespace lft

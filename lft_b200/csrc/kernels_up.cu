@@ -191,14 +191,13 @@ LFT_DEVINL void cubic_coeffs(float t, float* c) {
   c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
-// crop == 0: out = sr [B,1,H,H];   crop == 1: out = crops [B][A][A][16s][16s] (P must be 32)
+// crop == 0: out = sr [B,1,H,H];   crop == 1: out = crops [B][A][A][cs][cs], the block LFintegrate keeps of every SR view
+// (side cs = stride*s at offset c0 = ((P - stride)*s)/2, utils.py:145,152)
 __global__ void __launch_bounds__(256)
 k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* __restrict__ out, int B, int A, int P,
-            int s, int crop) {
+            int s, int crop, int cs, int c0) {
   const int H = A * P * s;
   const int Ps = P * s;
-  const int cs = crop ? 16 * s : Ps;     // side of the per-view output block
-  const int c0 = crop ? 8 * s : 0;       // offset of the block inside the SR view
   const long long total = (long long)B * A * A * cs * cs;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
@@ -258,21 +257,23 @@ k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* _
   out[crop ? gid : ((long long)b * H + Y) * H + X] = acc + bic;
 }
 
-// LFdivide (utils.py:91-138), patch size 32, stride 16, bdr 8. One thread per output element.
+// LFdivide (utils.py:91-138) for patch size P, stride S, bdr = (P - S) / 2 (test.py's defaults: 32, 16, 8).
+// One thread per output element.
 __global__ void __launch_bounds__(256)
-k_lf_divide(const float* __restrict__ lf, float* __restrict__ patches, int A, int h0, int w0, int numV, int p0, int n) {
-  const int W = A * 32;
+k_lf_divide(const float* __restrict__ lf, float* __restrict__ patches, int A, int h0, int w0, int numV, int p0, int n,
+            int P, int S, int bdr) {
+  const int W = A * P;
   const long long total = (long long)n * W * W;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const int col = (int)(gid % W), row = (int)((gid / W) % W);
   const int pi = p0 + (int)(gid / ((long long)W * W));
   const int kh = pi / numV, kw = pi - kh * numV;
-  const int u = row >> 5, y = row & 31, v = col >> 5, x = col & 31;
-  const int ey = kh * 16 + y, ex = kw * 16 + x;  // coordinates in the mirror-extended view
+  const int u = row / P, y = row - u * P, v = col / P, x = col - v * P;
+  const int ey = kh * S + y, ex = kw * S + x;  // coordinates in the mirror-extended view
   float val = 0.f;
-  if (ey < h0 + 16 && ex < w0 + 16) {
-    int jy = ey - 8, jx = ex - 8;
+  if (ey < h0 + 2 * bdr && ex < w0 + 2 * bdr) {  // beyond: the zero fill of dataE (utils.py:108)
+    int jy = ey - bdr, jx = ex - bdr;
     jy = jy < 0 ? -jy - 1 : (jy >= h0 ? 2 * h0 - 1 - jy : jy);
     jx = jx < 0 ? -jx - 1 : (jx >= w0 ? 2 * w0 - 1 - jx : jx);
     val = __ldg(lf + (long long)(u * h0 + jy) * (A * w0) + v * w0 + jx);
@@ -280,11 +281,10 @@ k_lf_divide(const float* __restrict__ lf, float* __restrict__ patches, int A, in
   patches[gid] = val;
 }
 
-// LFintegrate (utils.py:141-157) + test.py:100-101: crops [n][A][A][16s][16s] -> sr_lf [A*h0*s, A*w0*s]
+// LFintegrate (utils.py:141-157) + test.py:100-101: crops [n][A][A][cs][cs] (cs = stride*s) -> sr_lf [A*h0*s, A*w0*s]
 __global__ void __launch_bounds__(256)
 k_lf_integrate(const float* __restrict__ crops, float* __restrict__ sr, int A, int h0, int w0, int s, int numV, int p0,
-               int n) {
-  const int cs = 16 * s;
+               int n, int cs) {
   const long long total = (long long)n * A * A * cs * cs;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
@@ -302,8 +302,8 @@ int configure_up() {
   return 0;
 }
 
-// upsampling(mosaic(feat)) + bicubic(lr).  crop_mode: write only the kept central crops.
-int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float* pp, int B, int P, int crop_mode,
+// upsampling(mosaic(feat)) + bicubic(lr).  crop_stride > 0: write only the crops LFintegrate keeps for that LR stride.
+int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float* pp, int B, int P, int crop_stride,
                  cudaStream_t st) {
   const int A = h->cfg.ang_res, s = h->cfg.scale;
   const long long T = (long long)B * A * A * P * P;
@@ -314,30 +314,33 @@ int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float
     if ((rc = sc.finish())) return rc;
   }
   {
-    if (crop_mode && P != 32) return fail(LFT_ERR_ARG, "crop mode needs 32x32 patches");
-    const int cs = crop_mode ? 16 * s : P * s;
+    if (crop_stride < 0 || crop_stride > P) return fail(LFT_ERR_ARG, "crop stride %d outside [1, P=%d]", crop_stride, P);
+    const int cs = crop_stride ? crop_stride * s : P * s;
+    const int c0 = crop_stride ? ((P - crop_stride) * s) / 2 : 0;  // bdr of LFintegrate(pz = P*s, stride = S*s), utils.py:145
     const long long total = (long long)B * A * A * cs * cs;
     Scope sc(h, K_UP_GATHER, st);
-    k_up_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pp, lr, sr, B, A, P, s, crop_mode);
+    k_up_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pp, lr, sr, B, A, P, s, crop_stride ? 1 : 0, cs, c0);
     if ((rc = sc.finish())) return rc;
   }
   return 0;
 }
 
-int launch_divide(Handle* h, const float* lf, float* patches, int h0, int w0, int numV, int p0, int n, cudaStream_t st) {
+int launch_divide(Handle* h, const float* lf, float* patches, int h0, int w0, int numV, int p0, int n, int P, int S,
+                  cudaStream_t st) {
   const int A = h->cfg.ang_res;
-  const long long total = (long long)n * A * 32 * A * 32;
+  const long long total = (long long)n * A * P * A * P;
   Scope sc(h, K_DIVIDE, st);
-  k_lf_divide<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lf, patches, A, h0, w0, numV, p0, n);
+  k_lf_divide<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lf, patches, A, h0, w0, numV, p0, n, P, S, (P - S) / 2);
   return sc.finish();
 }
 
-int launch_integrate(Handle* h, const float* crops, float* sr, int h0, int w0, int numV, int p0, int n,
+int launch_integrate(Handle* h, const float* crops, float* sr, int h0, int w0, int numV, int p0, int n, int S,
                      cudaStream_t st) {
   const int A = h->cfg.ang_res, s = h->cfg.scale;
-  const long long total = (long long)n * A * A * 16 * s * 16 * s;
+  const int cs = S * s;
+  const long long total = (long long)n * A * A * cs * cs;
   Scope sc(h, K_INTEGRATE, st);
-  k_lf_integrate<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(crops, sr, A, h0, w0, s, numV, p0, n);
+  k_lf_integrate<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(crops, sr, A, h0, w0, s, numV, p0, n, cs);
   return sc.finish();
 }
 

@@ -52,9 +52,9 @@ int run_conv_init(Handle* h, const float* lr, float* out, float* tmp0, float* tm
   return 0;
 }
 
-// get_model.forward for one chunk of B patches (LFT.py:52-83).  crop_mode: `out` receives only the central
-// crops [B][A][A][16s][16s] that LFintegrate keeps.
-int run_forward_chunk(Handle* h, const float* lr, float* out, Workspace& w, int B, int P, int crop_mode,
+// get_model.forward for one chunk of B patches (LFT.py:52-83).  crop_stride > 0: `out` receives only the
+// crops [B][A][A][S*s][S*s] that LFintegrate keeps for LR stride S.
+int run_forward_chunk(Handle* h, const float* lr, float* out, Workspace& w, int B, int P, int crop_stride,
                       cudaStream_t st) {
   int rc;
   if ((rc = run_conv_init(h, lr, w.fres, w.f0, w.f1, w.f2, B, P, st))) return rc;
@@ -64,13 +64,29 @@ int run_forward_chunk(Handle* h, const float* lr, float* out, Workspace& w, int 
     if ((rc = run_spa(h, i, w.f1, w.f2, i == kLayers - 1 ? w.fres : nullptr, w, B, P, st))) return rc;
     x = w.f2;
   }
-  return run_upsample(h, w.f2, lr, out, w.pp, B, P, crop_mode, st);
+  return run_upsample(h, w.f2, lr, out, w.pp, B, P, crop_stride, st);
 }
 
-static void num_patches(int h0, int w0, int* numU, int* numV) {  // utils.py:95-104 with patch 32, stride 16
-  const int h = h0 + 16, w = w0 + 16;
-  *numU = (h - 32) / 16 + (((h - 32) % 16) ? 2 : 1);
-  *numV = (w - 32) / 16 + (((w - 32) % 16) ? 2 : 1);
+// numU / numV of LFdivide (utils.py:93-104) for patch size P and stride S (test.py:83 passes args.patch_size_for_test /
+// args.stride_for_test, defaults 32 / 16).  h - P may be negative (view smaller than a patch: Python's floor division then
+// gives one zero-padded patch as long as h - P > -S; below that the reference returns an empty tiling -> rejected here).
+static int num_patches_1d(int n0, int P, int S, int bdr) {
+  const int n = n0 + 2 * bdr;
+  if (n >= P) return (n - P) / S + (((n - P) % S) ? 2 : 1);
+  return (n - P > -S) ? 1 : 0;
+}
+
+static int tiling(int h0, int w0, int P, int S, int* numU, int* numV) {
+  if (P < 4 || P > 32) return fail(LFT_ERR_ARG, "patch size %d unsupported (4..32)", P);
+  if (S < 1 || S > P) return fail(LFT_ERR_ARG, "stride %d outside [1, patch size %d]", S, P);
+  const int bdr = (P - S) / 2;
+  if (h0 < 1 || w0 < 1 || h0 < bdr || w0 < bdr)
+    return fail(LFT_ERR_ARG, "light field %dx%d per view is smaller than the mirror border %d", h0, w0, bdr);
+  const int nu = num_patches_1d(h0, P, S, bdr), nv = num_patches_1d(w0, P, S, bdr);
+  if (nu < 1 || nv < 1) return fail(LFT_ERR_ARG, "light field %dx%d per view yields no patch of size %d at stride %d", h0, w0, P, S);
+  *numU = nu;
+  *numV = nv;
+  return 0;
 }
 
 }  // namespace lft
@@ -196,48 +212,66 @@ int lft_forward(lft_handle* hh, const float* lr, float* sr, int32_t B, int32_t P
   return 0;
 }
 
-int lft_lf_num_patches(int32_t h0, int32_t w0, int32_t* numU, int32_t* numV) {
-  if (!numU || !numV || h0 < 16 || w0 < 16) return fail(LFT_ERR_ARG, "bad light-field size");
+int lft_lf_num_patches_ex(int32_t h0, int32_t w0, int32_t patch, int32_t stride, int32_t* numU, int32_t* numV) {
+  if (!numU || !numV) return fail(LFT_ERR_ARG, "null argument");
   int a, b;
-  num_patches(h0, w0, &a, &b);
+  int rc = tiling(h0, w0, patch, stride, &a, &b);
+  if (rc) return rc;
   *numU = a;
   *numV = b;
   return 0;
 }
 
-int lft_divide(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t p0, int32_t p1, float* patches,
-               void* stream) {
+int lft_lf_num_patches(int32_t h0, int32_t w0, int32_t* numU, int32_t* numV) {
+  return lft_lf_num_patches_ex(h0, w0, 32, 16, numU, numV);
+}
+
+int lft_divide_ex(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride, int32_t p0,
+                  int32_t p1, float* patches, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
-  if (!h || !lr_lf || !patches || h0 < 16 || w0 < 16) return fail(LFT_ERR_ARG, "bad argument");
+  if (!h || !lr_lf || !patches) return fail(LFT_ERR_ARG, "bad argument");
   int nu, nv;
-  num_patches(h0, w0, &nu, &nv);
+  int rc = tiling(h0, w0, patch, stride, &nu, &nv);
+  if (rc) return rc;
   if (p0 < 0 || p1 > nu * nv || p0 > p1) return fail(LFT_ERR_ARG, "patch range [%d,%d) outside [0,%d)", p0, p1, nu * nv);
   if (p0 == p1) return 0;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  return launch_divide(h, lr_lf, patches, h0, w0, nv, p0, p1 - p0, (cudaStream_t)stream);
+  return launch_divide(h, lr_lf, patches, h0, w0, nv, p0, p1 - p0, patch, stride, (cudaStream_t)stream);
+}
+
+int lft_divide(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t p0, int32_t p1, float* patches,
+               void* stream) {
+  return lft_divide_ex(hh, lr_lf, h0, w0, 32, 16, p0, p1, patches, stream);
+}
+
+int lft_integrate_ex(lft_handle* hh, const float* sr_crops, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
+                     int32_t p0, int32_t p1, float* sr_lf, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !sr_crops || !sr_lf) return fail(LFT_ERR_ARG, "bad argument");
+  int nu, nv;
+  int rc = tiling(h0, w0, patch, stride, &nu, &nv);
+  if (rc) return rc;
+  if (p0 < 0 || p1 > nu * nv || p0 > p1) return fail(LFT_ERR_ARG, "patch range [%d,%d) outside [0,%d)", p0, p1, nu * nv);
+  if (p0 == p1) return 0;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  return launch_integrate(h, sr_crops, sr_lf, h0, w0, nv, p0, p1 - p0, stride, (cudaStream_t)stream);
 }
 
 int lft_integrate(lft_handle* hh, const float* sr_crops, int32_t h0, int32_t w0, int32_t p0, int32_t p1, float* sr_lf,
                   void* stream) {
-  Handle* h = reinterpret_cast<Handle*>(hh);
-  if (!h || !sr_crops || !sr_lf || h0 < 16 || w0 < 16) return fail(LFT_ERR_ARG, "bad argument");
-  int nu, nv;
-  num_patches(h0, w0, &nu, &nv);
-  if (p0 < 0 || p1 > nu * nv || p0 > p1) return fail(LFT_ERR_ARG, "patch range [%d,%d) outside [0,%d)", p0, p1, nu * nv);
-  if (p0 == p1) return 0;
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
-  return launch_integrate(h, sr_crops, sr_lf, h0, w0, nv, p0, p1 - p0, (cudaStream_t)stream);
+  return lft_integrate_ex(hh, sr_crops, h0, w0, 32, 16, p0, p1, sr_lf, stream);
 }
 
-int lft_forward_lf(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t p0, int32_t p1, float* sr_crops,
-                   void* ws, size_t ws_bytes, void* stream) {
+int lft_forward_lf_ex(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
+                      int32_t p0, int32_t p1, float* sr_crops, void* ws, size_t ws_bytes, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
-  const int P = 32;
-  int rc = check_ready(h, 1, P);
-  if (rc) return rc;
-  if (!lr_lf || !sr_crops || !ws || h0 < 16 || w0 < 16) return fail(LFT_ERR_ARG, "bad argument");
+  if (!h) return fail(LFT_ERR_ARG, "null handle");
+  if (!lr_lf || !sr_crops || !ws) return fail(LFT_ERR_ARG, "bad argument");
   int nu, nv;
-  num_patches(h0, w0, &nu, &nv);
+  int rc = tiling(h0, w0, patch, stride, &nu, &nv);
+  if (rc) return rc;
+  const int P = patch;
+  if ((rc = check_ready(h, 1, P))) return rc;
   if (p0 < 0 || p1 > nu * nv || p0 > p1) return fail(LFT_ERR_ARG, "patch range [%d,%d) outside [0,%d)", p0, p1, nu * nv);
   size_t per;
   lft_workspace_bytes(hh, 1, P, &per);
@@ -249,16 +283,21 @@ int lft_forward_lf(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, i
     const long long cap = (1LL << 30) / ((long long)A * P * s * A * P * s);
     if (chunk > cap) chunk = cap < 1 ? 1 : cap;
   }
-  const size_t crop_stride = (size_t)A * A * 16 * s * 16 * s;
+  const size_t crop_stride = (size_t)A * A * stride * s * stride * s;
   for (long long q0 = p0; q0 < p1; q0 += chunk) {
     const int Bc = (int)((p1 - q0) < chunk ? (p1 - q0) : chunk);
     const long long T = (long long)Bc * A * A * P * P;
     Workspace w = carve(ws, T, s);
-    if ((rc = launch_divide(h, lr_lf, w.lrp, h0, w0, nv, (int)q0, Bc, (cudaStream_t)stream))) return rc;
-    if ((rc = run_forward_chunk(h, w.lrp, sr_crops + (q0 - p0) * crop_stride, w, Bc, P, 1, (cudaStream_t)stream)))
+    if ((rc = launch_divide(h, lr_lf, w.lrp, h0, w0, nv, (int)q0, Bc, P, stride, (cudaStream_t)stream))) return rc;
+    if ((rc = run_forward_chunk(h, w.lrp, sr_crops + (q0 - p0) * crop_stride, w, Bc, P, stride, (cudaStream_t)stream)))
       return rc;
   }
   return 0;
+}
+
+int lft_forward_lf(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t p0, int32_t p1, float* sr_crops,
+                   void* ws, size_t ws_bytes, void* stream) {
+  return lft_forward_lf_ex(hh, lr_lf, h0, w0, 32, 16, p0, p1, sr_crops, ws, ws_bytes, stream);
 }
 
 int lft_debug_timeline(int32_t which, int64_t* out64) {

@@ -161,38 +161,41 @@ class Engine:
         return out
 
     # ---------------------------------------------------------------- light-field path
-    def num_patches(self, h0: int, w0: int):
+    # patch / stride = test.py's --patch_size_for_test / --stride_for_test (option.py:16-17, defaults 32 / 16)
+    def num_patches(self, h0: int, w0: int, patch: int = 32, stride: int = 16):
         nu, nv = C.c_int32(), C.c_int32()
-        capi.check(self.lib.lft_lf_num_patches(h0, w0, C.byref(nu), C.byref(nv)))
+        capi.check(self.lib.lft_lf_num_patches_ex(h0, w0, patch, stride, C.byref(nu), C.byref(nv)))
         return int(nu.value), int(nv.value)
 
-    def divide(self, lr_lf: torch.Tensor, p0: int, p1: int) -> torch.Tensor:
+    def divide(self, lr_lf: torch.Tensor, p0: int, p1: int, patch: int = 32, stride: int = 16) -> torch.Tensor:
         self._check_in(lr_lf, "lr_lf")
         h0, w0 = lr_lf.shape[0] // self.A, lr_lf.shape[1] // self.A
-        out = torch.empty(p1 - p0, 1, self.A * 32, self.A * 32, dtype=torch.float32, device=lr_lf.device)
-        capi.check(self.lib.lft_divide(self._h, _ptr(lr_lf), h0, w0, p0, p1, _ptr(out), _stream()))
+        out = torch.empty(p1 - p0, 1, self.A * patch, self.A * patch, dtype=torch.float32, device=lr_lf.device)
+        capi.check(self.lib.lft_divide_ex(self._h, _ptr(lr_lf), h0, w0, patch, stride, p0, p1, _ptr(out), _stream()))
         return out
 
     def forward_lf_crops(self, lr_lf: torch.Tensor, p0: int, p1: int, out: Optional[torch.Tensor] = None,
-                         max_ws_bytes: Optional[int] = None) -> torch.Tensor:
-        """LFdivide + forward for patches [p0,p1) -> kept crops [p1-p0, A, A, 16s, 16s]."""
+                         max_ws_bytes: Optional[int] = None, patch: int = 32, stride: int = 16) -> torch.Tensor:
+        """LFdivide + forward for patches [p0,p1) -> kept crops [p1-p0, A, A, stride*s, stride*s]."""
         self._check_in(lr_lf, "lr_lf")
         h0, w0 = lr_lf.shape[0] // self.A, lr_lf.shape[1] // self.A
         n = p1 - p0
-        c = 16 * self.s
+        c = stride * self.s
         if out is None:
             out = torch.empty(n, self.A, self.A, c, c, dtype=torch.float32, device=lr_lf.device)
         if n > 0:
-            ws = self._workspace(n, 32, max_ws_bytes)
-            capi.check(self.lib.lft_forward_lf(self._h, _ptr(lr_lf), h0, w0, p0, p1, _ptr(out), _ptr(ws), ws.numel(),
-                                               _stream()))
+            ws = self._workspace(n, patch, max_ws_bytes)
+            capi.check(self.lib.lft_forward_lf_ex(self._h, _ptr(lr_lf), h0, w0, patch, stride, p0, p1, _ptr(out),
+                                                  _ptr(ws), ws.numel(), _stream()))
         return out
 
-    def integrate(self, crops: torch.Tensor, h0: int, w0: int, p0: int, p1: int, sr_lf: torch.Tensor) -> torch.Tensor:
+    def integrate(self, crops: torch.Tensor, h0: int, w0: int, p0: int, p1: int, sr_lf: torch.Tensor,
+                  patch: int = 32, stride: int = 16) -> torch.Tensor:
         self._check_in(crops, "crops")
         self._check_in(sr_lf, "sr_lf")
         if p1 > p0:
-            capi.check(self.lib.lft_integrate(self._h, _ptr(crops), h0, w0, p0, p1, _ptr(sr_lf), _stream()))
+            capi.check(self.lib.lft_integrate_ex(self._h, _ptr(crops), h0, w0, patch, stride, p0, p1, _ptr(sr_lf),
+                                                 _stream()))
         return sr_lf
 
     # ---------------------------------------------------------------- profiling

@@ -27,10 +27,12 @@ def psnr_per_view(sr_sai: torch.Tensor, hr_sai: torch.Tensor, angRes: int) -> to
 
 
 @torch.no_grad()
-def test(test_loader: Iterable, device, net, angRes: Optional[int] = None) -> Tuple[float, List[torch.Tensor]]:
-    """Mirror of test.py:73-111: returns (mean PSNR over the loader, list of SR SAI mosaics on the CPU)."""
+def test(test_loader: Iterable, device, net, angRes: Optional[int] = None, patch_size_for_test: int = 32,
+         stride_for_test: int = 16) -> Tuple[float, List[torch.Tensor]]:
+    """Mirror of test.py:73-111: returns (mean PSNR over the loader, list of SR SAI mosaics on the CPU).
+    patch_size_for_test / stride_for_test are the reference's `args` of the same names (option.py:16-17; test.py:83,96)."""
     A = angRes if angRes is not None else net.angRes
-    sr = LightFieldSR(net)
+    sr = LightFieldSR(net, patch=patch_size_for_test, stride=stride_for_test)
     psnrs, outs = [], []
     for Lr_SAI_y, Hr_SAI_y in test_loader:
         lr = Lr_SAI_y.squeeze().to(device, torch.float32).contiguous()   # test.py:77

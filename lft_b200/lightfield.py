@@ -22,7 +22,8 @@ STRIDE = 16   # option.py:17  stride_for_test
 
 
 def num_patches(h0: int, w0: int, patch: int = PATCH, stride: int = STRIDE) -> Tuple[int, int]:
-    """numU, numV of LFdivide (utils/utils.py:95-104)."""
+    """numU, numV of LFdivide (utils/utils.py:95-104); Python floor division as in the reference, so a view smaller
+    than a patch yields one zero-padded patch (the C side, `lft_lf_num_patches_ex`, must agree)."""
     bdr = (patch - stride) // 2
     h, w = h0 + 2 * bdr, w0 + 2 * bdr
     nu = (h - patch) // stride + (2 if (h - patch) % stride else 1)
@@ -66,9 +67,10 @@ class LightFieldSR:
     """`sr = LightFieldSR(net_or_engine)(lr_sai)` with lr_sai [A*h0, A*w0] on the GPU ->
     sr_sai [A*h0*s, A*w0*s] (the `Sr_SAI_y` of test.py:100-101)."""
 
-    def __init__(self, net_or_engine, max_ws_bytes: Optional[int] = None):
+    def __init__(self, net_or_engine, max_ws_bytes: Optional[int] = None, patch: int = PATCH, stride: int = STRIDE):
         self._src = net_or_engine
         self.max_ws_bytes = max_ws_bytes
+        self.patch, self.stride = int(patch), int(stride)   # args.patch_size_for_test / args.stride_for_test
 
     def _engine(self, device) -> Engine:
         if isinstance(self._src, Engine):
@@ -80,15 +82,16 @@ class LightFieldSR:
         eng = self._engine(lr_sai.device)
         A, s = eng.A, eng.s
         h0, w0 = lr_sai.shape[0] // A, lr_sai.shape[1] // A
-        nu, nv = eng.num_patches(h0, w0)
+        nu, nv = eng.num_patches(h0, w0, self.patch, self.stride)
         ranges = patch_ranges(nu * nv, world)
         p0, p1 = ranges[rank]
-        crops = eng.forward_lf_crops(lr_sai.contiguous(), p0, p1, max_ws_bytes=self.max_ws_bytes)
+        crops = eng.forward_lf_crops(lr_sai.contiguous(), p0, p1, max_ws_bytes=self.max_ws_bytes, patch=self.patch,
+                                     stride=self.stride)
         allc = gather_crops(crops, ranges, rank, world, group)
         if allc is None:
             return None
         sr = torch.empty(A * h0 * s, A * w0 * s, dtype=torch.float32, device=lr_sai.device)
-        eng.integrate(allc, h0, w0, 0, nu * nv, sr)
+        eng.integrate(allc, h0, w0, 0, nu * nv, sr, self.patch, self.stride)
         return sr
 
 
@@ -104,8 +107,9 @@ class HostPipeline:
         pipe.drain()                                   # the current stream now waits for every output copy
     """
 
-    def __init__(self, net_or_engine, depth: int = 2, max_ws_bytes: Optional[int] = None):
-        self._sr = LightFieldSR(net_or_engine, max_ws_bytes)
+    def __init__(self, net_or_engine, depth: int = 2, max_ws_bytes: Optional[int] = None, patch: int = PATCH,
+                 stride: int = STRIDE):
+        self._sr = LightFieldSR(net_or_engine, max_ws_bytes, patch, stride)
         self._depth = depth
         self._slots: List[dict] = []
         self._copy: Optional[torch.cuda.Stream] = None   # device -> host

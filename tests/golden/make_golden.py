@@ -95,9 +95,40 @@ def run_tiler(ref_utils, name, A, h0, w0, s, seed, store_full):
     print(name, "numU,numV", numU, numV, "identity", rec["identity_ok"][0])
 
 
+# test.py:83,96 pass args.patch_size_for_test / args.stride_for_test (option.py:16-17) to the tiler: hash-only goldens
+# for non-default values, incl. an odd patch-stride difference (LR border 5 but SR crop offset 11*s//2), no overlap
+# (stride == patch) and a view smaller than one patch (h0 + 2*bdr < patch: one zero-padded patch row).
+TILER_PS_CASES = [  # name, A, h0, w0, s, seed, patch, stride
+    ("tilerps_A3_40x56_s2_p32_s24", 3, 40, 56, 2, 5, 32, 24),
+    ("tilerps_A3_40x56_s2_p32_s32", 3, 40, 56, 2, 5, 32, 32),
+    ("tilerps_A5_44x60_s4_p16_s8", 5, 44, 60, 4, 7, 16, 8),
+    ("tilerps_A3_40x56_s4_p32_s21", 3, 40, 56, 4, 8, 32, 21),
+    ("tilerps_A3_12x50_s2_p32_s16", 3, 12, 50, 2, 9, 32, 16),
+    ("tilerps_A2_33x47_s2_p24_s10", 2, 33, 47, 2, 10, 24, 10),
+]
+
+
+def run_tiler_ps(ref_utils, name, A, h0, w0, s, seed, patch, stride):
+    lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, seed))
+    sub = ref_utils.LFdivide(lf, A, patch, stride)
+    numU, numV = sub.shape[:2]
+    g = torch.arange(numU * numV * (A * patch * s) ** 2, dtype=torch.float32).remainder(65521.0)
+    fake_sr = g.view(numU, numV, A * patch * s, A * patch * s)
+    integ = ref_utils.LFintegrate(fake_sr, A, patch * s, stride * s, h0 * s, w0 * s)
+    np.savez(os.path.join(HERE, f"{name}.npz"),
+             meta=np.array([A, h0, w0, s, seed, numU, numV, patch, stride]),
+             divide_sha256=np.frombuffer(hashlib.sha256(sub.numpy().tobytes()).digest(), dtype=np.uint8),
+             integrate_sha256=np.frombuffer(hashlib.sha256(integ.numpy().tobytes()).digest(), dtype=np.uint8))
+    print(name, "numU,numV", numU, numV)
+
+
 def main():
     torch.manual_seed(0)
     ref_model, ref_utils = import_reference()
+    if "--tiler-ps-only" in sys.argv[1:]:   # add the patch/stride goldens without regenerating the others
+        for c in TILER_PS_CASES:
+            run_tiler_ps(ref_utils, *c)
+        return
     # name, A, s, h(=w), B, seed, stages
     run_case(ref_model, "fwd_A5_s4_h8_B1", 5, 4, 8, 1, 10, True)
     run_case(ref_model, "fwd_A5_s2_h8_B2", 5, 2, 8, 2, 11, False)
@@ -107,6 +138,8 @@ def main():
     run_tiler(ref_utils, "tiler_A3_40x56_s2", 3, 40, 56, 2, 5, True)
     run_tiler(ref_utils, "tiler_A5_108x156_s4", 5, 108, 156, 4, 3, False)
     run_tiler(ref_utils, "tiler_A5_128x128_s4", 5, 128, 128, 4, 2, False)
+    for c in TILER_PS_CASES:
+        run_tiler_ps(ref_utils, *c)
 
 
 if __name__ == "__main__":

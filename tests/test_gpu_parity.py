@@ -198,6 +198,52 @@ def test_device_tiler_bit_exact(A, h0, w0, s, seed):
     assert torch.equal(sr.cpu(), want.permute(0, 2, 1, 3).reshape(A * h0 * s, A * w0 * s))
 
 
+@pytest.mark.parametrize("A,h0,w0,s,seed,patch,stride", [
+    (3, 40, 56, 2, 5, 32, 24), (3, 40, 56, 2, 5, 32, 32), (5, 44, 60, 4, 7, 16, 8), (3, 40, 56, 4, 8, 32, 21),
+    (3, 12, 50, 2, 9, 32, 16), (2, 33, 47, 2, 10, 24, 10)])
+def test_device_tiler_patch_stride_bit_exact(A, h0, w0, s, seed, patch, stride):
+    """lft_divide_ex / lft_integrate_ex for test.py's --patch_size_for_test / --stride_for_test (same cases as the
+    reference-hashed goldens `tests/golden/tilerps_*`, which pin the oracle used here)."""
+    sd = synth.synth_state_dict(A, s, 1)
+    eng = _engine(A, s, sd)
+    lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, seed))
+    ref = O.lf_divide(lf, A, patch, stride)
+    nu, nv = ref.shape[:2]
+    assert eng.num_patches(h0, w0, patch, stride) == (nu, nv)
+    got = eng.divide(lf.cuda(), 0, nu * nv, patch, stride).cpu()
+    assert torch.equal(got.view(nu, nv, A * patch, A * patch), ref)
+    Ps = patch * s
+    fake = torch.arange(nu * nv * (A * Ps) ** 2, dtype=torch.float32).remainder(65521.0).view(nu, nv, A * Ps, A * Ps)
+    want = O.lf_integrate(fake, A, Ps, stride * s, h0 * s, w0 * s)
+    c, b = stride * s, (Ps - stride * s) // 2
+    crops = fake.view(nu * nv, A, Ps, A, Ps)[:, :, b:b + c, :, b:b + c].permute(0, 1, 3, 2, 4).contiguous()
+    sr = torch.full((A * h0 * s, A * w0 * s), -1.0).cuda()
+    eng.integrate(crops.cuda(), h0, w0, 0, nu * nv, sr, patch, stride)
+    assert torch.equal(sr.cpu(), want.permute(0, 2, 1, 3).reshape(A * h0 * s, A * w0 * s))
+
+
+@pytest.mark.parametrize("patch,stride,npatch", [(32, 24, 6), (16, 8, 35), (32, 21, 6), (24, 24, 6)])
+def test_full_light_field_patch_stride_vs_oracle(patch, stride, npatch):
+    """test.py:83-101 with non-default --patch_size_for_test / --stride_for_test, CUDA path vs the oracle's test loop;
+    the crop path must equal the central crops of forward(divide) bit for bit."""
+    from lft_b200.lightfield import LightFieldSR
+    A, s, h0, w0 = 5, 2, 40, 56
+    sd = synth.synth_state_dict(A, s, 6)
+    lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, 6))
+    want, n = O.infer_light_field(sd, lf, A, s, patch=patch, stride=stride, mode="window", batch=8)
+    assert n == npatch
+    eng = _engine(A, s, sd)
+    got = LightFieldSR(eng, patch=patch, stride=stride)(lf.cuda()).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max() <= TOL_FP32
+    patches = eng.divide(lf.cuda(), 0, n, patch, stride)
+    full = eng.forward(patches)
+    Ps = patch * s
+    c, b = stride * s, (Ps - stride * s) // 2
+    crops = full.view(n, A, Ps, A, Ps)[:, :, b:b + c, :, b:b + c].permute(0, 1, 3, 2, 4).contiguous()
+    assert torch.equal(crops, eng.forward_lf_crops(lf.cuda(), 0, n, patch=patch, stride=stride))
+
+
 def test_full_light_field_vs_oracle_test_loop():
     """test.py:83-101 end to end on a ragged light field (3x4 patches), CUDA path vs oracle."""
     from lft_b200.lightfield import LightFieldSR

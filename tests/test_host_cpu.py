@@ -91,6 +91,36 @@ def test_patch_partition_and_counts():
     assert LF.patch_ranges(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
 
 
+def test_c_tiling_counts_match_reference_formula():
+    """lft_lf_num_patches_ex (C, truncating division) against LFdivide's count formula (Python floor division,
+    utils.py:93-104) over a sweep of view sizes / patch sizes / strides, incl. views smaller than one patch."""
+    lib = capi.load()
+    nu, nv = C.c_int32(), C.c_int32()
+    checked = 0
+    for patch in (4, 8, 16, 24, 31, 32):
+        for stride in sorted({1, 2, patch // 2, patch - 3, patch - 1, patch}):
+            if stride < 1:
+                continue
+            bdr = (patch - stride) // 2
+            for h0, w0 in ((patch - 2 * bdr, 3 * patch + 1), (bdr, 57), (19, 19), (40, 56), (108, 156), (5, 128)):
+                want = LF.num_patches(h0, w0, patch, stride)
+                rc = lib.lft_lf_num_patches_ex(h0, w0, patch, stride, C.byref(nu), C.byref(nv))
+                if h0 < max(bdr, 1) or w0 < max(bdr, 1) or min(want) < 1:
+                    assert rc == -1, (h0, w0, patch, stride)
+                    continue
+                assert rc == 0, (h0, w0, patch, stride, lib.lft_last_error())
+                assert (nu.value, nv.value) == want, (h0, w0, patch, stride)
+                lf = torch.zeros(2 * h0, 2 * w0)
+                if patch * stride <= 256 or stride >= patch // 2:  # keep the oracle calls cheap
+                    assert tuple(O.lf_divide(lf, 2, patch, stride).shape[:2]) == want
+                checked += 1
+    assert checked > 100
+    # the two-argument entry point is the reference default (32, 16)
+    assert lib.lft_lf_num_patches(108, 156, C.byref(nu), C.byref(nv)) == 0 and (nu.value, nv.value) == (7, 10)
+    for bad in ((64, 64, 33, 16), (64, 64, 3, 1), (64, 64, 32, 0), (64, 64, 16, 17), (3, 64, 32, 16)):
+        assert lib.lft_lf_num_patches_ex(*bad, C.byref(nu), C.byref(nv)) == -1, bad
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"

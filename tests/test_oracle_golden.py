@@ -75,6 +75,27 @@ def test_tiler_matches_reference(golden_dir, name):
     assert torch.equal(ident, lf)
 
 
+TILER_PS = ["tilerps_A3_40x56_s2_p32_s24", "tilerps_A3_40x56_s2_p32_s32", "tilerps_A5_44x60_s4_p16_s8",
+            "tilerps_A3_40x56_s4_p32_s21", "tilerps_A3_12x50_s2_p32_s16", "tilerps_A2_33x47_s2_p24_s10"]
+
+
+@pytest.mark.parametrize("name", TILER_PS)
+def test_tiler_patch_stride_matches_reference(golden_dir, name):
+    """LFdivide / LFintegrate with test.py's --patch_size_for_test / --stride_for_test (test.py:83,96) at non-default
+    values: the oracle against hashes of the reference's own output (odd patch-stride difference, no overlap, view
+    smaller than a patch, small patches)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    A, h0, w0, s, seed, numU, numV, patch, stride = (int(x) for x in g["meta"])
+    lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, seed))
+    sub = O.lf_divide(lf, A, patch, stride)
+    assert tuple(sub.shape[:2]) == (numU, numV)
+    assert hashlib.sha256(sub.numpy().tobytes()).digest() == bytes(g["divide_sha256"])
+    fake = torch.arange(numU * numV * (A * patch * s) ** 2, dtype=torch.float32).remainder(65521.0)
+    fake = fake.view(numU, numV, A * patch * s, A * patch * s)
+    integ = O.lf_integrate(fake, A, patch * s, stride * s, h0 * s, w0 * s)
+    assert hashlib.sha256(integ.numpy().tobytes()).digest() == bytes(g["integrate_sha256"])
+
+
 def test_synth_checkpoint_format(tmp_path):
     sd = synth.synth_state_dict(5, 4, 0)
     assert len(sd) == 78 and sum(v.numel() for v in sd.values()) == 1163392
