@@ -12,11 +12,15 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT_DIR = os.path.join(HERE, "_lib")
+# LFT_VARIANT=<name> builds / loads an experimental variant next to the product library (lft_b200/_lib_<name>/), compiled
+# with the extra flags in LFT_DEFINES (e.g. "-DLFT_EXPERIMENT_X"); a variant that exists is loaded as is.  A/B timing only.
+VARIANT = os.environ.get("LFT_VARIANT", "")
+OUT_DIR = os.path.join(HERE, "_lib" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(OUT_DIR, "liblft_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("LFT_DEFINES", "").split()
 if os.environ.get("LFT_TIMELINE"):
     FLAGS.append("-DLFT_TIMELINE")
 if os.environ.get("LFT_EXPERIMENT_NOSTORE"):    # timing experiment (wrong results): k_spa_embed_qkv* never store
@@ -44,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     stamp = os.path.join(OUT_DIR, "build.sha256")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and (VARIANT or open(stamp).read() == dig):
         return LIB
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}; cannot build liblft_b200.so")

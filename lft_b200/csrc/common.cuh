@@ -498,6 +498,25 @@ LFT_DEVINL float hsum2(f32x2 v) {
   return a + b;
 }
 
+// 16-byte global store of data this kernel never reads back (Q/K/V/tok/O planes).  Cache policy, measured A/B with
+// tools/gpu_ab.py (profiles/r01_ab_cache_hints.md): default .L1::no_allocate (k_spa_embed_qkv -3.7 ... -6 %);
+// -DLFT_EXPERIMENT_ST=0 plain st.global; =1 st.global.cs (evict-first, -3.1 %); =3 .wt (no change).  The same hint on the
+// other kernels' outputs, and ld.global.nc.L1::no_allocate on their read-once inputs, changed nothing (+-0.5 %).
+#ifndef LFT_EXPERIMENT_ST
+#define LFT_EXPERIMENT_ST 2
+#endif
+LFT_DEVINL void st_stream_v4(float* p, const float4& v) {
+#if LFT_EXPERIMENT_ST == 0
+  *reinterpret_cast<float4*>(p) = v;
+#elif LFT_EXPERIMENT_ST == 1
+  __stcs(reinterpret_cast<float4*>(p), v);
+#elif LFT_EXPERIMENT_ST == 2
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+  __stwt(reinterpret_cast<float4*>(p), v);
+#endif
+}
+
 LFT_DEVINL float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

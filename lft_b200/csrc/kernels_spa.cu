@@ -33,8 +33,7 @@ LFT_DEVINL long long planar_off(long long v, int head, int y, int j, int x, int 
 LFT_DEVINL void planar_store16(float* base, long long v, int head, int y, int x, int P, const float* d) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<float4*>(base + planar_off(v, head, y, j, x, P)) =
-        make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+    st_stream_v4(base + planar_off(v, head, y, j, x, P), make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]));
 }
 
 // split 16 fp32 values into two k-chunks (kc0, kc0+1) of the K=128 A operand (hi at A, lo at A+32K)
@@ -165,8 +164,8 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
           if (ok) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<float4*>(tok + t32_off(token, 16 * q + 4 * c + i, 32)) =
-                  make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+              st_stream_v4(tok + t32_off(token, 16 * q + 4 * c + i, 32),
+                           make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]));
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) z[16 * c + i] += t[i];
@@ -271,10 +270,14 @@ LFT_DEVINL void axpy16(f32x2* o, float p, const ulonglong2& a, const ulonglong2&
 // CTA = (view, head, block of kAttnRB query rows): the K and V planes of rows [r0-2, r0+RB+2) are contiguous
 // in the planar layout and are staged in shared memory with two bulk copies (TMA engine).  Softmax is
 // evaluated online, one key row at a time (5 scores per query live at once).
-constexpr int kAttnRB = 8;
+#ifndef LFT_ATTN_RB
+#define LFT_ATTN_RB 8
+#endif
+constexpr int kAttnRB = LFT_ATTN_RB;       // query rows per CTA (A/B: 16 stages 20 key rows for 16 instead of 12 for 8)
+constexpr int kAttnThreads = kAttnRB * 16;  // 32 x-lanes x RB/2 row pairs
 constexpr size_t kSmemAttn = 2 * (kAttnRB + 4) * 4 * 32 * 16 + 16;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kAttnThreads)
 k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ Vv,
            float* __restrict__ O, int P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -393,7 +396,7 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
       ulonglong2 r;
       r.x = mul2(o0[2 * j], i02);
       r.y = mul2(o0[2 * j + 1], i02);
-      *reinterpret_cast<ulonglong2*>(O + base + y0 * rowstride + j * jstride) = r;
+      st_stream_v4(O + base + y0 * rowstride + j * jstride, *reinterpret_cast<const float4*>(&r));
     }
     if (two) {
       const float i1 = 1.f / l1;
@@ -403,7 +406,7 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
         ulonglong2 r;
         r.x = mul2(o1[2 * j], i12);
         r.y = mul2(o1[2 * j + 1], i12);
-        *reinterpret_cast<ulonglong2*>(O + base + (y0 + 1) * rowstride + j * jstride) = r;
+        st_stream_v4(O + base + (y0 + 1) * rowstride + j * jstride, *reinterpret_cast<const float4*>(&r));
       }
     }
   }
@@ -703,7 +706,7 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
   {
     Scope sc(h, K_SPA_ATTN, st);
     const int nblk = (P + kAttnRB - 1) / kAttnRB;
-    k_spa_attn<<<(unsigned)(V * 8 * nblk), 128, kSmemAttn, st>>>(w.q, w.k, w.v, w.o, P);
+    k_spa_attn<<<(unsigned)(V * 8 * nblk), kAttnThreads, kSmemAttn, st>>>(w.q, w.k, w.v, w.o, P);
     if ((rc = sc.finish())) return rc;
   }
   {
