@@ -30,11 +30,11 @@ ks = d["kernels"]; st = sum(v["ms_per_step"] for v in ks.values())
 out.append(f"\n## live CUDA-event shares from bench.py (same build, {bench}), ms per step / share; whole step {d['ms_per_step']:.2f} ms")
 for k, v in sorted(ks.items(), key=lambda kv: -kv[1]["ms_per_step"]):
     out.append(f"{k:22s} {v['ms_per_step']:7.3f} ms  share {100 * v['ms_per_step'] / st:5.1f}%  algorithmic {v['tflops']:7.1f} TFLOP/s")
-out.append("""
+out.append(f"""
 ## commands (one gpurun call; every ncu pass after the same bench command had exited 0 without ncu)
 python bench.py --steps 20 --warmup 5
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/v10_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline
-ncu --set full --clock-control none -k regex:'k_spa_ffn|k_spa_attn|k_ang|k_spa_embed|k_conv3x3' -s 35 -c 7 -o gpurun_out/prof_v10 python bench.py --steps 2 --warmup 3 --no-cpu-baseline
-ncu --set full --clock-control none -k regex:'k_up_gemm|k_up_gather' -s 2 -c 2 -o gpurun_out/prof_v7_up python bench.py --steps 2 --warmup 3 --no-cpu-baseline""")
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag.split('_')[-1]}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline
+ncu --set full --clock-control none --import-source on -k regex:'k_spa_ffn|k_spa_attn|k_ang|k_spa_embed|k_conv3x3|k_up_gemm|k_up_gather' -s 40 -c 9 -o gpurun_out/prof_{tag.split('_')[-1]} python bench.py --steps 2 --warmup 3 --no-cpu-baseline
+(the launch list is cut at 400 launches)""")
 open(f"profiles/{tag}_ncu_summary.md", "w").write("\n".join(out) + "\n")
 print("\n".join(out[-40:]))
