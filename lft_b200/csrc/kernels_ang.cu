@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kThreads2, 2)
 k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __restrict__ wqk,
       const uint8_t* __restrict__ wv, const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1,
       const uint8_t* __restrict__ w2, const __grid_constant__ Tab512 tab, const float* __restrict__ peqk,
-      const float* __restrict__ pe, int Nrt, int PP, long long npix, int passes) {
+      const float* __restrict__ pe, int Nrt, int PP, long long npix, int passes, int ntiles) {
   const int N = NV > 0 ? NV : Nrt;
   // Specialised views-per-pixel counts (A = 3, 5, 7, 9) pair two views of one pixel in lanes l / l+16 and share every K/V read
   // between them (kPair); pixels per tile: 12 / 5 / 2 / 1, softmax chunk = A keys.
@@ -224,14 +224,19 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
   if (warp == kWarpProducer2) {
 
     RingState<kAngNST> rs;
-    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_qk, passes);
-    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_v, passes);
-    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes);
-    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes);
-    ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // the ring runs ahead into the next tile's first slabs
+      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_qk, passes);
+      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_v, passes);
+      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_o, passes);
+      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_1, passes);
+      ring_produce<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes);
+    }
   } else if (warp == kWarpMma2) {
 
     RingState<kAngNST> rs;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // a_ready / mma_done complete four phases per tile, so the literal parities 0,1,0,1 below hold for every tile; the
+    // next tile's first MMA is gated by a_ready arrivals the row owners make only after their phase 4 reads of this tile
     mbar_wait(a_ready, 0);
     tc_fence_after();
     ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_qk, passes, R1, R1 + 16384, LBO, 0, NoShift{},
@@ -263,6 +268,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       ring_consume_mma<kAngNST>(rs, ring, kAngStage, full0, empty0, g_2, passes, R1, R2, LBO, 8 * LBO, NoShift{},
                                 tmem + 128, true);
     umma_commit_elected(mma_done);
+    }  // tiles
   } else {
     // ------------------------------------------------------------ row owner: row m, channel half q
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
@@ -301,17 +307,23 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       pl = m - a * PPT;
       kvrow = m;
     }
-    const long long gp = (long long)blockIdx.x * PPT + pl;
-    const bool rowok = (a < N) && (gp < npix);
-    long long tok = 0;
-    if (rowok) {
-      const unsigned b = (unsigned)gp / (unsigned)PP;  // npix < 2^31
-      const int p = (int)((unsigned)gp - b * (unsigned)PP);
-      tok = (b * N + a) * PP + p;
-    }
-    const int aa = rowok ? a : 0;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int bar_id = 1 + (warp & 3);
+    // token of this row in tile t (-1: idle row / beyond the last pixel)
+    auto row_token = [&](int t) -> long long {
+      const long long gp = (long long)t * PPT + pl;
+      if (a >= N || gp >= npix) return -1;
+      const unsigned b = (unsigned)gp / (unsigned)PP;  // npix < 2^31
+      const int p = (int)((unsigned)gp - b * (unsigned)PP);
+      return ((long long)b * N + a) * PP + p;
+    };
+    // persistent: the CTA walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ... keeping its TMEM, barriers and the
+    // weight ring (which already holds the next tile's first slabs when its phase 0 publishes)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long tok_or = row_token(tile);
+    const bool rowok = tok_or >= 0;
+    const long long tok = rowok ? tok_or : 0;
+    const int aa = rowok ? a : 0;
     float mean, rstd;
 
     LFT_TL(0);
@@ -537,6 +549,14 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     }
 
     LFT_TL(7);
+    {  // the next tile's X rows: pull them into L2 while FFN1 runs (phase 0 of the next tile then misses only L1)
+      const int nt = tile + (int)gridDim.x;
+      const long long ntok = nt < ntiles ? row_token(nt) : -1;
+      if (ntok >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) prefetch_l2(in + t32_off(ntok, 8 * q + i, 16));
+      }
+    }
     // ---- phase 3: hidden = relu(LN2-folded D[0,128)), own 64 columns -> K=128 operand (hi in R1, lo in R2)
     mbar_wait(mma_done, 0);
     tc_fence_after();
@@ -605,6 +625,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     }
     tc_fence_before();
     LFT_TL(11);
+    }  // tiles
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
 }
@@ -632,14 +653,15 @@ int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cud
   const int N = h->cfg.ang_res * h->cfg.ang_res;
   const long long npix = (long long)B * P * P;
   const int PPT = N == 9 ? 12 : N == 25 ? 5 : N == 49 ? 2 : N == 81 ? 1 : 128 / N;  // keep in step with kPPT in k_ang
-  const unsigned grid = (unsigned)((npix + PPT - 1) / PPT);
+  const unsigned ntiles = (unsigned)((npix + PPT - 1) / PPT);
+  const unsigned grid = ntiles < 2u * h->num_sms ? ntiles : 2u * h->num_sms;  // persistent: two CTAs per SM
   const Layer& L = h->layer[layer];
   Tab512 ta;
   memcpy(ta.v, L.a_tab.data(), sizeof(ta.v));
   Scope sc(h, K_ANG, st);
 #define LFT_ANG_LAUNCH(NV)                                                                                          \
   k_ang<NV><<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, ta, L.a_peqk, \
-                                               h->pe_ang, N, P * P, npix, h->passes())
+                                               h->pe_ang, N, P * P, npix, h->passes(), (int)ntiles)
   if (N == 25) LFT_ANG_LAUNCH(25);
   else if (N == 9) LFT_ANG_LAUNCH(9);
   else if (N == 49) LFT_ANG_LAUNCH(49);
