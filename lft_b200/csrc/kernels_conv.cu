@@ -120,17 +120,23 @@ LFT_DEVINL void conv_stage_window_lr(const float* __restrict__ lr, const W0Tab& 
   }
 }
 
+// Persistent: a CTA (two per SM) walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ... with TWO accumulators (tile k uses
+// TMEM columns [128 (k&1), +128)): once tile k's MMAs are complete the row owners stage tile k+1's window, publish it, and run
+// tile k's epilogue (accumulator loads, LeakyReLU / residual, stores) UNDER tile k+1's MMAs.  a_ready and mma_done complete one
+// phase per tile (parity k&1).  The accumulator of tile k is overwritten by tile k+2, whose MMAs are gated by a_ready arrivals
+// every row owner makes after its epilogue of tile k; the window is overwritten only after mma_done of the tile that read it.
 template <int N>
 __global__ void __launch_bounds__(kThreads2, 2)
 k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* __restrict__ out,
           const float* __restrict__ res, int V, int P, int passes, int epi, const float* __restrict__ lr,
-          const __grid_constant__ W0Tab w0, int A, const uint8_t* __restrict__ wst) {
+          const __grid_constant__ W0Tab w0, int A, const uint8_t* __restrict__ wst, int ntiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NST = 3;
   // fp32 mode streams STACKED slabs: per tap one [128 x 64] B operand (rows 0..63 hi, 64..127 lo), so that A_hi is read once
   // for A_hi*W_hi and A_hi*W_lo (one N = 128 MMA per k step, accumulator columns [0,64) | [64,128)) and A_lo*W_hi adds into
   // [0,64) with an N = 64 MMA on the same slab: 14 KB instead of 18 KB of operands and 112 instead of 144 pipe cycles per k step.
   constexpr uint32_t STAGE = 2 * N * 128;
+  static_assert(2 * N <= 128, "one accumulator = 128 TMEM columns");
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t s_base = smem_u32(smem);
   const uint32_t a_hi = s_base + kCtlBytes;
@@ -142,9 +148,10 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
   const int P1 = P + 1;
   const long long VS = (long long)P1 * P1;
   const long long G = (long long)V * VS;
-  const long long g0 = (long long)blockIdx.x * 128;
+  const int first = blockIdx.x, step = gridDim.x;
+  const int ntl = first < ntiles ? (ntiles - first + step - 1) / step : 0;
 
-  cta_setup<NST>(ctl, warp, lane, kRowThreads2, 128, kWarpMma2);
+  cta_setup<NST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
   const bool stacked = passes == 3;
 
@@ -152,117 +159,129 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
   if (warp == kWarpProducer2) {
 
     RingState<NST> rs;
-    if (stacked) {  // one 16 KB slab per tap, consecutive in memory
-      for (uint32_t t = 0; t < 9; ++t) {
-        mbar_wait(empty0 + 8u * rs.stage, rs.phase ^ 1u);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(full0 + 8u * rs.stage, STAGE);
-          bulk_g2s(ring + rs.stage * STAGE, wst + (size_t)t * STAGE, STAGE, full0 + 8u * rs.stage);
+    for (int k = 0; k < ntl; ++k) {
+      if (stacked) {  // one 16 KB slab per tap, consecutive in memory
+        for (uint32_t t = 0; t < 9; ++t) {
+          mbar_wait(empty0 + 8u * rs.stage, rs.phase ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full0 + 8u * rs.stage, STAGE);
+            bulk_g2s(ring + rs.stage * STAGE, wst + (size_t)t * STAGE, STAGE, full0 + 8u * rs.stage);
+          }
+          __syncwarp();
+          rs.advance();
         }
-        __syncwarp();
-        rs.advance();
+      } else {
+        ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
       }
-    } else {
-      ring_produce<NST>(rs, ring, STAGE, full0, empty0, ph, passes);
     }
   } else if (warp == kWarpMma2) {
 
     RingState<NST> rs;
-    mbar_wait(a_ready, 0);
-    tc_fence_after();
     auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
-    if (stacked) {
-      const uint32_t id_wide = umma_idesc_bf16(2 * N), id_half = umma_idesc_bf16(N);
-      const uint32_t a_lbo = kConvRows * 16, b_lbo = 2 * N * 16;
-      const uint32_t a_step = (2u * a_lbo) >> 4, b_step = (2u * b_lbo) >> 4;
-      const uint32_t ahi0 = umma_desc_lo(a_hi + kConvOff * 16, a_lbo), alo0 = umma_desc_lo(a_lo + kConvOff * 16, a_lbo);
-      for (uint32_t t = 0; t < 9; ++t) {
-        const uint32_t ah = ahi0 + (uint32_t)shift(t), al = alo0 + (uint32_t)shift(t);
-        mbar_wait(full0 + 8u * rs.stage, rs.phase);
-        tc_fence_after();
-        const uint32_t b0 = umma_desc_lo(ring + rs.stage * STAGE, b_lbo);
-        if (elect_one()) {
+    for (int k = 0; k < ntl; ++k) {
+      const uint32_t acc = tmem + 128u * (uint32_t)(k & 1);
+      mbar_wait(a_ready, (uint32_t)(k & 1));
+      tc_fence_after();
+      if (stacked) {
+        const uint32_t id_wide = umma_idesc_bf16(2 * N), id_half = umma_idesc_bf16(N);
+        const uint32_t a_lbo = kConvRows * 16, b_lbo = 2 * N * 16;
+        const uint32_t a_step = (2u * a_lbo) >> 4, b_step = (2u * b_lbo) >> 4;
+        const uint32_t ahi0 = umma_desc_lo(a_hi + kConvOff * 16, a_lbo), alo0 = umma_desc_lo(a_lo + kConvOff * 16, a_lbo);
+        for (uint32_t t = 0; t < 9; ++t) {
+          const uint32_t ah = ahi0 + (uint32_t)shift(t), al = alo0 + (uint32_t)shift(t);
+          mbar_wait(full0 + 8u * rs.stage, rs.phase);
+          tc_fence_after();
+          const uint32_t b0 = umma_desc_lo(ring + rs.stage * STAGE, b_lbo);
+          if (elect_one()) {
 #pragma unroll
-          for (uint32_t j = 0; j < 4; ++j)   // A_hi x [W_hi; W_lo] -> columns [0,64) | [64,128)
-            umma_bf16(tmem, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), id_wide, (t | j) ? 1u : 0u);
+            for (uint32_t j = 0; j < 4; ++j)   // A_hi x [W_hi; W_lo] -> columns [0,64) | [64,128)
+              umma_bf16(acc, umma_desc_from(ah + j * a_step), umma_desc_from(b0 + j * b_step), id_wide, (t | j) ? 1u : 0u);
 #pragma unroll
-          for (uint32_t j = 0; j < 4; ++j)   // A_lo x W_hi (rows 0..63 of the same slab) -> columns [0,64)
-            umma_bf16(tmem, umma_desc_from(al + j * a_step), umma_desc_from(b0 + j * b_step), id_half, 1u);
-          umma_commit(empty0 + 8u * rs.stage);
+            for (uint32_t j = 0; j < 4; ++j)   // A_lo x W_hi (rows 0..63 of the same slab) -> columns [0,64)
+              umma_bf16(acc, umma_desc_from(al + j * a_step), umma_desc_from(b0 + j * b_step), id_half, 1u);
+            umma_commit(empty0 + 8u * rs.stage);
+          }
+          __syncwarp();
+          rs.advance();
         }
-        __syncwarp();
-        rs.advance();
+      } else {
+        ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi + kConvOff * 16, a_lo + kConvOff * 16,
+                              kConvRows * 16, 0, shift, acc, true);
       }
-    } else {
-      ring_consume_mma<NST>(rs, ring, STAGE, full0, empty0, ph, passes, a_hi + kConvOff * 16, a_lo + kConvOff * 16,
-                            kConvRows * 16, 0, shift, tmem, true);
+      umma_commit_elected(mma_done);
     }
-    umma_commit_elected(mma_done);
   } else {
-    // ---- stage the input window: rows r <-> positions g0 - kConvOff + r, lanes <-> rows
-    if (N == 64 && in == nullptr)
-      conv_stage_window_lr(lr, w0, A, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
-    else
-      conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
-    fence_proxy_async_smem();
-    mbar_arrive(a_ready);
+    // ---- stage the input window of tile k: rows r <-> positions g0 - kConvOff + r, lanes <-> rows
+    auto stage = [&](int k) {
+      const long long g0 = (long long)(first + k * step) * 128;
+      if (N == 64 && in == nullptr)
+        conv_stage_window_lr(lr, w0, A, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
+      else
+        conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
+      fence_proxy_async_smem();
+      mbar_arrive(a_ready);
+    };
+    if (ntl > 0) stage(0);
 
     // ---- epilogue: row m <-> position, column half q
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     constexpr int HC = N / 2;  // own columns
-    const long long g = g0 + m;
-    long long tok = -1;
-    float4 r4[HC / 4];
-    if (g < G) {
-      const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
-      const unsigned v = gu / vsu;
-      const int qq = (int)(gu - v * vsu);
-      const int y = qq / P1, x = qq - y * P1;
-      if (y < P && x < P) tok = (long long)((v * P + y) * P + x);
-      if (N == 64 && (epi & 2) && res == nullptr && tok >= 0) {  // residual = conv_init0(lr), own 32 channels
-        float t[9];
-        conv0_taps(lr, A, P, v, y, x, t);
-        float* rr = reinterpret_cast<float*>(r4);
-        if (q == 0) conv0_channels<0, 32>(w0, t, rr);
-        else conv0_channels<32, 32>(w0, t, rr);
+    for (int k = 0; k < ntl; ++k) {
+      mbar_wait(mma_done, (uint32_t)(k & 1));
+      tc_fence_after();
+      if (k + 1 < ntl) stage(k + 1);  // the window is free; tile k+1's MMAs (other accumulator) run under the epilogue below
+      const long long g = (long long)(first + k * step) * 128 + m;
+      long long tok = -1;
+      float4 r4[HC / 4];
+      if (g < G) {
+        const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
+        const unsigned v = gu / vsu;
+        const int qq = (int)(gu - v * vsu);
+        const int y = qq / P1, x = qq - y * P1;
+        if (y < P && x < P) tok = (long long)((v * P + y) * P + x);
+        if (N == 64 && (epi & 2) && res == nullptr && tok >= 0) {  // residual = conv_init0(lr), own 32 channels
+          float t[9];
+          conv0_taps(lr, A, P, v, y, x, t);
+          float* rr = reinterpret_cast<float*>(r4);
+          if (q == 0) conv0_channels<0, 32>(w0, t, rr);
+          else conv0_channels<32, 32>(w0, t, rr);
+        }
       }
-    }
-    if ((epi & 2) && res != nullptr && tok >= 0) {
+      if ((epi & 2) && res != nullptr && tok >= 0) {
 #pragma unroll
-      for (int i = 0; i < HC / 4; ++i)
-        r4[i] = __ldg(reinterpret_cast<const float4*>(res + t32_off(tok, q * (HC / 4) + i, N / 4)));
-    }
-    mbar_wait(mma_done, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float v[HC];
-#pragma unroll
-    for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(trow + HC * q + 16 * c, v + 16 * c);
-    if (stacked) {  // + A_hi*W_lo from columns [64,128)
-      float u[HC];
-#pragma unroll
-      for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(trow + N + HC * q + 16 * c, u + 16 * c);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < HC; ++i) v[i] += u[i];
-    } else {
-      tmem_wait_ld();
-    }
-    if (tok >= 0) {
-      if (epi & 1) {
-#pragma unroll
-        for (int i = 0; i < HC; ++i) v[i] = lrelu02(v[i]);
+        for (int i = 0; i < HC / 4; ++i)
+          r4[i] = __ldg(reinterpret_cast<const float4*>(res + t32_off(tok, q * (HC / 4) + i, N / 4)));
       }
+      const uint32_t trow = tmem + 128u * (uint32_t)(k & 1) + ((uint32_t)((warp & 3) * 32) << 16);
+      float v[HC];
 #pragma unroll
-      for (int i = 0; i < HC / 4; ++i) {
-        float4 o4 = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        if (epi & 2) { o4.x += r4[i].x; o4.y += r4[i].y; o4.z += r4[i].z; o4.w += r4[i].w; }
-        *reinterpret_cast<float4*>(out + t32_off(tok, q * (HC / 4) + i, N / 4)) = o4;
+      for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(trow + HC * q + 16 * c, v + 16 * c);
+      if (stacked) {  // + A_hi*W_lo from columns [64,128)
+        float u[HC];
+#pragma unroll
+        for (int c = 0; c < HC / 16; ++c) tmem_ld16_nowait(trow + N + HC * q + 16 * c, u + 16 * c);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < HC; ++i) v[i] += u[i];
+      } else {
+        tmem_wait_ld();
+      }
+      if (tok >= 0) {
+        if (epi & 1) {
+#pragma unroll
+          for (int i = 0; i < HC; ++i) v[i] = lrelu02(v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < HC / 4; ++i) {
+          float4 o4 = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (epi & 2) { o4.x += r4[i].x; o4.y += r4[i].y; o4.z += r4[i].z; o4.w += r4[i].w; }
+          *reinterpret_cast<float4*>(out + t32_off(tok, q * (HC / 4) + i, N / 4)) = o4;
+        }
       }
     }
     tc_fence_before();
   }
-  cta_teardown(ctl, warp, 128, kWarpMma2);
+  cta_teardown(ctl, warp, 256, kWarpMma2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -496,14 +515,15 @@ int configure_conv() {
 int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, const uint8_t* wst, float* out, const float* res,
                    int V, int P, int epi, const float* lr, cudaStream_t st) {
   const long long G = (long long)V * (P + 1) * (P + 1);
-  const unsigned grid = (unsigned)((G + 127) / 128);
+  const unsigned ntiles = (unsigned)((G + 127) / 128);
+  const unsigned grid = ntiles < 2u * h->num_sms ? ntiles : 2u * h->num_sms;  // persistent: two CTAs per SM
   if ((in == nullptr || ((epi & 2) && res == nullptr)) && (N != 64 || lr == nullptr))
     return fail(LFT_ERR_ARG, "launch_conv3x3: fused conv_init0 needs N == 64 and the LR mosaic");
   W0Tab w0;
   memcpy(w0.w, h->w_conv0_host.data(), sizeof(w0.w));
   Scope sc(h, K_CONV64, st);
   if (N != 64) return fail(LFT_ERR_ARG, "launch_conv3x3: only the 64 -> 64 conv stack uses this kernel (the 64 -> 128 token embedding is part of k_spa_embed_qkv)");
-  k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst);
+  k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst, (int)ntiles);
   return sc.finish();
 }
 
