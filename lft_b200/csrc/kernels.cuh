@@ -125,6 +125,25 @@ LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, u
   }
 }
 
+// L2 prefetch of the rows conv_stage_window will read for the tile at g0 (same row <-> thread mapping)
+LFT_DEVINL void conv_prefetch_window(const float* __restrict__ in, long long g0, long long G, long long VS, int P, int tid) {
+  const int P1 = P + 1;
+  for (int r = tid; r < kConvRows; r += kRowThreads2) {
+    const long long g = g0 - kConvOff + r;
+    if (g >= 0 && g < G) {
+      const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
+      const unsigned v = gu / vsu;
+      const int qq = (int)(gu - v * vsu);
+      const int y = qq / P1, x = qq - y * P1;
+      if (y < P && x < P) {
+        const long long tok = (long long)((v * P + y) * P + x);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) prefetch_l2(in + t32_off(tok, i, 16));
+      }
+    }
+  }
+}
+
 // LayerNorm statistics of a row whose two halves live in two partner threads (same lane, warps w / w+4).
 // Each thread reduces its own H values (two-pass, in registers), publishes (mean_q, M2_q) through 4 TMEM
 // columns it owns, and combines with its partner's pair (Chan's parallel variance).  eps = 1e-5.

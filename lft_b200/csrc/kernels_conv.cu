@@ -278,6 +278,9 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
           *reinterpret_cast<float4*>(out + t32_off(tok, q * (HC / 4) + i, N / 4)) = o4;
         }
       }
+      // pull the window of tile k+2 into L2 while tile k+1's MMAs run (-4.6 %; the same hint in k_spa_embed_qkv, whose
+      // staging is already hidden under its Q MMA, changed nothing)
+      if (in != nullptr && k + 2 < ntl) conv_prefetch_window(in, (long long)(first + (k + 2) * step) * 128, G, VS, P, tid);
     }
     tc_fence_before();
   }
