@@ -552,6 +552,23 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
     const float4* u1 = reinterpret_cast<const float4*>(tab.v);        // [u_1 256 | c_1 256] (constant bank)
     const float4* c1 = reinterpret_cast<const float4*>(tab.v + 256);
 
+    {  // speculative L2 prefetch of the O pieces and token row of the tile 2 CTAs x 148 SMs ahead, i.e. of the CTA that follows
+       // on some SM about one tile time from now (k_spa_ffn -1 %; a persistent version of this kernel was 7 % slower)
+      const long long tn = t + 296ll * 128;
+      if (tn < T) {
+        const unsigned tnu = (unsigned)tn, vn = tnu / PP;
+        const int pn = (int)(tnu - vn * PP), yn = pn / P, xn = pn - yn * P;
+        const float* obn = O + planar_off(vn, 4 * q, yn, 0, xn, P);
+        const long long hs = (long long)PP * 16, js = (long long)P * 4;
+        const float* tgn = tok + t32_off(tnu, 16 * q, 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) prefetch_l2(obn + c * hs + j * js);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) prefetch_l2(tgn + 128 * i);
+      }
+    }
     // phase 2: hidden[:, :128] (own 64 columns of D[0,128)) -> A
     await();
     float dh[64];  // all four accumulator loads in flight, one wait

@@ -125,6 +125,10 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
       fence_proxy_async_smem();
       mbar_arrive(a1_ready);
     }
+    if (t + 296ll * 128 < T) {  // speculative L2 prefetch of the rows of the tile 2 CTAs x 148 SMs ahead (-1.8 %)
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) prefetch_l2(feat + t32_off(tu + 296u * 128u, 8 * q + kc, 16));
+    }
     float pj[4][5];                             // [sub-pixel column j][own tap]
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
