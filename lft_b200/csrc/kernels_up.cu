@@ -22,14 +22,21 @@ constexpr uint32_t kLbo64 = 128 * 16;
 
 // The 1x1 conv (64 -> 64 s^2, one [64 x 64] GEMM per sub-pixel ij, PixelShuffle order) and the 64 -> 9 tap contraction of
 // the final 3x3 conv are TWO chained tcgen05 GEMMs per sub-pixel:
-//   G1(ij): D1[b] = A1 (feat tile, smem)  x  W_up[ij]^T          (N = 64, weights through the ring, double-buffered D1)
+//   G1(ij): D1[b] = A1 (feat tile, smem)  x  W_up[ij]^T          (N = 64, weights through the ring, two buffers)
 //   G2(ij): D2    = lrelu(D1[b]) (TMEM A operand, TS form)  x  W3^T   (N = 16: taps 0..8 + 7 zero rows, W3 resident in smem)
 // The row owners only convert: D1 -> LeakyReLU -> bf16 hi/lo -> TMEM, and read the 9 per-tap partial sums back (the CUDA-core
 // 64 x 9 FFMA contraction this replaces made the kernel issue-bound at 82 %).  One completed HR row (s sub-pixels) is stored
 // per tap as one 16-byte vector; thread (row, q) owns taps 0..4 (q = 0) or 5..8 (q = 1).
-//   TMEM: D1[0] [0,64) | D1[1] [64,128) | A2 hi [128,160) lo [160,192) | D2 [192,208)
-//   barriers: aux[0] A1 + W3 staged (256) | aux[2], aux[3] D1[b] full (commit) | a_ready: A2 ready = D1[b] drained (256) |
-//   mma_done: D2 full (commit) | aux[1]: D2 drained (256).  Re-arrivals are separated by waits on the MMA in between.
+// Pipelining: the row owners convert D1[b] IN PLACE into the A2 operand (64 fp32 columns ->
+// 32 hi + 32 lo columns of the same region X[b]; the two threads of a row exchange a pair barrier first because each writes
+// into the half its partner reads), so A2 is double-buffered for free, D2 gets two buffers, and the read-back of D2(ij) is
+// deferred by one iteration: the conversion of sub-pixel ij+1 runs under G2(ij) instead of waiting for it.
+//   TMEM: X[0] [0,64) | X[1] [64,128) (D1, then A2 hi [0,32) lo [32,64) of the region) | D2[0] [128,144) | D2[1] [144,160)
+//   barriers (every one has its own per-buffer instance so that no thread can arrive twice on one phase):
+//     aux[0] A1 + W3 staged (256) | aux[2], aux[3] D1[b] full (commit) | a_ready, aux[1] A2[b] ready (256) |
+//     mma_done, full[4] D2[c] full (commit) | empty[4], empty[5] D2[c] drained (256).
+//   G1(ij+2) overwrites X[b] that G2(ij) reads as its A operand: the MMA warp waits for G2(ij)'s commit before issuing it (the
+//   wait is off the critical path, G1(ij+2) is needed two iterations later).
 __global__ void __launch_bounds__(kThreads2, 2)
 k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const uint8_t* __restrict__ w3p,
           float* __restrict__ Pp, long long T, int A, int P, int s, int passes) {
@@ -41,14 +48,21 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a1_ready = smem_u32(&ctl->aux[0]);
   const uint32_t d1_full0 = smem_u32(&ctl->aux[2]);  // aux[2], aux[3]
-  const uint32_t a2_ready = smem_u32(&ctl->a_ready);
-  const uint32_t d2_full = smem_u32(&ctl->mma_done);
-  const uint32_t d2_free = smem_u32(&ctl->aux[1]);
+  const uint32_t a2r0 = smem_u32(&ctl->a_ready), a2r1 = smem_u32(&ctl->aux[1]);
+  const uint32_t d2f0 = smem_u32(&ctl->mma_done), d2f1 = smem_u32(&ctl->full[4]);
+  const uint32_t d2e0 = smem_u32(&ctl->empty[4]), d2e1 = smem_u32(&ctl->empty[5]);
+  auto a2_ready = [=](int b) { return b ? a2r1 : a2r0; };   // selects, not indexed arrays (those would live in local memory)
+  auto d2_full = [=](int b) { return b ? d2f1 : d2f0; };
+  auto d2_free = [=](int b) { return b ? d2e1 : d2e0; };
+  static_assert(kUpNST <= 4, "full[4], empty[4..5] double as D2 barriers");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   cta_setup<kUpNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   if (tid == 0) {  // accumulator-full barriers are completed by one tcgen05.commit each
     mbar_init(d1_full0, 1);
     mbar_init(d1_full0 + 8, 1);
+    mbar_init(d2_full(1), 1);
+    mbar_init(d2_free(0), kRowThreads2);
+    mbar_init(d2_free(1), kRowThreads2);
     mbar_fence_init();
   }
   __syncthreads();
@@ -77,10 +91,12 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
     if (s2 > 1) g1(1);
     const uint32_t idesc = umma_idesc_bf16(16);
     const uint32_t bh = umma_desc_lo(W3, 256), bl = umma_desc_lo(W3 + 2048, 256);  // LBO = 16 rows x 16 B
-    const uint32_t a_hi = tmem + 128, a_lo = tmem + 160, d2 = tmem + 192;
     for (int ij = 0; ij < s2; ++ij) {
-      mbar_wait(a2_ready, ij & 1);
-      if (ij > 0) mbar_wait(d2_free, (ij - 1) & 1);
+      const int b = ij & 1;
+      const uint32_t ph = (uint32_t)((ij >> 1) & 1);
+      const uint32_t a_hi = tmem + 64u * b, a_lo = a_hi + 32, d2 = tmem + 128 + 16u * b;
+      mbar_wait(a2_ready(b), ph);
+      if (ij >= 2) mbar_wait(d2_free(b), ph ^ 1u);  // D2[b] of sub-pixel ij-2 has been read
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -91,10 +107,14 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
 #pragma unroll
           for (uint32_t j = 0; j < 4; ++j) umma_bf16_ts(d2, a_hi + j * 8, umma_desc_from(bl + j * 32), idesc, 1u);
         }
-        umma_commit(d2_full);
+        umma_commit(d2_full(b));
       }
       __syncwarp();
-      if (ij + 2 < s2) g1(ij + 2);  // D1[ij & 1] was drained before the row owners arrived on a2_ready
+      if (ij + 2 < s2) {
+        mbar_wait(d2_full(b), ph);  // G2(ij) has consumed X[b] as its A operand before G1(ij+2) overwrites it
+        tc_fence_after();
+        g1(ij + 2);
+      }
     }
   } else {
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
@@ -134,30 +154,16 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
       for (int tp = 0; tp < 5; ++tp) pj[jj][tp] = 0.f;
-    for (int ij = 0; ij < s2; ++ij) {
-      const int bsel = ij & 1;
-      mbar_wait(d1_full0 + 8u * bsel, (ij >> 1) & 1);
-      tc_fence_after();
-      {  // own 32 columns of D1 -> LeakyReLU -> A2 (the previous G2 is complete: its D2 was read below)
-        float d[32];
-        tmem_ld16_nowait(trow + 64 * bsel + 32 * q, d);
-        tmem_ld16_nowait(trow + 64 * bsel + 32 * q + 16, d + 16);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) d[i] = lrelu02(d[i]);
-        a_tmem_store16(trow + 128, trow + 160, 32 * q, d, passes == 3);
-        a_tmem_store16(trow + 128, trow + 160, 32 * q + 16, d + 16, passes == 3);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(a2_ready);
-      mbar_wait(d2_full, ij & 1);
+    // read D2 of sub-pixel i back, release its buffer, and store a completed HR row
+    auto consume = [&](int i) {
+      const int c = i & 1;
+      mbar_wait(d2_full(c), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       float acc[16];
-      tmem_ld16(trow + 192, acc);
+      tmem_ld16(trow + 128 + 16 * c, acc);
       tc_fence_before();
-      mbar_arrive(d2_free);
-      const int j = ij % s;
+      mbar_arrive(d2_free(c));
+      const int j = i % s;
       float own[5];
 #pragma unroll
       for (int tp = 0; tp < 5; ++tp) own[tp] = q ? acc[5 + (tp < 4 ? tp : 3)] : acc[tp];
@@ -165,13 +171,13 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
       for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
         for (int tp = 0; tp < 5; ++tp) pj[jj][tp] = (jj == j) ? own[tp] : pj[jj][tp];
-      if (j == s - 1 && ok) {  // one HR row i = ij / s of this LR pixel is complete
-        const int i = ij / s;
+      if (j == s - 1 && ok) {  // one HR row i / s of this LR pixel is complete
+        const int hr = i / s;
         const int ntap = q ? 4 : 5;
 #pragma unroll
         for (int tp = 0; tp < 5; ++tp) {
           if (tp < ntap) {
-            float* dst = Pp + ((b * 9 + (q ? 5 : 0) + tp) * H + (Y0 + i)) * H + X0;
+            float* dst = Pp + ((b * 9 + (q ? 5 : 0) + tp) * H + (Y0 + hr)) * H + X0;
             if (s == 4)
               *reinterpret_cast<float4*>(dst) = make_float4(pj[0][tp], pj[1][tp], pj[2][tp], pj[3][tp]);
             else
@@ -179,7 +185,30 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
           }
         }
       }
+    };
+    for (int ij = 0; ij < s2; ++ij) {
+      const int bsel = ij & 1;
+      mbar_wait(d1_full0 + 8u * bsel, (uint32_t)((ij >> 1) & 1));
+      tc_fence_after();
+      {  // own 32 columns of D1 -> LeakyReLU -> A2, in place (the partner thread must have read its half first)
+        float d[32];
+        tmem_ld16_nowait(trow + 64 * bsel + 32 * q, d);
+        tmem_ld16_nowait(trow + 64 * bsel + 32 * q + 16, d + 16);
+        tmem_wait_ld();
+        tc_fence_before();
+        pair_bar_sync(warp & 3);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[i] = lrelu02(d[i]);
+        a_tmem_store16(trow + 64 * bsel, trow + 64 * bsel + 32, 32 * q, d, passes == 3);
+        a_tmem_store16(trow + 64 * bsel, trow + 64 * bsel + 32, 32 * q + 16, d + 16, passes == 3);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(a2_ready(bsel));
+      if (ij >= 1) consume(ij - 1);  // D2 of the previous sub-pixel: its G2 ran under the conversion above
     }
+    consume(s2 - 1);
     tc_fence_before();
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);
