@@ -91,6 +91,14 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def workload_config(world):
+    """`config` of the JSON line - the same dict for both arms (the reference arm times a bounded sample of this workload;
+    what the sample was is in its `cpu_baseline.sample`)."""
+    return {"workload": "LFT 5x5 4x full-LF inference, HCInew-shape 5x5x128x128 LR -> 512x512 SR, 64 patches of 32x32 per light field, one light field per GPU per step",
+            "weights": "seeded synthetic checkpoint in the reference format (shipped pth absent)",
+            "l2": "working set ~6.8 GB per step >> 126 MB L2 (no flush needed)", "parallelism": f"patch-sharded dp{world}"}
+
+
 def cpu_baseline(sd, lf, n_patches, threads=None):
     """The reference's CPU path (test.py:83-99 semantics, one net() call per patch, dense masked
     attention with the mask rebuilt per call) restated by oracle/lft_oracle.py, on a bounded sample."""
@@ -130,10 +138,10 @@ def run_reference(args):
         "impl": "reference", "metric": "SR output megapixels/sec (5x5 4x full LF)", "value": val, "unit": "MP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "LFT 5x5 4x full-LF inference, HCInew-shape 5x5x128x128 LR -> 512x512 SR, 64 patches of 32x32",
-                   "sample": "one 32x32-per-view patch per step (1/64 of a light field), B=1 per net() call"},
+        "config": workload_config(args.gpus),
         "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} steps x 1 patch (test.py:88-95 semantics, dense masked attention, mask rebuilt per call)"},
+                         "sample": f"{len(times)} steps x 1 patch = 1/64 of a light field per step, B=1 per net() call "
+                                   "(test.py:88-95 semantics, dense masked attention, mask rebuilt per call)"},
         "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -303,9 +311,7 @@ def main():
             "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.precision == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": "LFT 5x5 4x full-LF inference, HCInew-shape 5x5x128x128 LR -> 512x512 SR, 64 patches of 32x32 per light field, one light field per GPU per step",
-                       "weights": "seeded synthetic checkpoint in the reference format (shipped pth absent)",
-                       "l2": "working set ~6.8 GB per step >> 126 MB L2 (no flush needed)", "parallelism": f"patch-sharded dp{world}"},
+            "config": workload_config(world),
             "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(lf_host.numel() * 4),
                     "d2h_bytes_per_step": int(sr_host.numel() * 4), "steps": n_e2e,
                     "blocks": [round(b, 1) for b in e2e_blocks], "reported": "median of 3 blocks"},
