@@ -6,7 +6,7 @@
 
 Metrics are not part of the hot path (skimage PSNR/SSIM, out of scope); a per-view PSNR with the
 reference's definition (utils.py:79,85: 10 log10(1/MSE) on [0,1] images, mean over views) is provided because the
-bf16 gate is stated in PSNR.
+bf16 gate is stated in PSNR, and `ssim_per_view` restates the SSIM of utils.py:82-84 (CPU, scipy; unpinned - see there).
 """
 from __future__ import annotations
 
@@ -24,6 +24,34 @@ def psnr_per_view(sr_sai: torch.Tensor, hr_sai: torch.Tensor, angRes: int) -> to
     d = (sr_sai.double() - hr_sai.double().to(sr_sai.device)).view(A, H, A, W).permute(0, 2, 1, 3)
     mse = (d * d).mean(dim=(2, 3)).clamp_min(1e-20)
     return 10.0 * torch.log10(1.0 / mse)
+
+
+def ssim_per_view(sr_sai: torch.Tensor, hr_sai: torch.Tensor, angRes: int, data_range: float = 2.0) -> torch.Tensor:
+    """[A, A] SSIM of every view, restating what `metrics.structural_similarity(label, out, gaussian_weights=True)` of
+    utils.py:82-84 computes: Gaussian window sigma 1.5 truncated at 3.5 sigma (11 x 11), population covariances, K1 = 0.01,
+    K2 = 0.03, borders of (11 - 1) / 2 pixels dropped before the mean.  `data_range`: the reference passes none; the
+    scikit-image of its era (<= 0.18; README.md:15 names python 3.6 / PyTorch 1.3) then takes the dtype range of float
+    images, -1..1, i.e. 2.0 - later versions refuse float images without it.  UNPINNED: scikit-image is not installed in the
+    authoring container, so this function is checked only against an independent direct-convolution evaluation of the same
+    definition (tests/test_host_cpu.py), not against the reference's library.  CPU-side (scipy), not part of the hot path."""
+    import numpy as np
+    from scipy.ndimage import gaussian_filter
+    A = angRes
+    H, W = sr_sai.shape[0] // A, sr_sai.shape[1] // A
+    x = hr_sai.detach().cpu().double().numpy().reshape(A, H, A, W).transpose(0, 2, 1, 3)   # label first, as in utils.py:82
+    y = sr_sai.detach().cpu().double().numpy().reshape(A, H, A, W).transpose(0, 2, 1, 3)
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    pad = 5                                                                                # (win_size - 1) // 2, win_size = 11
+    out = np.zeros((A, A))
+    f = lambda im: gaussian_filter(im, sigma=1.5, truncate=3.5)                            # mode='reflect', scipy's default
+    for u in range(A):
+        for v in range(A):
+            a, b = x[u, v], y[u, v]
+            ux, uy = f(a), f(b)
+            vx, vy, vxy = f(a * a) - ux * ux, f(b * b) - uy * uy, f(a * b) - ux * uy
+            smap = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))
+            out[u, v] = smap[pad:H - pad, pad:W - pad].mean()
+    return torch.from_numpy(out)
 
 
 @torch.no_grad()

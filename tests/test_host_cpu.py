@@ -169,3 +169,48 @@ def test_crop_slab_integrates_like_reference_tiler():
     crops = sr_patches.view(nu * nv, A, 32 * s, A, 32 * s)[:, :, b:b + c, :, b:b + c].permute(0, 1, 3, 2, 4)
     full = crops.reshape(nu, nv, A, A, c, c).permute(2, 3, 0, 4, 1, 5).reshape(A, A, nu * c, nv * c)
     assert torch.equal(full[:, :, :h0 * s, :w0 * s], want)
+
+
+def test_psnr_per_view_matches_reference_definition():
+    """utils.py:79 (skimage PSNR of non-negative float images = 10 log10(1 / MSE)) per view, utils.py:85 mean over views."""
+    from lft_b200.evalloop import psnr_per_view
+    A, H, W = 3, 20, 28
+    g = torch.Generator().manual_seed(3)
+    hr = torch.rand(A * H, A * W, generator=g)
+    sr = (hr + 0.05 * torch.randn(A * H, A * W, generator=g)).clamp(0, 1)
+    got = psnr_per_view(sr, hr, A).numpy()
+    for u in range(A):
+        for v in range(A):
+            a = hr[u * H:(u + 1) * H, v * W:(v + 1) * W].double().numpy()
+            b = sr[u * H:(u + 1) * H, v * W:(v + 1) * W].double().numpy()
+            assert abs(got[u, v] - 10 * np.log10(1.0 / np.mean((a - b) ** 2))) < 1e-9
+
+
+def test_ssim_per_view_against_direct_convolution():
+    """ssim_per_view (scipy separable filter) against an independent direct 11 x 11 evaluation of the same definition
+    (Gaussian sigma 1.5, reflect borders, population covariances, data range 2) on the interior pixels."""
+    from lft_b200.evalloop import ssim_per_view
+    A, H, W = 2, 24, 30
+    g = torch.Generator().manual_seed(4)
+    hr = torch.rand(A * H, A * W, generator=g)
+    sr = (hr + 0.1 * torch.randn(A * H, A * W, generator=g)).clamp(0, 1)
+    got = ssim_per_view(sr, hr, A).numpy()
+    k1 = np.exp(-0.5 * (np.arange(-5, 6) / 1.5) ** 2)
+    k1 /= k1.sum()
+    k2 = np.outer(k1, k1)
+    c1, c2 = (0.01 * 2.0) ** 2, (0.03 * 2.0) ** 2
+    for u in range(A):
+        for v in range(A):
+            a = hr[u * H:(u + 1) * H, v * W:(v + 1) * W].double().numpy()
+            b = sr[u * H:(u + 1) * H, v * W:(v + 1) * W].double().numpy()
+            vals = []
+            for y in range(5, H - 5):          # interior: the window never touches the border, so no padding rule is involved
+                for x in range(5, W - 5):
+                    wa, wb = a[y - 5:y + 6, x - 5:x + 6], b[y - 5:y + 6, x - 5:x + 6]
+                    ua, ub = (k2 * wa).sum(), (k2 * wb).sum()
+                    va, vb = (k2 * wa * wa).sum() - ua * ua, (k2 * wb * wb).sum() - ub * ub
+                    vab = (k2 * wa * wb).sum() - ua * ub
+                    vals.append((2 * ua * ub + c1) * (2 * vab + c2) / ((ua * ua + ub * ub + c1) * (va + vb + c2)))
+            assert abs(got[u, v] - np.mean(vals)) < 1e-9
+    same = ssim_per_view(hr, hr, A)
+    assert torch.allclose(same, torch.ones(A, A, dtype=torch.float64))
