@@ -214,3 +214,71 @@ def test_ssim_per_view_against_direct_convolution():
             assert abs(got[u, v] - np.mean(vals)) < 1e-9
     same = ssim_per_view(hr, hr, A)
     assert torch.allclose(same, torch.ones(A, A, dtype=torch.float64))
+
+
+class _StubEngine:
+    """CPU stand-in with the Engine methods LightFieldSR uses: 'SR' = nearest-neighbour upsampling of each LR patch view, so
+    that the sharded path (patch_ranges -> per-rank crops -> gather -> integrate) can run under gloo without a GPU.  The
+    tiling itself comes from the oracle (pinned against the reference in test_oracle_golden.py)."""
+
+    def __init__(self, A, s):
+        self.A, self.s = A, s
+
+    def engine(self, device):
+        return self
+
+    def num_patches(self, h0, w0, patch=32, stride=16):
+        return LF.num_patches(h0, w0, patch, stride)
+
+    def forward_lf_crops(self, lr_lf, p0, p1, out=None, max_ws_bytes=None, patch=32, stride=16):
+        A, s = self.A, self.s
+        sub = O.lf_divide(lr_lf, A, patch, stride)
+        nu, nv = sub.shape[:2]
+        flat = sub.view(nu * nv, A, patch, A, patch)[p0:p1]
+        sr = flat.repeat_interleave(s, dim=2).repeat_interleave(s, dim=4)            # [n, A, P*s, A, P*s]
+        c, b = stride * s, ((patch - stride) * s) // 2
+        return sr[:, :, b:b + c, :, b:b + c].permute(0, 1, 3, 2, 4).contiguous()      # [n, A, A, c, c]
+
+    def integrate(self, crops, h0, w0, p0, p1, sr_lf, patch=32, stride=16):
+        A, s = self.A, self.s
+        nu, nv = LF.num_patches(h0, w0, patch, stride)
+        c = stride * s
+        full = crops.reshape(nu, nv, A, A, c, c).permute(2, 0, 4, 3, 1, 5).reshape(A, nu * c, A, nv * c)
+        sr_lf.copy_(full[:, :h0 * s, :, :w0 * s].reshape(A * h0 * s, A * w0 * s))
+        return sr_lf
+
+
+def _sharded_worker(rank, world, port, q, patch, stride):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        A, s, h0, w0 = 3, 2, 40, 56
+        lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, 5))
+        got = LF.LightFieldSR(_StubEngine(A, s), patch=patch, stride=stride)(lf, rank=rank, world=world)
+        if rank == 0:
+            want = lf.view(A, h0, A, w0).repeat_interleave(s, dim=1).repeat_interleave(s, dim=3).reshape(A * h0 * s, A * w0 * s)
+            q.put(bool(torch.equal(got, want)))
+        else:
+            q.put(got is None)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("patch,stride", [(32, 16), (32, 24), (16, 8)])
+def test_light_field_sharding_world2_gloo(patch, stride):
+    """LightFieldSR's rank logic end to end on two gloo ranks: ragged patch ranges (12 / 6 / 35 patches over 2 ranks),
+    one gather, integrate on rank 0.  With a nearest-neighbour stand-in for the network the assembled light field must be
+    the upsampled input exactly (the divide -> crop -> integrate identity of the reference tiler, utils.py:91-157)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + patch + stride
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q, patch, stride)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(res)
