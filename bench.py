@@ -1,20 +1,22 @@
 #!/usr/bin/env python
-"""Headline benchmark: SR output megapixels/s for 5x5, 4x full light-field inference (BASELINE.json).
+"""Headline benchmark: SR output megapixels/s for 5x5, 4x full light-field inference (BASELINE.json configs[2]).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|bf16] [--impl reference]
   (N > 1: launched by torchrun, one rank per GPU, NCCL)
 
-A step = one pass of the hot path over one batch of synthetic input: N light fields of HCInew shape
-(5x5 views of 128x128 LR -> 512x512 SR, 64 overlapping 32x32 patches each; BASELINE.json configs[2]),
-one per rank, patches sharded rank-wise with no data-path collective; the kept SR crops are gathered to
-rank 0 (NCCL) which assembles all N SR light fields ("weak" scaling: per-GPU work fixed).
-`value` counts INTEGRATED output pixels (after LFintegrate) of all ranks / max-over-ranks device time,
-inputs resident in HBM.  `e2e` is the same metric through the public API (lightfield.HostPipeline) from pinned
-host memory to pinned host memory, copies inside the timed region.
+A step = one pass of the hot path over ONE synthetic light field of HCInew shape (5x5 views of 128x128 LR -> 512x512 SR,
+64 overlapping 32x32 patches).  At N > 1 the 64 patches of that ONE light field are sharded over the ranks
+(`lightfield.patch_ranges(64, N)`, 8 per GPU at N = 8) and the SR light field is re-assembled on rank 0 ("strong"
+scaling: total work fixed) - by peer stores into rank 0's buffer over NVLink (default) or the NCCL gather
+(`--assemble collective`).  `value` counts INTEGRATED output pixels (after LFintegrate) / max-over-ranks device time,
+inputs resident in HBM.  `e2e` is the same metric through the public API (lightfield.HostPipeline) from pinned host memory
+to pinned host memory, every copy inside the timed region.  The old weak-scaling number (one whole light field per GPU)
+is kept as the extra key `weak`.
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import statistics
@@ -33,21 +35,22 @@ TOKENS_PER_LF = PATCHES * A * A * 32 * 32          # 1,638,400
 # algorithmic FLOP per LR token and launch (window attention at its mean 23.16 keys)
 FLOP_PER_TOKEN = {
     "conv3x3_64": 73728,   # + conv_init0 (1,152) fused into the first launch
-    "conv3x3_128": 147456, "ang_fused": 71936, "spa_embed_qkv": 147456 + 98304,
-    "spa_attn": 11858, "spa_ffn": 180224, "up_gemm": 131072 + 18432, "up_gather": 32 * S * S,
+    "ang_fused": 71936, "spa_embed_qkv": 147456 + 98304,
+    "spa_attn": 11858, "spa_ffn": 180224, "up_gemm": 131072 + 18432,
 }
-FLOP_PER_LF = 2411464 * TOKENS_PER_LF              # 3.951 TFLOP
-# algorithmic HBM bytes per token for the bandwidth-bound kernels (fp32 in/out, once each)
-BYTES_PER_TOKEN = {"spa_attn": 4 * 128 * 4, "up_gather": (9 * 16 + 16) * 4}
-TENSOR_KINDS = {"conv3x3_64", "conv3x3_128", "ang_fused", "spa_embed_qkv", "spa_ffn", "up_gemm"}
+FLOP_PER_LF = 2411464 * TOKENS_PER_LF              # 3.951 TFLOP: the reference's work per light field (every token of every patch)
+# algorithmic HBM bytes per unit for the bandwidth-bound kernels (fp32, each operand once): window attention reads Q, K, V and
+# writes O (4 x 128 floats per token); the gather reads 9 tap sums and writes one SR pixel (+ bicubic taps from L2)
+BYTES_PER_UNIT = {"spa_attn": 4 * 128 * 4, "up_gather": (9 + 1) * 4, "lf_divide": 8, "lf_integrate": 8}
+TENSOR_KINDS = set(FLOP_PER_TOKEN) - {"spa_attn"}
 
 
 def ncu_traffic(kind):
-    """DRAM bytes per launch of `kind` from the committed ncu --set full capture (profiles/r01_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(kind)
-    return None
+    """DRAM bytes per launch of `kind` from the newest committed ncu --set full capture (profiles/r*_traffic.json)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if files:
+        return json.load(open(files[-1])).get(kind), os.path.basename(files[-1])
+    return None, None
 
 
 def peaks():
@@ -94,29 +97,31 @@ class ClockSampler:
 def workload_config(world):
     """`config` of the JSON line - the same dict for both arms (the reference arm times a bounded sample of this workload;
     what the sample was is in its `cpu_baseline.sample`)."""
-    return {"workload": "LFT 5x5 4x full-LF inference, HCInew-shape 5x5x128x128 LR -> 512x512 SR, 64 patches of 32x32 per light field, one light field per GPU per step",
+    return {"workload": "LFT 5x5 4x full-LF inference, ONE HCInew-shape light field per step: 5x5x128x128 LR -> 512x512 SR, 64 "
+                        "patches of 32x32 (stride 16) sharded over the GPUs, SR light field assembled on rank 0",
             "weights": "seeded synthetic checkpoint in the reference format (shipped pth absent)",
-            "l2": "working set ~6.8 GB per step >> 126 MB L2 (no flush needed)", "parallelism": f"patch-sharded dp{world}"}
+            "l2": "working set ~6.8 GB per step at N=1 (0.85 GB per GPU at N=8) >> 126 MB L2 (no flush needed)",
+            "parallelism": f"patch-sharded dp{world}"}
+
+
+REF_PATCHES_PER_STEP = 3
 
 
 def cpu_baseline(sd, lf, n_patches, threads=None):
-    """The reference's CPU path (test.py:83-99 semantics, one net() call per patch, dense masked
-    attention with the mask rebuilt per call) restated by oracle/lft_oracle.py, on a bounded sample."""
+    """The reference's CPU path (test.py:83-101: LFdivide, one net() call per patch, LFintegrate) on a bounded sample: the
+    UNMODIFIED reference staged under baseline/_ref when present (kind "reference"), else the oracle port (kind "port")."""
     import torch
-    from oracle import lft_oracle as O
+    from oracle import reference_arm as R
     if threads:
         torch.set_num_threads(threads)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        _, n = O.infer_light_field(sd, lf, A, S, mode="dense", batch=1, max_patches=n_patches)
-    dt = time.perf_counter() - t0
+    _, n, dt, kind = R.run_light_field(sd, lf, A, S, max_patches=n_patches)
     mp = n * A * A * (16 * S) ** 2 / 1e6
-    return mp / dt, dt, n, torch.get_num_threads()
+    return mp / dt, dt, n, torch.get_num_threads(), kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference
-    is pure Python and cannot travel to the GPU box), all host threads, one patch per step."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, all threads,
+    REF_PATCHES_PER_STEP patches of the benchmark's light field per step (the whole light field is 64)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -126,22 +131,25 @@ def run_reference(args):
     lf = torch.from_numpy(synth.synth_light_field(A, H0, W0, 2))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    kind = "port"
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(sd, lf, 1)
     times = []
     for _ in range(args.steps):
-        v, dt, n, th = cpu_baseline(sd, lf, 1)
+        v, dt, n, th, kind = cpu_baseline(sd, lf, REF_PATCHES_PER_STEP)
         times.append(dt)
-    mp_per_step = A * A * (16 * S) ** 2 / 1e6
+    mp_per_step = REF_PATCHES_PER_STEP * A * A * (16 * S) ** 2 / 1e6
     val = mp_per_step * len(times) / sum(times)
+    what = ("the unmodified reference (model/LFT.py get_model + utils.py LFdivide / LFintegrate, staged in baseline/_ref)"
+            if kind == "reference" else "oracle port of test.py:83-101 (dense masked attention, mask rebuilt per call)")
     line = {
         "impl": "reference", "metric": "SR output megapixels/sec (5x5 4x full LF)", "value": val, "unit": "MP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} steps x 1 patch = 1/64 of a light field per step, B=1 per net() call "
-                                   "(test.py:88-95 semantics, dense masked attention, mask rebuilt per call)"},
+        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": kind,
+                         "sample": f"{len(times)} steps x {REF_PATCHES_PER_STEP} of the 64 patches of the light field per step "
+                                   f"(LFdivide of the whole light field + B=1 net() per patch + LFintegrate, test.py:83-101); {what}"},
         "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,8 +182,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--impl", default="lft_b200", choices=["lft_b200", "reference"])
+    ap.add_argument("--assemble", default="auto", choices=["auto", "direct", "collective"],
+                    help="N > 1: peer stores into rank 0's SR buffer (direct) or NCCL gather + integrate (collective)")
     ap.add_argument("--cpu-patches", type=int, default=3, help="patches in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling leg at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -188,7 +199,7 @@ def main():
     import torch.distributed as dist
     from lft_b200 import synth
     from lft_b200.engine import Engine
-    from lft_b200.lightfield import HostPipeline, gather_crops
+    from lft_b200.lightfield import HostPipeline, LightFieldSR, patch_ranges
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -201,67 +212,62 @@ def main():
     sd = synth.synth_state_dict(A, S, 0)
     eng = Engine(A, S, precision=args.precision, device=local)
     eng.load_state_dict(sd)
-    lf_host = torch.from_numpy(synth.synth_light_field(A, H0, W0, 2 + rank)).pin_memory()
+    lf_host = torch.from_numpy(synth.synth_light_field(A, H0, W0, 2)).pin_memory()   # the SAME light field on every rank
     lf = lf_host.to(dev)
-    sr_all = torch.empty(world, A * H0 * S, A * W0 * S, dtype=torch.float32, device=dev) if rank == 0 else None
-    crops = torch.empty(PATCHES, A, A, 16 * S, 16 * S, dtype=torch.float32, device=dev)
-    ranges = [(i * PATCHES, (i + 1) * PATCHES) for i in range(world)]
+    sr_pipe = LightFieldSR(eng, assemble=args.assemble)
 
     def step():
-        eng.forward_lf_crops(lf, 0, PATCHES, out=crops)
-        allc = gather_crops(crops, ranges, rank, world)
-        if rank == 0:
-            for r in range(world):
-                eng.integrate(allc[r * PATCHES:(r + 1) * PATCHES], H0, W0, 0, PATCHES, sr_all[r])
+        return sr_pipe(lf, rank, world)    # patches [p0, p1) of this rank; SR light field assembled on rank 0
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(args.warmup):
         step()
     sync()
+    assembled = "single GPU" if world == 1 else ("direct peer stores (CUDA IPC over NVLink) + 2 one-element all-reduces"
+                                                   if any(v is not None for v in sr_pipe._peer.values()) else "NCCL gather + lft_integrate")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n0 = eng.launch_count()
     eng.profile_enable(True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
-    ev[0].record()
+    e0.record()
     for i in range(args.steps):
         step()
-        ev[i + 1].record()
+    e1.record()
     sync()
-    total_ms = ev[0].elapsed_time(ev[-1])
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count() - n0
     prof = eng.profile_read()
     eng.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    value = MP_PER_LF * args.steps / (total_ms / 1e3)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = world * MP_PER_LF * args.steps / (total_ms / 1e3)
+        dist.all_reduce(lt)
+    launches_all = int(lt.item())
 
-    # ---- e2e: public API, pinned host -> device -> SR -> pinned host, every step
-    sr_host = torch.empty(A * H0 * S, A * W0 * S, dtype=torch.float32).pin_memory()
-    sr_hosts = [sr_host, torch.empty_like(sr_host).pin_memory()]
-    pipe = HostPipeline(eng)   # public API: copies of step i overlap the kernels of step i+1 (all inside the timed region)
+    # ---- e2e: public API (HostPipeline), pinned host -> device -> SR -> pinned host, every step; at N > 1 every rank uploads
+    # the light field from ITS pinned host copy and rank 0 downloads the assembled SR light field
+    sr_hosts = [torch.empty(A * H0 * S, A * W0 * S, dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else [None, None]
+    pipe = HostPipeline(sr_pipe)   # copies of step i overlap the kernels of step i+1 (all inside the timed region)
     e2e_i = [0]
+
     def e2e_step():
-        if world == 1:
-            pipe.submit(lf_host, sr_hosts[e2e_i[0] & 1])
-            e2e_i[0] += 1
-        else:
-            x = lf_host.to(dev, non_blocking=True)
-            eng.forward_lf_crops(x, 0, PATCHES, out=crops)
-            allc = gather_crops(crops, ranges, rank, world)
-            if rank == 0:
-                for r in range(world):
-                    eng.integrate(allc[r * PATCHES:(r + 1) * PATCHES], H0, W0, 0, PATCHES, sr_all[r])
-                sr_host.copy_(sr_all[0], non_blocking=True)
+        pipe.submit(lf_host, sr_hosts[e2e_i[0] & 1], rank=rank, world=world)
+        e2e_i[0] += 1
+
     for _ in range(6):   # untimed: every pipeline slot reused twice, so the caching allocator has reached its steady state
         e2e_step()
     pipe.drain()
@@ -269,20 +275,35 @@ def main():
     n_e2e = max(3, min(args.steps, 10))
     blocks = []
     for _ in range(3):   # three timed blocks of n_e2e steps; the median block is reported, all three are listed
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync()
-        e0.record()
+        b0.record()
         for _ in range(n_e2e):
             e2e_step()
         pipe.drain()   # every result is in host memory before the closing event
-        e1.record()
+        b1.record()
         sync()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        blocks.append(float(t.item()))
-    e2e_blocks = [world * MP_PER_LF * n_e2e / (b / 1e3) for b in blocks]
+        blocks.append(max_over_ranks(b0.elapsed_time(b1)))
+    e2e_blocks = [MP_PER_LF * n_e2e / (b / 1e3) for b in blocks]
     e2e_val = sorted(e2e_blocks)[1]
+
+    # ---- extra: weak scaling (one WHOLE light field per GPU per step, assembled where it was computed)
+    weak = None
+    if world > 1 and not args.no_weak:
+        own = LightFieldSR(eng)
+        lf_own = torch.from_numpy(synth.synth_light_field(A, H0, W0, 2 + rank)).to(dev)
+        for _ in range(3):
+            own(lf_own)
+        w0_, w1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        w0_.record()
+        for _ in range(args.steps):
+            own(lf_own)
+        w1_.record()
+        sync()
+        wms = max_over_ranks(w0_.elapsed_time(w1_))
+        weak = {"value": world * MP_PER_LF * args.steps / (wms / 1e3), "unit": "MP/s", "ms_per_step": wms / args.steps,
+                "what": "one whole light field per GPU per step (per-GPU work fixed), no cross-GPU traffic"}
 
     if rank == 0:
         pk = peaks()
@@ -290,42 +311,58 @@ def main():
         step_kernel_ms = sum(v["ms"] for v in kinds.values()) / args.steps
         top = max(kinds, key=lambda k: kinds[k]["ms"])
         avg_ms = kinds[top]["ms"] / kinds[top]["launches"]
+        units_per_launch = kinds[top]["units"] / kinds[top]["launches"]
         if top in TENSOR_KINDS:
-            ach = FLOP_PER_TOKEN[top] * TOKENS_PER_LF / (avg_ms * 1e-3) / 1e12
+            ach = FLOP_PER_TOKEN[top] * units_per_launch / (avg_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"]}
         else:
-            ach = BYTES_PER_TOKEN.get(top, 0) * TOKENS_PER_LF / (avg_ms * 1e-3) / 1e9
+            ach = BYTES_PER_UNIT.get(top, 0) * units_per_launch / (avg_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
-        roof.update({"kernel": top, "avg_launch_ms": avg_ms, "share_of_step": kinds[top]["ms"] / args.steps / step_kernel_ms,
-                     "traffic": ncu_traffic(top), "traffic_unit": "bytes/launch (dram read+write, ncu --set full, profiles/)",
+        traffic, traffic_src = ncu_traffic(top)
+        roof.update({"kernel": top, "avg_launch_ms": avg_ms, "units_per_launch": units_per_launch,
+                     "units": "LR tokens (pixels x views) the launch processes, averaged over the layers (the last layers of the "
+                              "light-field path run on the pixels the kept crop depends on only)",
+                     "share_of_step": kinds[top]["ms"] / args.steps / step_kernel_ms,
+                     "traffic": traffic if world == 1 else None,
+                     "traffic_unit": f"bytes/launch at N=1 (dram read+write, ncu --set full, profiles/{traffic_src})",
                      "peak_source": pk["src"],
                      "note": ("fp32 path issues 3 bf16 MMAs per product (hi*hi+lo*hi+hi*lo): attainable frac <= 1/3"
-                              if args.precision == "fp32" else "single bf16 MMA per product")
-                             + ("; ang_fused and spa_embed_qkv share the top spot within run-to-run noise - ang_fused spends 13 % of "
-                                "its time in GEMMs, the rest in the per-pixel 25x25 (head dim 8) attention on CUDA cores, which is "
-                                "shared-memory bound (DESIGN.md section 6)" if top == "ang_fused" else "")})
-        whole = FLOP_PER_LF * world * args.steps / (total_ms * 1e-3) / 1e12
+                              if args.precision == "fp32" else "single bf16 MMA per product")})
+        executed = sum(FLOP_PER_TOKEN.get(k, 0) * v["units"] for k, v in kinds.items())   # rank 0's share
+        whole_ref = FLOP_PER_LF * args.steps / (total_ms * 1e-3) / 1e12
         line = {
             "metric": "SR output megapixels/sec (5x5 4x full LF)", "value": value, "unit": "MP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong", "vs_baseline": None,
             "dtype": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.precision == "fp32" else "bf16",
             "data": "synthetic",
             "config": workload_config(world),
-            "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(lf_host.numel() * 4),
-                    "d2h_bytes_per_step": int(sr_host.numel() * 4), "steps": n_e2e,
-                    "blocks": [round(b, 1) for b in e2e_blocks], "reported": "median of 3 blocks"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-            "whole_step": {"algorithmic_tflops": whole, "frac_of_bf16_peak": whole / pk["tensor"]},
-            "kernels": {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
-                            "tflops": (FLOP_PER_TOKEN.get(k, 0) * TOKENS_PER_LF * v["launches"] / max(v["ms"], 1e-9) / 1e9)}
+            "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(lf_host.numel() * 4) * world,
+                    "d2h_bytes_per_step": int(A * H0 * S * A * W0 * S * 4), "steps": n_e2e,
+                    "blocks": [round(b, 1) for b in e2e_blocks], "reported": "median of 3 blocks",
+                    "what": "lightfield.HostPipeline: every rank uploads the LR light field from pinned host memory, rank 0 "
+                            "downloads the assembled SR light field into pinned host memory; copies overlap the next step's kernels"},
+            "gpu_launches": launches_all, "clocks": clocks, "roofline": roof, "assembly": assembled,
+            "patches_per_rank": [b - a for a, b in patch_ranges(PATCHES, world)],
+            "whole_step": {"reference_work_tflops": whole_ref, "frac_of_bf16_peak": whole_ref / (pk["tensor"] * world),
+                           "executed_tflops_rank0": executed / (total_ms * 1e-3) / 1e12,
+                           "note": "reference_work = 2,411,464 FLOP x every token of every patch (SURVEY 8d) / step time, divided by "
+                                   "the peak of all N GPUs; executed = what rank 0's kernels really ran after skipping the pixels "
+                                   "LFintegrate discards"},
+            "kernels": {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps, "units_per_step": v["units"] / args.steps,
+                            "tflops": (FLOP_PER_TOKEN.get(k, 0) * v["units"] / max(v["ms"], 1e-9) / 1e9)}
                         for k, v in kinds.items()},
         }
+        if weak is not None:
+            line["weak"] = weak
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, n, th = cpu_baseline(sd, lf_host.clone(), args.cpu_patches)
-            line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": th, "kind": "port",
-                                    "sample": f"{n} of 64 patches of the same light field, B=1 per call, {dt:.1f} s (oracle port of test.py:83-99, dense masked attention)"}
+            v, dt, n, th, kind = cpu_baseline(sd, lf_host.clone(), args.cpu_patches)
+            line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": th, "kind": kind,
+                                    "sample": f"{n} of 64 patches of the same light field, B=1 per call, {dt:.1f} s "
+                                              + ("(the unmodified reference staged in baseline/_ref: LFdivide + get_model per patch + LFintegrate, test.py:83-101)"
+                                                 if kind == "reference" else "(oracle port of test.py:83-101, dense masked attention)")}
         _emit(line)
+    sr_pipe.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -70,7 +70,10 @@ int lft_set_weight(lft_handle* h, const char* key, const float* host_data, const
 int lft_finalize_weights(lft_handle* h);
 int lft_set_precision(lft_handle* h, int32_t precision);
 
-/* bytes of device scratch lft_forward needs for a batch of B patches of P x P pixels per view */
+/* bytes of device scratch lft_forward needs for a batch of B patches of P x P pixels per view.
+ * Threading: a handle owns no scratch of its own, but every compute call on it uses the workspace it is given for the whole
+ * call - two calls that overlap in time (two streams, two threads) need two workspaces; weight reloads
+ * (lft_set_weight / lft_finalize_weights) must not overlap compute calls on the same handle. */
 int lft_workspace_bytes(lft_handle* h, int32_t B, int32_t P, size_t* bytes);
 
 /* get_model.forward (LFT.py:52-83). lr/sr are DEVICE pointers in the layouts above. */
@@ -107,6 +110,27 @@ int lft_forward_lf_ex(lft_handle* h, const float* lr_lf, int32_t h0, int32_t w0,
 int lft_integrate_ex(lft_handle* h, const float* sr_crops, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
                      int32_t patch_begin, int32_t patch_end, float* sr_lf, void* stream);
 
+/* The same path with LFintegrate (utils.py:141-157) and the SAI re-mosaic of test.py:100-101 fused into the last kernel:
+ * the kept crop of every patch in [patch_begin, patch_end) is stored at its final position in the assembled SR light field
+ *   sr_lf : device float32 [A*h0*s, A*w0*s]   (`Sr_SAI_y`)
+ * (ragged last row / column clipped).  Patches are independent, so ranks that each own a patch range may all write into ONE
+ * sr_lf: on a multi-GPU node sr_lf may be the peer mapping (lft_peer_open) of a buffer that lives on another GPU - the
+ * stores then travel over NVLink and no gather collective is needed, only a barrier before the owner reads the result.
+ * Nothing else is written; pixels of patches outside the range keep their previous contents. */
+int lft_forward_lf_sr(lft_handle* h, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
+                      int32_t patch_begin, int32_t patch_end, float* sr_lf, void* workspace, size_t ws_bytes,
+                      void* stream);
+
+/* Peer-visible device buffers for lft_forward_lf_sr (CUDA IPC, one process per GPU on one node; the reference has no
+ * multi-GPU inference at all - test.py:18 pins one device).  The owner allocates with lft_peer_alloc and ships the 64-byte
+ * handle to the other processes by any transport; they map it with lft_peer_open (peer access is enabled lazily by the
+ * runtime) and unmap it with lft_peer_close before the owner frees it with lft_peer_free. */
+typedef struct { unsigned char bytes[64]; } lft_peer_handle;
+int lft_peer_alloc(int32_t device, size_t bytes, void** dev_ptr, lft_peer_handle* handle);
+int lft_peer_free(int32_t device, void* dev_ptr);
+int lft_peer_open(int32_t device, const lft_peer_handle* handle, void** mapped_ptr);
+int lft_peer_close(int32_t device, void* mapped_ptr);
+
 /* Stage-level entry points (device pointers, channels-last tokens [B, A*A, P, P, C]) for parity tests
  * against the reference's own sub-modules:
  *   conv_init : conv_init0 + conv_init + residual           LFT.py:65-66   lr [B,1,A*P,A*P] -> [T,64]
@@ -128,6 +152,10 @@ int lft_stage_upsample(lft_handle* h, const float* feat, const float* lr, float*
 #define LFT_PROFILE_MAX_KINDS 16
 int lft_profile_enable(lft_handle* h, int32_t on);
 int lft_profile_read(lft_handle* h, int32_t* n_kinds, const char** names, int64_t* launches, double* total_ms);
+/* the same plus, per kind, the units the recorded launches processed (LR tokens = pixels x views for the network kernels - on
+ * the light-field path the last layers run on the pixels the kept crop depends on only -, output pixels for the tilers) */
+int lft_profile_read2(lft_handle* h, int32_t* n_kinds, const char** names, int64_t* launches, double* total_ms,
+                      int64_t* units);
 int64_t lft_launch_count(lft_handle* h); /* kernels launched by this handle since creation */
 
 /* Debug: per-phase clock64() marks of the middle CTA of the last k_spa_ffn (which=0) / k_ang (1) / k_spa_embed_qkv (2) launch

@@ -44,7 +44,11 @@ def _digest():
     return h.hexdigest()
 
 
+LAST_BUILD_COMPILED = False   # True once build() has actually run nvcc in this process (build_mode evidence)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    global LAST_BUILD_COMPILED
     os.makedirs(OUT_DIR, exist_ok=True)
     stamp = os.path.join(OUT_DIR, "build.sha256")
     dig = _digest()
@@ -73,6 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     open(stamp, "w").write(dig)
+    LAST_BUILD_COMPILED = True
     return LIB
 
 

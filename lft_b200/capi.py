@@ -54,6 +54,12 @@ SIGNATURES = {
     "lft_lf_num_patches_ex": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32_p, c_i32_p]),
     "lft_forward_lf_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lft_forward_lf_sr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lft_peer_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "lft_peer_free": (C.c_int, [C.c_int32, C.c_void_p]),
+    "lft_peer_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "lft_peer_close": (C.c_int, [C.c_int32, C.c_void_p]),
     "lft_integrate_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_void_p]),
     "lft_divide_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -68,6 +74,7 @@ SIGNATURES = {
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
     "lft_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "lft_profile_read": (C.c_int, [C.c_void_p, c_i32_p, C.POINTER(C.c_char_p), c_i64_p, C.POINTER(C.c_double)]),
+    "lft_profile_read2": (C.c_int, [C.c_void_p, c_i32_p, C.POINTER(C.c_char_p), c_i64_p, C.POINTER(C.c_double), c_i64_p]),
     "lft_launch_count": (C.c_int64, [C.c_void_p]),
     "lft_debug_timeline": (C.c_int, [C.c_int32, c_i64_p]),
     "lft_mma_bench": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64_p]),

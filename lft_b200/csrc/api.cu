@@ -124,10 +124,25 @@ static std::vector<float> pos_axis(int length, int C) {
   return t;
 }
 
+// Release every device allocation of the current weight generation (packed slabs, constant tables, the per-patch-size
+// position tables).  cudaFree waits for the device, so kernels still reading the old weights finish first.
+static void free_weights(Handle* h) {
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+  h->pe_cache.clear();
+  h->pe_P = -1;
+  for (int i = 0; i < kLayers; ++i) h->layer[i] = Layer();
+  for (int i = 0; i < 3; ++i) h->w_conv[i] = h->w_conv_st[i] = nullptr;
+  h->w_up = h->w_up3 = nullptr;
+  h->pe_ang = nullptr;
+  h->finalized = false;
+}
+
 static int finalize(Handle* h) {
   const int C = 64, S = 128, A = h->cfg.ang_res, s = h->cfg.scale, s2 = s * s;
   for (auto& kv : h->spec)
     if (!h->host_w.count(kv.first)) return fail(LFT_ERR_STATE, "missing state_dict key '%s'", kv.first.c_str());
+  free_weights(h);  // a reload replaces the previous generation instead of leaking it
   auto W = [&](const std::string& k) -> const float* { return h->host_w[k].data(); };
   int rc;
   // conv_init0: fp32 [64][9]
@@ -286,8 +301,17 @@ static int finalize(Handle* h) {
 }
 
 // spatial PE token table per layer: SAI2Token(spa_position) (LFT.py:180) = conv3x3(PE_hw, MLP.weight), [P*P][128]
+// Built on the host once per (weights, patch size) and cached: alternating patch sizes costs nothing after the first use.
 int ensure_spa_pe(Handle* h, int P) {
   if (h->pe_P == P) return 0;
+  {
+    auto it = h->pe_cache.find(P);
+    if (it != h->pe_cache.end()) {
+      for (int i = 0; i < kLayers; ++i) { h->layer[i].s_pe = it->second.pe[i]; h->layer[i].s_pev = it->second.pev[i]; }
+      h->pe_P = P;
+      return 0;
+    }
+  }
   const int C = 64, S = 128;
   std::vector<float> ax = pos_axis(P, C);
   std::vector<float> pe((size_t)P * P * C);
@@ -332,6 +356,8 @@ int ensure_spa_pe(Handle* h, int P) {
       }
     if ((rc = upload_f32(h, pvt, &h->layer[i].s_pev))) return rc;
   }
+  SpaPe& e = h->pe_cache[P];
+  for (int i = 0; i < kLayers; ++i) { e.pe[i] = h->layer[i].s_pe; e.pev[i] = h->layer[i].s_pev; }
   h->pe_P = P;
   return 0;
 }
@@ -354,7 +380,9 @@ int lft_create(const lft_config* cfg, lft_handle** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(LFT_ERR_CUDA, "no CUDA device: lft_b200 has no CPU fallback");
-  CUDA_TRY(cudaSetDevice(cfg->device));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(LFT_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+  DeviceGuard dg(cfg->device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", cfg->device);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) return fail(LFT_ERR_CUDA, "device is sm_%d%d; this library is sm_100a only", prop.major, prop.minor);
@@ -362,7 +390,7 @@ int lft_create(const lft_config* cfg, lft_handle** out) {
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
   build_spec(h);
-  int rc = configure_kernels();
+  int rc = configure_kernels(cfg->device);
   if (rc) { delete h; return rc; }
   *out = reinterpret_cast<lft_handle*>(h);
   return 0;
@@ -371,8 +399,8 @@ int lft_create(const lft_config* cfg, lft_handle** out) {
 int lft_destroy(lft_handle* hh) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h) return 0;
-  cudaSetDevice(h->cfg.device);
-  for (void* p : h->allocs) cudaFree(p);
+  DeviceGuard dg(h->cfg.device);
+  free_weights(h);
   for (auto& e : h->events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
   delete h;
   return 0;
@@ -396,8 +424,8 @@ int lft_set_weight(lft_handle* hh, const char* key, const float* host_data, cons
 int lft_finalize_weights(lft_handle* hh) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h) return fail(LFT_ERR_ARG, "null handle");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
-  h->pe_P = -1;
+  DeviceGuard dg(h->cfg.device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", h->cfg.device);
   return finalize(h);
 }
 
@@ -412,23 +440,28 @@ int lft_profile_enable(lft_handle* hh, int32_t on) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h) return fail(LFT_ERR_ARG, "null handle");
   h->profiling = on != 0;
-  if (on) {
-    for (auto& e : h->events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
-    h->events.clear();
-  }
+  if (on) h->n_events = 0;  // a new session reuses the pooled events
   return 0;
 }
 
 int lft_profile_read(lft_handle* hh, int32_t* n_kinds, const char** names, int64_t* launches, double* total_ms) {
+  return lft_profile_read2(hh, n_kinds, names, launches, total_ms, nullptr);
+}
+
+int lft_profile_read2(lft_handle* hh, int32_t* n_kinds, const char** names, int64_t* launches, double* total_ms,
+                      int64_t* units) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h || !n_kinds || !names || !launches || !total_ms) return fail(LFT_ERR_ARG, "null argument");
-  for (int k = 0; k < K_COUNT; ++k) { names[k] = kKindNames[k]; launches[k] = 0; total_ms[k] = 0.0; }
-  for (auto& e : h->events) {
+  for (int k = 0; k < K_COUNT; ++k) { names[k] = kKindNames[k]; launches[k] = 0; total_ms[k] = 0.0; if (units) units[k] = 0; }
+  DeviceGuard dg(h->cfg.device);
+  for (size_t i = 0; i < h->n_events; ++i) {
+    const ProfEvent& e = h->events[i];
     CUDA_TRY(cudaEventSynchronize(e.stop));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, e.start, e.stop));
     launches[e.kind] += 1;
     total_ms[e.kind] += ms;
+    if (units) units[e.kind] += e.units;
   }
   *n_kinds = K_COUNT;
   return 0;

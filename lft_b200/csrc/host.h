@@ -22,6 +22,13 @@ int fail(int code, const char* fmt, ...);
     if (_e != cudaSuccess) return ::lft::fail(LFT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+// A square pixel region [r0, r0 + rn)^2 of every P x P view.  The light-field path (lft_forward_lf*) keeps only the
+// central crop of every SR patch view, so the last layers are evaluated on the shrinking regions that crop depends on
+// (launch.cu: crop_regions); every other caller passes the full view {0, P}.
+struct Region {
+  int r0, rn;
+};
+
 enum Kind {
   K_CONV0 = 0,
   K_CONV64,
@@ -48,8 +55,8 @@ struct Layer {
   const uint8_t *s_wmlp = nullptr, *s_wq = nullptr, *s_wk = nullptr, *s_wv = nullptr, *s_wo = nullptr;
   const uint8_t *s_w1a = nullptr, *s_w1b = nullptr, *s_w2a = nullptr, *s_w2b = nullptr, *s_wlin = nullptr;
   const float* s_ln = nullptr;  // [norm.w | norm.b | ff0.w | ff0.b] x 128
-  const float* s_pe = nullptr;    // [P*P][128] SAI2Token(spa_position), rebuilt when P changes
-  const float* s_pev = nullptr;   // chunk-planar [32][P*P][4]: PE_s Wv^T, rebuilt when P changes
+  const float* s_pe = nullptr;    // [P*P][128] SAI2Token(spa_position) for the current patch size (points into Handle::pe_cache)
+  const float* s_pev = nullptr;   // chunk-planar [32][P*P][4]: PE_s Wv^T, likewise
   std::vector<float> s_tab;       // [u_q 128 | u_k 128 | c_q 128 | c_k 128 | u_1 256 | c_1 256] (host; kernel params)
 
 };
@@ -57,6 +64,28 @@ struct Layer {
 struct ProfEvent {
   cudaEvent_t start, stop;
   int kind;
+  long long units;  // what the launch processed: LR tokens (pixels x views) for the network kernels, output pixels for the tilers
+};
+
+// spatial position tables of one patch size (per layer), kept for the life of the weights they were built from
+struct SpaPe {
+  const float* pe[kLayers] = {nullptr, nullptr, nullptr, nullptr};
+  const float* pev[kLayers] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+// RAII: make `dev` current for the duration of an API call and restore the caller's device afterwards (the library must not
+// change the current device of the torch process that calls it)
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    else if (prev == dev) prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
 };
 
 struct Handle {
@@ -64,7 +93,8 @@ struct Handle {
   std::map<std::string, std::vector<int64_t>> spec;
   std::map<std::string, std::vector<float>> host_w;
   bool finalized = false;
-  std::vector<void*> allocs;
+  std::vector<void*> allocs;       // device allocations of the current weight generation (freed on re-finalize / destroy)
+  std::map<int, SpaPe> pe_cache;   // patch size -> spatial position tables (same life time as `allocs`)
   std::vector<float> w_conv0_host;  // conv_init0 weight [64][9] (kernel parameter of the fused first/last conv)
   const uint8_t* w_conv[3] = {nullptr, nullptr, nullptr};
   const uint8_t* w_conv_st[3] = {nullptr, nullptr, nullptr};  // fp32 mode: hi and lo rows stacked to one [128 x 64] slab per tap
@@ -74,7 +104,8 @@ struct Handle {
   const float* pe_ang = nullptr;
   int pe_P = -1;
   bool profiling = false;
-  std::vector<ProfEvent> events;
+  std::vector<ProfEvent> events;   // event pool: created once, reused by every profiling session
+  size_t n_events = 0;             // events of the current session
   int64_t launches = 0;
   int num_sms = 148;
   int passes() const { return cfg.precision == LFT_PREC_FP32 ? 3 : 1; }
@@ -89,11 +120,16 @@ struct Scope {  // profiling + launch accounting around one kernel launch
   cudaStream_t st;
   ProfEvent ev{};
   bool on;
-  Scope(Handle* h_, int kind, cudaStream_t st_) : h(h_), st(st_), on(h_->profiling) {
+  Scope(Handle* h_, int kind, cudaStream_t st_, long long units = 0) : h(h_), st(st_), on(h_->profiling) {
     if (on) {
-      cudaEventCreate(&ev.start);
-      cudaEventCreate(&ev.stop);
+      if (h->n_events == h->events.size()) {  // grow the pool (only the first session of a given length pays for this)
+        ProfEvent e{};
+        if (cudaEventCreate(&e.start) != cudaSuccess || cudaEventCreate(&e.stop) != cudaSuccess) { on = false; return; }
+        h->events.push_back(e);
+      }
+      ev = h->events[h->n_events];
       ev.kind = kind;
+      ev.units = units;
       cudaEventRecord(ev.start, st);
     }
   }
@@ -101,7 +137,7 @@ struct Scope {  // profiling + launch accounting around one kernel launch
     h->launches++;
     if (on) {
       cudaEventRecord(ev.stop, st);
-      h->events.push_back(ev);
+      h->events[h->n_events++] = ev;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LFT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -110,7 +146,7 @@ struct Scope {  // profiling + launch accounting around one kernel launch
 };
 
 // launch.cu
-int configure_kernels();
+int configure_kernels(int device);
 // per-file kernel configuration (max dynamic smem opt-in) and launchers
 int configure_conv();
 int configure_ang();
@@ -136,14 +172,22 @@ Workspace carve(void* ws, long long T, int scale);
 
 int run_conv_init(Handle* h, const float* lr, float* out, float* tmp0, float* tmp1, float* tmp2, int B, int P,
                   cudaStream_t st);
-int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cudaStream_t st);
+int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, Region rg, cudaStream_t st);
 int run_spa(Handle* h, int layer, const float* in, float* out, const float* final_res, Workspace& w, int B, int P,
-            cudaStream_t st);
+            Region need, cudaStream_t st);
 int launch_divide(Handle* h, const float* lf, float* patches, int h0, int w0, int numV, int p0, int n, int P, int S,
                   cudaStream_t st);
 int launch_integrate(Handle* h, const float* crops, float* sr, int h0, int w0, int numV, int p0, int n, int S,
                      cudaStream_t st);
-int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float* pp, int B, int P, int crop_stride,
+// where the up-sampling tail writes: whole SR patches, the crops LFintegrate keeps, or those crops at their final position in
+// the assembled SR light field (which may be a peer-mapped buffer of another GPU)
+struct UpTarget {
+  int mode = 0;           // 0: sr [B,1,H,H]   1: crops [B][A][A][cs][cs]   2: sr_lf [A*h0*s, A*w0*s] (LFintegrate fused)
+  int crop_stride = 0;    // LR stride S of the tiling (modes 1, 2)
+  int h0 = 0, w0 = 0, numV = 0, p0 = 0;  // mode 2: light-field geometry and the index of the first patch of this chunk
+};
+Region up_region(int P, int s, const UpTarget& t);  // LR pixels of every view the kept SR pixels depend on
+int run_upsample(Handle* h, const float* feat, const float* lr, float* out, float* pp, int B, int P, const UpTarget& t,
                  cudaStream_t st);
 
 }  // namespace lft

@@ -1,6 +1,7 @@
 // Kernel-side shared declarations: CTA roles, control block, setup/teardown, kernel prototypes.
 #pragma once
 #include "common.cuh"
+#include "host.h"
 
 namespace lft {
 
@@ -98,9 +99,11 @@ LFT_DEVINL long long t32_off(long long t, int chunk, int C4) {
 
 // Stage the 64-channel input window of a 3x3 conv tile: smem rows r <-> padded positions g0-kConvOff+r,
 // one lane per row (T32 source: a warp reads 512 contiguous bytes per chunk), bf16 hi/lo, chunk-major.
+// The position space covers the region `e` of every view: rows of e.rn + 1 positions (+ one pad row), VS = (e.rn + 1)^2;
+// position (yy, xx) <-> pixel (e.r0 + yy, e.r0 + xx).
 LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, uint32_t a_lo, long long g0, long long G,
-                                  long long VS, int P, int tid, bool fp32_mode) {
-  const int P1 = P + 1;
+                                  long long VS, int P, Region e, int tid, bool fp32_mode) {
+  const int P1 = e.rn + 1;
   for (int r = tid; r < kConvRows; r += kRowThreads2) {
     const long long g = g0 - kConvOff + r;
     long long tok = -1;
@@ -109,7 +112,7 @@ LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, u
       const unsigned v = gu / vsu;
       const int qq = (int)(gu - v * vsu);
       const int y = qq / P1, x = qq - y * P1;
-      if (y < P && x < P) tok = (long long)((v * P + y) * P + x);
+      if (y < e.rn && x < e.rn) tok = (long long)((v * P + e.r0 + y) * P + e.r0 + x);
     }
     float4 f[16];
 #pragma unroll
@@ -126,8 +129,9 @@ LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, u
 }
 
 // L2 prefetch of the rows conv_stage_window will read for the tile at g0 (same row <-> thread mapping)
-LFT_DEVINL void conv_prefetch_window(const float* __restrict__ in, long long g0, long long G, long long VS, int P, int tid) {
-  const int P1 = P + 1;
+LFT_DEVINL void conv_prefetch_window(const float* __restrict__ in, long long g0, long long G, long long VS, int P, Region e,
+                                     int tid) {
+  const int P1 = e.rn + 1;
   for (int r = tid; r < kConvRows; r += kRowThreads2) {
     const long long g = g0 - kConvOff + r;
     if (g >= 0 && g < G) {
@@ -135,8 +139,8 @@ LFT_DEVINL void conv_prefetch_window(const float* __restrict__ in, long long g0,
       const unsigned v = gu / vsu;
       const int qq = (int)(gu - v * vsu);
       const int y = qq / P1, x = qq - y * P1;
-      if (y < P && x < P) {
-        const long long tok = (long long)((v * P + y) * P + x);
+      if (y < e.rn && x < e.rn) {
+        const long long tok = (long long)((v * P + e.r0 + y) * P + e.r0 + x);
 #pragma unroll
         for (int i = 0; i < 16; ++i) prefetch_l2(in + t32_off(tok, i, 16));
       }

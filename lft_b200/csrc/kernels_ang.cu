@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(kThreads2, 2)
 k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __restrict__ wqk,
       const uint8_t* __restrict__ wv, const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1,
       const uint8_t* __restrict__ w2, const __grid_constant__ Tab512 tab, const float* __restrict__ peqk,
-      const float* __restrict__ pe, int Nrt, int PP, long long npix, int passes, int ntiles) {
+      const float* __restrict__ pe, int Nrt, int P, long long npix, int passes, int ntiles, Region rg) {
+  // rg: the pixels of every patch view this launch computes (full view: {0, P}); npix = B * rg.rn^2 compacted pixels
+  const int PP = P * P;
   const int N = NV > 0 ? NV : Nrt;
   // Specialised views-per-pixel counts (A = 3, 5, 7, 9) pair two views of one pixel in lanes l / l+16 and share every K/V read
   // between them (kPair); pixels per tile: 12 / 5 / 2 / 1, softmax chunk = A keys.
@@ -313,8 +315,11 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     auto row_token = [&](int t) -> long long {
       const long long gp = (long long)t * PPT + pl;
       if (a >= N || gp >= npix) return -1;
-      const unsigned b = (unsigned)gp / (unsigned)PP;  // npix < 2^31
-      const int p = (int)((unsigned)gp - b * (unsigned)PP);
+      const unsigned RR = (unsigned)(rg.rn * rg.rn);
+      const unsigned b = (unsigned)gp / RR;  // npix < 2^31
+      const int rem = (int)((unsigned)gp - b * RR);
+      const int yy = rem / rg.rn;
+      const int p = (rg.r0 + yy) * P + rg.r0 + rem - yy * rg.rn;
       return ((long long)b * N + a) * PP + p;
     };
     // persistent: the CTA walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ... keeping its TMEM, barriers and the
@@ -649,19 +654,19 @@ int configure_ang() {
   return 0;
 }
 
-int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, cudaStream_t st) {
+int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, Region rg, cudaStream_t st) {
   const int N = h->cfg.ang_res * h->cfg.ang_res;
-  const long long npix = (long long)B * P * P;
+  const long long npix = (long long)B * rg.rn * rg.rn;
   const int PPT = N == 9 ? 12 : N == 25 ? 5 : N == 49 ? 2 : N == 81 ? 1 : 128 / N;  // keep in step with kPPT in k_ang
   const unsigned ntiles = (unsigned)((npix + PPT - 1) / PPT);
   const unsigned grid = ntiles < 2u * h->num_sms ? ntiles : 2u * h->num_sms;  // persistent: two CTAs per SM
   const Layer& L = h->layer[layer];
   Tab512 ta;
   memcpy(ta.v, L.a_tab.data(), sizeof(ta.v));
-  Scope sc(h, K_ANG, st);
+  Scope sc(h, K_ANG, st, npix * N);
 #define LFT_ANG_LAUNCH(NV)                                                                                          \
   k_ang<NV><<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, ta, L.a_peqk, \
-                                               h->pe_ang, N, P * P, npix, h->passes(), (int)ntiles)
+                                               h->pe_ang, N, P, npix, h->passes(), (int)ntiles, rg)
   if (N == 25) LFT_ANG_LAUNCH(25);
   else if (N == 9) LFT_ANG_LAUNCH(9);
   else if (N == 49) LFT_ANG_LAUNCH(49);

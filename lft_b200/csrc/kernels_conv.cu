@@ -217,7 +217,7 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
       if (N == 64 && in == nullptr)
         conv_stage_window_lr(lr, w0, A, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
       else
-        conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
+        conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, Region{0, P}, tid, passes == 3);
       fence_proxy_async_smem();
       mbar_arrive(a_ready);
     };
@@ -280,7 +280,7 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
       }
       // pull the window of tile k+2 into L2 while tile k+1's MMAs run (-4.6 %; the same hint in k_spa_embed_qkv, whose
       // staging is already hidden under its Q MMA, changed nothing)
-      if (in != nullptr && k + 2 < ntl) conv_prefetch_window(in, (long long)(first + (k + 2) * step) * 128, G, VS, P, tid);
+      if (in != nullptr && k + 2 < ntl) conv_prefetch_window(in, (long long)(first + (k + 2) * step) * 128, G, VS, P, Region{0, P}, tid);
     }
     tc_fence_before();
   }
@@ -524,7 +524,7 @@ int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, const u
     return fail(LFT_ERR_ARG, "launch_conv3x3: fused conv_init0 needs N == 64 and the LR mosaic");
   W0Tab w0;
   memcpy(w0.w, h->w_conv0_host.data(), sizeof(w0.w));
-  Scope sc(h, K_CONV64, st);
+  Scope sc(h, K_CONV64, st, (long long)V * P * P);
   if (N != 64) return fail(LFT_ERR_ARG, "launch_conv3x3: only the 64 -> 64 conv stack uses this kernel (the 64 -> 128 token embedding is part of k_spa_embed_qkv)");
   k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst, (int)ntiles);
   return sc.finish();

@@ -60,7 +60,10 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
                   const float* __restrict__ pev, const __grid_constant__ Tab512 tab, const uint8_t* __restrict__ wq,
                   const uint8_t* __restrict__ wk, const uint8_t* __restrict__ wv, float* __restrict__ tok,
                   float* __restrict__ Q, float* __restrict__ K, float* __restrict__ Vv, int V, int P, int passes,
-                  int ntiles) {
+                  int ntiles, Region e, Region o) {
+  // e: the pixels the position space covers (conv inputs; zero padding outside it), o: the pixels whose tok / Q / K / V are
+  // stored.  Full view: e = o = {0, P}.  On the light-field path e is the region the conv inputs are valid on and o = e
+  // shrunk by one pixel wherever e's border is not the view border (there the zero padding is not the true neighbour).
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t U = smem_u32(smem) + kCtlBytes;
@@ -70,7 +73,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
   const uint32_t f_ready = smem_u32(&ctl->aux[0]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int P1 = P + 1;
+  const int P1 = e.rn + 1;
   const long long VS = (long long)P1 * P1;
   const long long G = (long long)V * VS;
   cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
@@ -124,7 +127,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       tc_fence_after();
     };
     auto stage = [&](int k) {
-      conv_stage_window(feat, c_hi, c_lo, (long long)(first + k * step) * 128, G, VS, P, tid, passes == 3);
+      conv_stage_window(feat, c_hi, c_lo, (long long)(first + k * step) * 128, G, VS, P, e, tid, passes == 3);
       fence_proxy_async_smem();
       mbar_arrive(f_ready);
     };
@@ -138,9 +141,10 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
         const unsigned gu = (unsigned)g, vsu = (unsigned)VS;
         v = gu / vsu;
         const int qq = (int)(gu - (unsigned)v * vsu);
-        y = qq / P1;
-        x = qq - y * P1;
-        ok = (y < P && x < P);
+        const int yy = qq / P1, xx = qq - yy * P1;
+        y = e.r0 + yy;
+        x = e.r0 + xx;
+        ok = yy < e.rn && xx < e.rn && (unsigned)(y - o.r0) < (unsigned)o.rn && (unsigned)(x - o.r0) < (unsigned)o.rn;
       }
       if (!ok) { v = 0; y = 0; x = 0; }
 #ifdef LFT_EXPERIMENT_NOSTORE
@@ -279,14 +283,17 @@ constexpr size_t kSmemAttn = 2 * (kAttnRB + 4) * 4 * 32 * 16 + 16;
 
 __global__ void __launch_bounds__(kAttnThreads)
 k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ Vv,
-           float* __restrict__ O, int P) {
+           float* __restrict__ O, int P, Region qr) {
+  // qr: the query pixels [qr.r0, qr.r0 + qr.rn)^2 of every view (full view: {0, P}); keys come from the 5 x 5 window clamped
+  // to the VIEW, so K / V must be valid on qr grown by two pixels.
   extern __shared__ __align__(128) uint8_t smem[];
-  const int nblk = (P + kAttnRB - 1) / kAttnRB;
+  const int nblk = (qr.rn + kAttnRB - 1) / kAttnRB;
   const int rb = blockIdx.x % nblk;
   const int head = (blockIdx.x / nblk) & 7;
   const long long v = blockIdx.x / (nblk * 8);
-  const int r0 = rb * kAttnRB;
-  const int ys = max(r0 - 2, 0), ye = min(r0 + kAttnRB + 2, P);   // staged key rows [ys, ye)
+  const int r0 = qr.r0 + rb * kAttnRB;
+  const int rend = qr.r0 + qr.rn;                                  // one past the last query row / column
+  const int ys = max(r0 - 2, 0), ye = min(min(r0 + kAttnRB, rend) + 2, P);   // staged key rows [ys, ye)
   const uint32_t rowbytes = (uint32_t)P * 64;                      // one (y) plane: 4 pieces x P x 16 B
   const uint32_t nbytes = (uint32_t)(ye - ys) * rowbytes;
   const uint32_t bar = smem_u32(smem);
@@ -303,11 +310,11 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
     bulk_g2s(smem_u32(ks), K + src, nbytes, bar);
     bulk_g2s(smem_u32(vs), Vv + src, nbytes, bar);
   }
-  const int x = threadIdx.x % P;
-  const int rp = threadIdx.x / P;
+  const int x = qr.r0 + (int)(threadIdx.x % (unsigned)qr.rn);
+  const int rp = threadIdx.x / (unsigned)qr.rn;
   const int y0 = r0 + 2 * rp;
-  const bool active = (rp < kAttnRB / 2) && (y0 < P);
-  const bool two = active && (y0 + 1) < P;
+  const bool active = (rp < kAttnRB / 2) && (y0 < rend);
+  const bool two = active && (y0 + 1) < rend;
   const long long rowstride = (long long)P * 16;  // floats between consecutive y
   const int jstride = P * 4;                      // floats between the 4 pieces of one (y, x)
   const long long base = planar_off(v, head, 0, 0, x, P);
@@ -417,7 +424,8 @@ __global__ void __launch_bounds__(kThreads2, 2)
 k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_constant__ Tab512 tab,
           const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1a, const uint8_t* __restrict__ w1b,
           const uint8_t* __restrict__ w2a, const uint8_t* __restrict__ w2b, const uint8_t* __restrict__ wlin,
-          float* __restrict__ out, const float* __restrict__ final_res, long long T, int P, int passes) {
+          float* __restrict__ out, const float* __restrict__ final_res, long long T, int P, int passes, Region fr) {
+  // fr: the pixels of every view this launch computes (full view: {0, P}); T = views * fr.rn^2 compacted tokens, 128 per CTA
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t A = smem_u32(smem) + kCtlBytes;
@@ -476,12 +484,20 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     const long long t = (long long)blockIdx.x * 128 + m;
     const bool ok = t < T;
-    const unsigned tt = ok ? (unsigned)t : 0u;  // T < 2^31 (checked on the host): 32-bit index math
-    const unsigned PP = (unsigned)(P * P);
-    const unsigned vu = tt / PP;
+    const unsigned PP = (unsigned)(P * P), RR = (unsigned)(fr.rn * fr.rn);
+    // compacted token index -> (view, y, x) -> token of the full view; T < 2^31 (checked on the host): 32-bit index math
+    auto locate = [&](unsigned tc, unsigned& vu, int& y, int& x) {
+      vu = tc / RR;
+      const int rem = (int)(tc - vu * RR);
+      const int yy = rem / fr.rn;
+      y = fr.r0 + yy;
+      x = fr.r0 + rem - yy * fr.rn;
+      return vu * PP + (unsigned)(y * P + x);
+    };
+    unsigned vu;
+    int y, x;
+    const unsigned tt = locate(ok ? (unsigned)t : 0u, vu, y, x);
     const long long v = vu;
-    const int p = (int)(tt - vu * PP);
-    const int y = p / P, x = p - y * P;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* trow_g = tok + t32_off(tt, 16 * q, 32);  // own half of the token row, chunk stride 128 floats (Y1 is spilled here)
     uint32_t par = 0;
@@ -556,8 +572,9 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
        // on some SM about one tile time from now (k_spa_ffn -1 %; a persistent version of this kernel was 7 % slower)
       const long long tn = t + 296ll * 128;
       if (tn < T) {
-        const unsigned tnu = (unsigned)tn, vn = tnu / PP;
-        const int pn = (int)(tnu - vn * PP), yn = pn / P, xn = pn - yn * P;
+        unsigned vn;
+        int yn, xn;
+        const unsigned tnu = locate((unsigned)tn, vn, yn, xn);
         const float* obn = O + planar_off(vn, 4 * q, yn, 0, xn, P);
         const long long hs = (long long)PP * 16, js = (long long)P * 4;
         const float* tgn = tok + t32_off(tnu, 16 * q, 32);
@@ -701,38 +718,48 @@ int configure_spa() {
   return 0;
 }
 
-// altblock[layer].spa_trans: in [T,64] -> out [T,64]
+// altblock[layer].spa_trans: in [T,64] -> out [T,64].  `need`: the pixels of every view the caller needs `out` on (full view:
+// {0, P}); `in` must be valid on `need` grown by 3 pixels (2 for the attention window + 1 for the 3x3 token embedding), clipped
+// to the view.
+static Region grow(Region r, int k, int P) {
+  const int lo = r.r0 - k < 0 ? 0 : r.r0 - k;
+  const int hi = r.r0 + r.rn + k > P ? P : r.r0 + r.rn + k;
+  return Region{lo, hi - lo};
+}
+
 int run_spa(Handle* h, int layer, const float* in, float* out, const float* final_res, Workspace& w, int B, int P,
-            cudaStream_t st) {
+            Region need, cudaStream_t st) {
   const int A = h->cfg.ang_res;
   const long long V = (long long)B * A * A;
-  const long long T = V * P * P;
   const Layer& L = h->layer[layer];
+  const Region kv = grow(need, 2, P);   // K / V (and tok, Q) are stored here
+  const Region e = grow(need, 3, P);    // conv inputs
   int rc;
   {
-    const long long G = V * (P + 1) * (P + 1);
+    const long long G = V * (e.rn + 1) * (e.rn + 1);
     Tab512 tq;
     memcpy(tq.v, L.s_tab.data(), sizeof(tq.v));  // [u_q | u_k | c_q | c_k]
-    Scope sc(h, K_SPA_QKV, st);
+    Scope sc(h, K_SPA_QKV, st, V * kv.rn * kv.rn);
     const unsigned ntiles = (unsigned)((G + 127) / 128);
     const unsigned pg = ntiles < 2u * h->num_sms ? ntiles : 2u * h->num_sms;  // persistent: two CTAs per SM
     k_spa_embed_qkv<<<pg, kThreads2, kSmemSpa, st>>>(in, L.s_wmlp, L.s_pe, L.s_pev, tq, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q,
-                                                     w.k, w.v, (int)V, P, h->passes(), (int)ntiles);
+                                                     w.k, w.v, (int)V, P, h->passes(), (int)ntiles, e, kv);
     if ((rc = sc.finish())) return rc;
   }
   {
-    Scope sc(h, K_SPA_ATTN, st);
-    const int nblk = (P + kAttnRB - 1) / kAttnRB;
-    k_spa_attn<<<(unsigned)(V * 8 * nblk), kAttnThreads, kSmemAttn, st>>>(w.q, w.k, w.v, w.o, P);
+    Scope sc(h, K_SPA_ATTN, st, V * need.rn * need.rn);
+    const int nblk = (need.rn + kAttnRB - 1) / kAttnRB;
+    k_spa_attn<<<(unsigned)(V * 8 * nblk), kAttnThreads, kSmemAttn, st>>>(w.q, w.k, w.v, w.o, P, need);
     if ((rc = sc.finish())) return rc;
   }
   {
     Tab512 tf;
     memcpy(tf.v, L.s_tab.data() + 512, sizeof(tf.v));  // [u_1 256 | c_1 256]
-    Scope sc(h, K_SPA_FFN, st);
+    const long long T = V * need.rn * need.rn;
+    Scope sc(h, K_SPA_FFN, st, T);
     k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
                                                                         L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P,
-                                                                        h->passes());
+                                                                        h->passes(), need);
     if ((rc = sc.finish())) return rc;
   }
   return 0;

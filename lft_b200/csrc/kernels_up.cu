@@ -39,7 +39,8 @@ constexpr uint32_t kLbo64 = 128 * 16;
 //   wait is off the critical path, G1(ij+2) is needed two iterations later).
 __global__ void __launch_bounds__(kThreads2, 2)
 k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const uint8_t* __restrict__ w3p,
-          float* __restrict__ Pp, long long T, int A, int P, int s, int passes) {
+          float* __restrict__ Pp, long long T, int A, int P, int s, int passes, Region ur) {
+  // ur: the LR pixels of every view this launch computes (full view: {0, P}); T = views * ur.rn^2 compacted tokens
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t A1 = smem_u32(smem) + kCtlBytes;
@@ -120,11 +121,21 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
     const long long t = (long long)blockIdx.x * 128 + m;
     const bool ok = t < T;
-    const unsigned tu = ok ? (unsigned)t : 0u;  // T < 2^31
-    const unsigned PP = (unsigned)(P * P), N = (unsigned)(A * A);
-    const int x = (int)(tu % (unsigned)P), y = (int)((tu / (unsigned)P) % (unsigned)P);
-    const int a = (int)((tu / PP) % N);
-    const long long b = tu / (PP * N);
+    const unsigned PP = (unsigned)(P * P), N = (unsigned)(A * A), RR = (unsigned)(ur.rn * ur.rn);
+    // compacted token index -> (view, y, x) -> token of the full view (T < 2^31)
+    auto locate = [&](unsigned tc, unsigned& va, int& y, int& x) {
+      va = tc / RR;
+      const int rem = (int)(tc - va * RR);
+      const int yy = rem / ur.rn;
+      y = ur.r0 + yy;
+      x = ur.r0 + rem - yy * ur.rn;
+      return va * PP + (unsigned)(y * P + x);
+    };
+    unsigned va;
+    int y, x;
+    const unsigned tu = locate(ok ? (unsigned)t : 0u, va, y, x);
+    const int a = (int)(va % N);
+    const long long b = va / N;
     const int u = a / A, v = a - u * A;
     const int H = A * P * s;
     const long long Y0 = (long long)(u * P + y) * s, X0 = (long long)(v * P + x) * s;
@@ -146,8 +157,11 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
       mbar_arrive(a1_ready);
     }
     if (t + 296ll * 128 < T) {  // speculative L2 prefetch of the rows of the tile 2 CTAs x 148 SMs ahead (-1.8 %)
+      unsigned vn;
+      int yn, xn;
+      const unsigned tn = locate((unsigned)t + 296u * 128u, vn, yn, xn);
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) prefetch_l2(feat + t32_off(tu + 296u * 128u, 8 * q + kc, 16));
+      for (int kc = 0; kc < 8; ++kc) prefetch_l2(feat + t32_off(tn, 8 * q + kc, 16));
     }
     float pj[4][5];                             // [sub-pixel column j][own tap]
 #pragma unroll
@@ -224,11 +238,14 @@ LFT_DEVINL void cubic_coeffs(float t, float* c) {
   c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
-// crop == 0: out = sr [B,1,H,H];   crop == 1: out = crops [B][A][A][cs][cs], the block LFintegrate keeps of every SR view
-// (side cs = stride*s at offset c0 = ((P - stride)*s)/2, utils.py:145,152)
+// mode 0: out = sr [B,1,H,H];   mode 1: out = crops [B][A][A][cs][cs], the block LFintegrate keeps of every SR view
+// (side cs = stride*s at offset c0 = ((P - stride)*s)/2, utils.py:145,152);   mode 2: the same block stored at its final place
+// in the assembled SR light field out = sr_lf [A*h0*s, A*w0*s] (LFintegrate, utils.py:141-157, + test.py:100-101 fused;
+// patch b of this launch is patch p0 + b of the light field, the ragged last row / column is clipped).  In mode 2 `out` may
+// be a peer-mapped buffer of another GPU: plain stores over NVLink, one 256-byte run per crop row.
 __global__ void __launch_bounds__(256)
 k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* __restrict__ out, int B, int A, int P,
-            int s, int crop, int cs, int c0) {
+            int s, int mode, int cs, int c0, int h0, int w0, int numV, int p0) {
   const int H = A * P * s;
   const int Ps = P * s;
   const long long total = (long long)B * A * A * cs * cs;
@@ -236,7 +253,7 @@ k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* _
   if (gid >= total) return;
   const unsigned gu = (unsigned)gid;  // total < 2^31 (host-checked)
   int b, u, v, yy, xx;
-  if (crop) {  // [b][u][v][cy][cx]
+  if (mode) {  // [b][u][v][cy][cx]
     const unsigned csu = (unsigned)cs, Au = (unsigned)A;
     xx = (int)(gu % csu) + c0;
     yy = (int)((gu / csu) % csu) + c0;
@@ -249,6 +266,18 @@ k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* _
     b = (int)(gu / (Hu * Hu));
     u = Y / Ps; yy = Y - u * Ps;
     v = X / Ps; xx = X - v * Ps;
+  }
+  long long dst;
+  if (mode == 2) {
+    const int pi = p0 + b;
+    const int kh = pi / numV, kw = pi - kh * numV;
+    const int Yd = kh * cs + (yy - c0), Xd = kw * cs + (xx - c0);
+    if (Yd >= h0 * s || Xd >= w0 * s) return;  // temp[0:h0, 0:w0] of utils.py:155
+    dst = ((long long)u * h0 * s + Yd) * ((long long)A * w0 * s) + (long long)v * w0 * s + Xd;
+  } else if (mode == 1) {
+    dst = gid;
+  } else {
+    dst = ((long long)b * H + (u * Ps + yy)) * H + v * Ps + xx;
   }
   const int Y = u * Ps + yy, X = v * Ps + xx;
   float acc = 0.f;
@@ -287,7 +316,7 @@ k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* _
     rowv[r] = e[0] * wx[0] + e[1] * wx[1] + e[2] * wx[2] + e[3] * wx[3];
   }
   bic = rowv[0] * wy[0] + rowv[1] * wy[1] + rowv[2] * wy[2] + rowv[3] * wy[3];
-  out[crop ? gid : ((long long)b * H + Y) * H + X] = acc + bic;
+  out[dst] = acc + bic;
 }
 
 // LFdivide (utils.py:91-138) for patch size P, stride S, bdr = (P - S) / 2 (test.py's defaults: 32, 16, 8).
@@ -335,24 +364,39 @@ int configure_up() {
   return 0;
 }
 
-// upsampling(mosaic(feat)) + bicubic(lr).  crop_stride > 0: write only the crops LFintegrate keeps for that LR stride.
-int run_upsample(Handle* h, const float* feat, const float* lr, float* sr, float* pp, int B, int P, int crop_stride,
+// LR pixels of every view that the SR pixels kept by `t` depend on: the kept HR block [c0, c0 + cs) plus the one-pixel halo
+// of the final 3x3 conv, in LR pixels.  c0 == 0 (stride == patch) keeps whole views, whose halo reaches into the neighbouring
+// views of the mosaic: full region.
+Region up_region(int P, int s, const UpTarget& t) {
+  if (t.mode == 0 || t.crop_stride <= 0) return Region{0, P};
+  const int cs = t.crop_stride * s, c0 = ((P - t.crop_stride) * s) / 2;
+  if (c0 == 0) return Region{0, P};
+  const int lo = (c0 - 1) / s;
+  int hi = (c0 + cs) / s;  // LR pixel of HR row c0 + cs (the halo below the block)
+  if (hi > P - 1) hi = P - 1;
+  return Region{lo, hi - lo + 1};
+}
+
+// upsampling(mosaic(feat)) + bicubic(lr); see UpTarget for where the result goes.  Only the LR pixels the kept SR pixels
+// depend on go through the two GEMMs (18 x 18 of 32 x 32 per view for the default 32 / 16 tiling).
+int run_upsample(Handle* h, const float* feat, const float* lr, float* out, float* pp, int B, int P, const UpTarget& t,
                  cudaStream_t st) {
   const int A = h->cfg.ang_res, s = h->cfg.scale;
-  const long long T = (long long)B * A * A * P * P;
+  if (t.mode && (t.crop_stride < 1 || t.crop_stride > P)) return fail(LFT_ERR_ARG, "crop stride %d outside [1, P=%d]", t.crop_stride, P);
+  const Region ur = up_region(P, s, t);
+  const long long T = (long long)B * A * A * ur.rn * ur.rn;
   int rc;
   {
-    Scope sc(h, K_UP_GEMM, st);
-    k_up_gemm<<<(unsigned)((T + 127) / 128), kThreads2, kSmemUp, st>>>(feat, h->w_up, h->w_up3, pp, T, A, P, s, h->passes());
+    Scope sc(h, K_UP_GEMM, st, T);
+    k_up_gemm<<<(unsigned)((T + 127) / 128), kThreads2, kSmemUp, st>>>(feat, h->w_up, h->w_up3, pp, T, A, P, s, h->passes(), ur);
     if ((rc = sc.finish())) return rc;
   }
   {
-    if (crop_stride < 0 || crop_stride > P) return fail(LFT_ERR_ARG, "crop stride %d outside [1, P=%d]", crop_stride, P);
-    const int cs = crop_stride ? crop_stride * s : P * s;
-    const int c0 = crop_stride ? ((P - crop_stride) * s) / 2 : 0;  // bdr of LFintegrate(pz = P*s, stride = S*s), utils.py:145
+    const int cs = t.mode ? t.crop_stride * s : P * s;
+    const int c0 = t.mode ? ((P - t.crop_stride) * s) / 2 : 0;  // bdr of LFintegrate(pz = P*s, stride = S*s), utils.py:145
     const long long total = (long long)B * A * A * cs * cs;
-    Scope sc(h, K_UP_GATHER, st);
-    k_up_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pp, lr, sr, B, A, P, s, crop_stride ? 1 : 0, cs, c0);
+    Scope sc(h, K_UP_GATHER, st, total);
+    k_up_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pp, lr, out, B, A, P, s, t.mode, cs, c0, t.h0, t.w0, t.numV, t.p0);
     if ((rc = sc.finish())) return rc;
   }
   return 0;
@@ -362,7 +406,7 @@ int launch_divide(Handle* h, const float* lf, float* patches, int h0, int w0, in
                   cudaStream_t st) {
   const int A = h->cfg.ang_res;
   const long long total = (long long)n * A * P * A * P;
-  Scope sc(h, K_DIVIDE, st);
+  Scope sc(h, K_DIVIDE, st, total);
   k_lf_divide<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lf, patches, A, h0, w0, numV, p0, n, P, S, (P - S) / 2);
   return sc.finish();
 }
@@ -372,7 +416,7 @@ int launch_integrate(Handle* h, const float* crops, float* sr, int h0, int w0, i
   const int A = h->cfg.ang_res, s = h->cfg.scale;
   const int cs = S * s;
   const long long total = (long long)n * A * A * cs * cs;
-  Scope sc(h, K_INTEGRATE, st);
+  Scope sc(h, K_INTEGRATE, st, total);
   k_lf_integrate<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(crops, sr, A, h0, w0, s, numV, p0, n, cs);
   return sc.finish();
 }

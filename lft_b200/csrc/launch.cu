@@ -1,20 +1,28 @@
 // Launch sequences: which kernels run, in what order, on which buffers (all on the caller's stream).
 #include "host.h"
 
+#include <cstring>
+#include <mutex>
+#include <set>
+
 namespace lft {
 
 const char* const kKindNames[K_COUNT] = {"conv0",    "conv3x3_64", "conv3x3_128", "ang_fused", "spa_embed_qkv", "spa_attn",
                                          "spa_ffn",  "up_gemm",    "up_gather",   "lf_divide", "lf_integrate"};
 
-int configure_kernels() {
-  static bool done = false;
-  if (done) return 0;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: configure every device a handle is created on once
+// (the caller has made `device` current).
+int configure_kernels(int device) {
+  static std::mutex mu;
+  static std::set<int> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count(device)) return 0;
   int rc;
   if ((rc = configure_conv())) return rc;
   if ((rc = configure_ang())) return rc;
   if ((rc = configure_spa())) return rc;
   if ((rc = configure_up())) return rc;
-  done = true;
+  done.insert(device);
   return 0;
 }
 
@@ -52,19 +60,33 @@ int run_conv_init(Handle* h, const float* lr, float* out, float* tmp0, float* tm
   return 0;
 }
 
-// get_model.forward for one chunk of B patches (LFT.py:52-83).  crop_stride > 0: `out` receives only the
-// crops [B][A][A][S*s][S*s] that LFintegrate keeps for LR stride S.
-int run_forward_chunk(Handle* h, const float* lr, float* out, Workspace& w, int B, int P, int crop_stride,
+static Region grow3(Region r, int P) {  // receptive field of one AltFilter: 5x5 window (2) + 3x3 token embedding (1)
+  const int lo = r.r0 - 3 < 0 ? 0 : r.r0 - 3;
+  const int hi = r.r0 + r.rn + 3 > P ? P : r.r0 + r.rn + 3;
+  return Region{lo, hi - lo};
+}
+
+// get_model.forward for one chunk of B patches (LFT.py:52-83); `up` says where the result goes (whole SR patches, the crops
+// LFintegrate keeps, or those crops at their place in the assembled light field).
+// Dead-work elimination on the light-field path: LFintegrate keeps the central stride*s block of every SR patch view, which
+// depends on the LR pixels up_region() of the last feature map; each AltFilter widens that by 3 pixels (AngTrans is
+// pixel-wise, SpaTrans = 5x5 window + 3x3 embedding).  Layer i therefore runs on need[i] only - for the default 32 / 16
+// tiling 18^2, 24^2, 30^2, 32^2 of the 32^2 pixels from the last layer backwards.  Every kernel computes a token exactly as
+// it does on the full view, so the kept pixels are bit-identical to the crop of the full forward.
+int run_forward_chunk(Handle* h, const float* lr, float* out, Workspace& w, int B, int P, const UpTarget& up,
                       cudaStream_t st) {
   int rc;
   if ((rc = run_conv_init(h, lr, w.fres, w.f0, w.f1, w.f2, B, P, st))) return rc;
+  Region need[kLayers];
+  need[kLayers - 1] = up_region(P, h->cfg.scale, up);
+  for (int i = kLayers - 2; i >= 0; --i) need[i] = grow3(need[i + 1], P);
   const float* x = w.fres;
   for (int i = 0; i < kLayers; ++i) {  // AltFilter: ang_trans then spa_trans (LFT.py:248-252)
-    if ((rc = run_ang(h, i, x, w.f1, B, P, st))) return rc;
-    if ((rc = run_spa(h, i, w.f1, w.f2, i == kLayers - 1 ? w.fres : nullptr, w, B, P, st))) return rc;
+    if ((rc = run_ang(h, i, x, w.f1, B, P, grow3(need[i], P), st))) return rc;
+    if ((rc = run_spa(h, i, w.f1, w.f2, i == kLayers - 1 ? w.fres : nullptr, w, B, P, need[i], st))) return rc;
     x = w.f2;
   }
-  return run_upsample(h, w.f2, lr, out, w.pp, B, P, crop_stride, st);
+  return run_upsample(h, w.f2, lr, out, w.pp, B, P, up, st);
 }
 
 // numU / numV of LFdivide (utils.py:93-104) for patch size P and stride S (test.py:83 passes args.patch_size_for_test /
@@ -84,6 +106,10 @@ static int tiling(int h0, int w0, int P, int S, int* numU, int* numV) {
     return fail(LFT_ERR_ARG, "light field %dx%d per view is smaller than the mirror border %d", h0, w0, bdr);
   const int nu = num_patches_1d(h0, P, S, bdr), nv = num_patches_1d(w0, P, S, bdr);
   if (nu < 1 || nv < 1) return fail(LFT_ERR_ARG, "light field %dx%d per view yields no patch of size %d at stride %d", h0, w0, P, S);
+  // an odd (patch - stride) can leave numU*stride == h0 - 1: the reference's LFintegrate then fails with a shape mismatch
+  // (utils.py:155 assigns a [numU*stride, ...] block to [h0, ...]); rejected instead of returning an unwritten last row
+  if (nu * S < h0 || nv * S < w0)
+    return fail(LFT_ERR_ARG, "patch %d / stride %d does not cover a %dx%d view (%d x %d kept pixels): the reference's LFintegrate fails here too", P, S, h0, w0, nu * S, nv * S);
   *numU = nu;
   *numV = nv;
   return 0;
@@ -98,7 +124,6 @@ static int check_ready(Handle* h, int B, int P) {
   if (!h->finalized) return fail(LFT_ERR_STATE, "weights not finalized (call lft_finalize_weights)");
   if (B < 1) return fail(LFT_ERR_ARG, "B must be >= 1");
   if (P < 4 || P > 32) return fail(LFT_ERR_ARG, "patch size P=%d unsupported (4..32, square patches only)", P);
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
   return ensure_spa_pe(h, P);
 }
 
@@ -124,6 +149,9 @@ int lft_workspace_bytes(lft_handle* hh, int32_t B, int32_t P, size_t* bytes) {
 int lft_stage_conv_init(lft_handle* hh, const float* lr, float* feat, int32_t B, int32_t P, void* ws, size_t ws_bytes,
                         void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(LFT_ERR_ARG, "null handle");
+  DeviceGuard dg(h->cfg.device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", h->cfg.device);
   int rc = check_ready(h, B, P);
   if (rc) return rc;
   if ((rc = check_stage_size(h, B, P))) return rc;
@@ -139,6 +167,9 @@ int lft_stage_conv_init(lft_handle* hh, const float* lr, float* feat, int32_t B,
 int lft_stage_ang(lft_handle* hh, int32_t layer, const float* in, float* out, int32_t B, int32_t P, void* ws,
                   size_t ws_bytes, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(LFT_ERR_ARG, "null handle");
+  DeviceGuard dg(h->cfg.device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", h->cfg.device);
   int rc = check_ready(h, B, P);
   if (rc) return rc;
   if ((rc = check_stage_size(h, B, P))) return rc;
@@ -149,13 +180,16 @@ int lft_stage_ang(lft_handle* hh, int32_t layer, const float* in, float* out, in
   const long long T = (long long)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
   Workspace w = carve(ws, T, h->cfg.scale);
   if ((rc = launch_layout(h, in, w.f0, T, 64, 1, (cudaStream_t)stream))) return rc;
-  if ((rc = run_ang(h, layer, w.f0, w.f1, B, P, (cudaStream_t)stream))) return rc;
+  if ((rc = run_ang(h, layer, w.f0, w.f1, B, P, Region{0, P}, (cudaStream_t)stream))) return rc;
   return launch_layout(h, w.f1, out, T, 64, 0, (cudaStream_t)stream);
 }
 
 int lft_stage_spa(lft_handle* hh, int32_t layer, const float* in, float* out, int32_t B, int32_t P, void* ws,
                   size_t ws_bytes, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(LFT_ERR_ARG, "null handle");
+  DeviceGuard dg(h->cfg.device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", h->cfg.device);
   int rc = check_ready(h, B, P);
   if (rc) return rc;
   if ((rc = check_stage_size(h, B, P))) return rc;
@@ -166,13 +200,16 @@ int lft_stage_spa(lft_handle* hh, int32_t layer, const float* in, float* out, in
   const long long T = (long long)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
   Workspace w = carve(ws, T, h->cfg.scale);
   if ((rc = launch_layout(h, in, w.f0, T, 64, 1, (cudaStream_t)stream))) return rc;
-  if ((rc = run_spa(h, layer, w.f0, w.f1, nullptr, w, B, P, (cudaStream_t)stream))) return rc;
+  if ((rc = run_spa(h, layer, w.f0, w.f1, nullptr, w, B, P, Region{0, P}, (cudaStream_t)stream))) return rc;
   return launch_layout(h, w.f1, out, T, 64, 0, (cudaStream_t)stream);
 }
 
 int lft_stage_upsample(lft_handle* hh, const float* feat, const float* lr, float* sr, int32_t B, int32_t P, void* ws,
                        size_t ws_bytes, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(LFT_ERR_ARG, "null handle");
+  DeviceGuard dg(h->cfg.device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", h->cfg.device);
   int rc = check_ready(h, B, P);
   if (rc) return rc;
   if ((rc = check_stage_size(h, B, P))) return rc;
@@ -182,12 +219,15 @@ int lft_stage_upsample(lft_handle* hh, const float* feat, const float* lr, float
   const long long T = (long long)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
   Workspace w = carve(ws, T, h->cfg.scale);
   if ((rc = launch_layout(h, feat, w.f0, T, 64, 1, (cudaStream_t)stream))) return rc;
-  return run_upsample(h, w.f0, lr, sr, w.pp, B, P, 0, (cudaStream_t)stream);
+  return run_upsample(h, w.f0, lr, sr, w.pp, B, P, UpTarget{}, (cudaStream_t)stream);
 }
 
 int lft_forward(lft_handle* hh, const float* lr, float* sr, int32_t B, int32_t P, void* ws, size_t ws_bytes,
                 void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return fail(LFT_ERR_ARG, "null handle");
+  DeviceGuard dg(h->cfg.device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", h->cfg.device);
   int rc = check_ready(h, B, P);
   if (rc) return rc;
   if (!lr || !sr || !ws) return fail(LFT_ERR_ARG, "null pointer");
@@ -206,7 +246,7 @@ int lft_forward(lft_handle* hh, const float* lr, float* sr, int32_t B, int32_t P
     const int Bc = (int)((B - b0) < chunk ? (B - b0) : chunk);
     const long long T = (long long)Bc * A * A * P * P;
     Workspace w = carve(ws, T, s);
-    if ((rc = run_forward_chunk(h, lr + b0 * lr_stride, sr + b0 * sr_stride, w, Bc, P, 0, (cudaStream_t)stream)))
+    if ((rc = run_forward_chunk(h, lr + b0 * lr_stride, sr + b0 * sr_stride, w, Bc, P, UpTarget{}, (cudaStream_t)stream)))
       return rc;
   }
   return 0;
@@ -235,7 +275,8 @@ int lft_divide_ex(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, in
   if (rc) return rc;
   if (p0 < 0 || p1 > nu * nv || p0 > p1) return fail(LFT_ERR_ARG, "patch range [%d,%d) outside [0,%d)", p0, p1, nu * nv);
   if (p0 == p1) return 0;
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  DeviceGuard dg(h->cfg.device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", h->cfg.device);
   return launch_divide(h, lr_lf, patches, h0, w0, nv, p0, p1 - p0, patch, stride, (cudaStream_t)stream);
 }
 
@@ -253,7 +294,8 @@ int lft_integrate_ex(lft_handle* hh, const float* sr_crops, int32_t h0, int32_t 
   if (rc) return rc;
   if (p0 < 0 || p1 > nu * nv || p0 > p1) return fail(LFT_ERR_ARG, "patch range [%d,%d) outside [0,%d)", p0, p1, nu * nv);
   if (p0 == p1) return 0;
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  DeviceGuard dg(h->cfg.device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", h->cfg.device);
   return launch_integrate(h, sr_crops, sr_lf, h0, w0, nv, p0, p1 - p0, stride, (cudaStream_t)stream);
 }
 
@@ -262,11 +304,14 @@ int lft_integrate(lft_handle* hh, const float* sr_crops, int32_t h0, int32_t w0,
   return lft_integrate_ex(hh, sr_crops, h0, w0, 32, 16, p0, p1, sr_lf, stream);
 }
 
-int lft_forward_lf_ex(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
-                      int32_t p0, int32_t p1, float* sr_crops, void* ws, size_t ws_bytes, void* stream) {
+// LFdivide -> forward -> (crops | crops at their place in sr_lf) for the patch range [p0, p1), chunked to the workspace
+static int forward_lf_impl(lft_handle* hh, const float* lr_lf, int h0, int w0, int patch, int stride, int p0, int p1,
+                           float* dst, bool direct, void* ws, size_t ws_bytes, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h) return fail(LFT_ERR_ARG, "null handle");
-  if (!lr_lf || !sr_crops || !ws) return fail(LFT_ERR_ARG, "bad argument");
+  DeviceGuard dg(h->cfg.device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", h->cfg.device);
+  if (!lr_lf || !dst || !ws) return fail(LFT_ERR_ARG, "bad argument");
   int nu, nv;
   int rc = tiling(h0, w0, patch, stride, &nu, &nv);
   if (rc) return rc;
@@ -278,6 +323,8 @@ int lft_forward_lf_ex(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0
   per -= 1024;
   if (ws_bytes < per + 1024) return fail(LFT_ERR_WORKSPACE, "workspace too small for one patch: %zu < %zu", ws_bytes, per + 1024);
   const int A = h->cfg.ang_res, s = h->cfg.scale;
+  if (direct && (long long)A * h0 * s * A * w0 * s >= (1LL << 31))
+    return fail(LFT_ERR_ARG, "assembled light field too large for 32-bit pixel indices");
   long long chunk = (long long)((ws_bytes - 1024) / per);
   {
     const long long cap = (1LL << 30) / ((long long)A * P * s * A * P * s);
@@ -289,9 +336,69 @@ int lft_forward_lf_ex(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0
     const long long T = (long long)Bc * A * A * P * P;
     Workspace w = carve(ws, T, s);
     if ((rc = launch_divide(h, lr_lf, w.lrp, h0, w0, nv, (int)q0, Bc, P, stride, (cudaStream_t)stream))) return rc;
-    if ((rc = run_forward_chunk(h, w.lrp, sr_crops + (q0 - p0) * crop_stride, w, Bc, P, stride, (cudaStream_t)stream)))
-      return rc;
+    UpTarget up;
+    up.mode = direct ? 2 : 1;
+    up.crop_stride = stride;
+    up.h0 = h0; up.w0 = w0; up.numV = nv; up.p0 = (int)q0;
+    float* out = direct ? dst : dst + (q0 - p0) * crop_stride;
+    if ((rc = run_forward_chunk(h, w.lrp, out, w, Bc, P, up, (cudaStream_t)stream))) return rc;
   }
+  return 0;
+}
+
+int lft_forward_lf_ex(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
+                      int32_t p0, int32_t p1, float* sr_crops, void* ws, size_t ws_bytes, void* stream) {
+  return forward_lf_impl(hh, lr_lf, h0, w0, patch, stride, p0, p1, sr_crops, false, ws, ws_bytes, stream);
+}
+
+int lft_forward_lf_sr(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
+                      int32_t p0, int32_t p1, float* sr_lf, void* ws, size_t ws_bytes, void* stream) {
+  return forward_lf_impl(hh, lr_lf, h0, w0, patch, stride, p0, p1, sr_lf, true, ws, ws_bytes, stream);
+}
+
+// ---- peer-visible device buffers (CUDA IPC): rank 0 allocates the assembled SR light field with lft_peer_alloc, sends the
+// 64-byte handle to the other ranks of the node (any byte transport: torch.distributed broadcast), they map it with
+// lft_peer_open and pass the mapped pointer to lft_forward_lf_sr, whose last kernel then stores the kept crops straight into
+// rank 0's memory over NVLink.
+int lft_peer_alloc(int32_t device, size_t bytes, void** dev_ptr, lft_peer_handle* handle) {
+  if (!dev_ptr || !handle || bytes == 0) return fail(LFT_ERR_ARG, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(lft_peer_handle), "lft_peer_handle too small");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", device);
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(LFT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+  memset(handle, 0, sizeof(*handle));
+  memcpy(handle->bytes, &hd, sizeof(hd));
+  *dev_ptr = p;
+  return 0;
+}
+
+int lft_peer_free(int32_t device, void* dev_ptr) {
+  if (!dev_ptr) return 0;
+  DeviceGuard dg(device);
+  CUDA_TRY(cudaFree(dev_ptr));
+  return 0;
+}
+
+int lft_peer_open(int32_t device, const lft_peer_handle* handle, void** mapped_ptr) {
+  if (!handle || !mapped_ptr) return fail(LFT_ERR_ARG, "bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(LFT_ERR_CUDA, "cannot select device %d", device);
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle->bytes, sizeof(hd));
+  void* p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+  *mapped_ptr = p;
+  return 0;
+}
+
+int lft_peer_close(int32_t device, void* mapped_ptr) {
+  if (!mapped_ptr) return 0;
+  DeviceGuard dg(device);
+  CUDA_TRY(cudaIpcCloseMemHandle(mapped_ptr));
   return 0;
 }
 
@@ -315,7 +422,9 @@ int lft_gemm_selftest(const float* A, const float* W, float* D, float* aux, int3
                       int32_t precision, int32_t variant) {
   if (!A || !W || !D || !aux || M % 128 || K % 64 || N % 16 || N > 256 || N < 16 || K > 256)
     return fail(LFT_ERR_ARG, "bad selftest shape");
-  int rc = configure_kernels();
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  int rc = configure_kernels(dev);
   if (rc) return rc;
   std::vector<uint16_t> p = pack_weight(N, N, K, [=](int n, int k) { return W[(size_t)n * K + k]; });
   float *dA = nullptr, *dD = nullptr, *dX = nullptr;

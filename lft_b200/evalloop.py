@@ -28,7 +28,8 @@ def psnr_per_view(sr_sai: torch.Tensor, hr_sai: torch.Tensor, angRes: int) -> to
 
 def ssim_per_view(sr_sai: torch.Tensor, hr_sai: torch.Tensor, angRes: int, data_range: float = 2.0) -> torch.Tensor:
     """[A, A] SSIM of every view, restating what `metrics.structural_similarity(label, out, gaussian_weights=True)` of
-    utils.py:82-84 computes: Gaussian window sigma 1.5 truncated at 3.5 sigma (11 x 11), population covariances, K1 = 0.01,
+    utils.py:82-84 computes: Gaussian window sigma 1.5 truncated at 3.5 sigma (11 x 11), SAMPLE covariances (the call leaves
+    scikit-image's `use_sample_covariance=True`, so vx, vy and vxy carry the factor NP / (NP - 1) = 121 / 120), K1 = 0.01,
     K2 = 0.03, borders of (11 - 1) / 2 pixels dropped before the mean.  `data_range`: the reference passes none; the
     scikit-image of its era (<= 0.18; README.md:15 names python 3.6 / PyTorch 1.3) then takes the dtype range of float
     images, -1..1, i.e. 2.0 - later versions refuse float images without it.  UNPINNED: scikit-image is not installed in the
@@ -42,30 +43,46 @@ def ssim_per_view(sr_sai: torch.Tensor, hr_sai: torch.Tensor, angRes: int, data_
     y = sr_sai.detach().cpu().double().numpy().reshape(A, H, A, W).transpose(0, 2, 1, 3)
     c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
     pad = 5                                                                                # (win_size - 1) // 2, win_size = 11
+    cov_norm = 121.0 / 120.0                                                               # NP / (NP - 1), NP = win_size ** 2
     out = np.zeros((A, A))
     f = lambda im: gaussian_filter(im, sigma=1.5, truncate=3.5)                            # mode='reflect', scipy's default
     for u in range(A):
         for v in range(A):
             a, b = x[u, v], y[u, v]
             ux, uy = f(a), f(b)
-            vx, vy, vxy = f(a * a) - ux * ux, f(b * b) - uy * uy, f(a * b) - ux * uy
+            vx, vy, vxy = (cov_norm * (f(a * a) - ux * ux), cov_norm * (f(b * b) - uy * uy),
+                           cov_norm * (f(a * b) - ux * uy))
             smap = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))
             out[u, v] = smap[pad:H - pad, pad:W - pad].mean()
     return torch.from_numpy(out)
 
 
+def cal_metrics(angRes: int, label: torch.Tensor, out: torch.Tensor) -> Tuple[float, float]:
+    """utils.py:56-88 for two SAI mosaics: per-view PSNR / SSIM averaged over the views with a NON-ZERO value
+    (`PSNR.sum() / np.sum(PSNR > 0)`, utils.py:85-86)."""
+    import numpy as np
+    ps = psnr_per_view(out, label, angRes).cpu().numpy().astype("float32")
+    ss = ssim_per_view(out, label, angRes).numpy().astype("float32")
+    return float(ps.sum() / max(int((ps > 0).sum()), 1)), float(ss.sum() / max(int((ss > 0).sum()), 1))
+
+
 @torch.no_grad()
 def test(test_loader: Iterable, device, net, angRes: Optional[int] = None, patch_size_for_test: int = 32,
-         stride_for_test: int = 16) -> Tuple[float, List[torch.Tensor]]:
-    """Mirror of test.py:73-111: returns (mean PSNR over the loader, list of SR SAI mosaics on the CPU).
+         stride_for_test: int = 16, outputs: Optional[List[torch.Tensor]] = None) -> Tuple[float, float]:
+    """Mirror of test.py:73-111: returns (psnr_epoch_test, ssim_epoch_test) like the reference; the SR SAI mosaics are
+    appended (on the CPU) to `outputs` if a list is passed.
     patch_size_for_test / stride_for_test are the reference's `args` of the same names (option.py:16-17; test.py:83,96)."""
     A = angRes if angRes is not None else net.angRes
     sr = LightFieldSR(net, patch=patch_size_for_test, stride=stride_for_test)
-    psnrs, outs = [], []
+    psnrs, ssims = [], []
     for Lr_SAI_y, Hr_SAI_y in test_loader:
         lr = Lr_SAI_y.squeeze().to(device, torch.float32).contiguous()   # test.py:77
         Sr_SAI_y = sr(lr)                                                 # test.py:83-101
-        outs.append(Sr_SAI_y.cpu())
+        if outputs is not None:
+            outputs.append(Sr_SAI_y.cpu())
         if Hr_SAI_y is not None:
-            psnrs.append(float(psnr_per_view(Sr_SAI_y, Hr_SAI_y.squeeze(), A).mean()))
-    return (sum(psnrs) / len(psnrs) if psnrs else float("nan")), outs
+            p, q = cal_metrics(A, Hr_SAI_y.squeeze(), Sr_SAI_y.cpu())    # test.py:103
+            psnrs.append(p)
+            ssims.append(q)
+    nan = float("nan")
+    return (sum(psnrs) / len(psnrs) if psnrs else nan), (sum(ssims) / len(ssims) if ssims else nan)

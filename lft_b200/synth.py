@@ -63,10 +63,15 @@ def _uniform(tag: str, seed: int, n: int) -> np.ndarray:
 
 
 def synth_state_dict_np(angRes: int = 5, scale: int = 4, seed: int = 0, channels: int = 64,
-                        gain: float = 1.0) -> "OrderedDict[str, np.ndarray]":
+                        gain: float = 1.0, qk_gain: float = 1.0, ln_wide: bool = False) -> "OrderedDict[str, np.ndarray]":
     """Weights ~ U(-b, b), b = gain/sqrt(fan_in) (torch's default conv/linear bound, and the
     kaiming_uniform_(a=sqrt(5)) the reference applies to in_proj_weight, LFT.py:132,204);
-    LayerNorm gamma = 1 + 0.2(u-0.5), beta = 0.2(u-0.5) so the affine path is exercised."""
+    LayerNorm gamma = 1 + 0.2(u-0.5), beta = 0.2(u-0.5) so the affine path is exercised.
+
+    `qk_gain` multiplies the Wq and Wk rows (the first 2E rows of every `attention.in_proj_weight`, LFT.py:131,203) only:
+    logits grow with qk_gain^2 while every other activation keeps its range, which is how a trained network's peaky
+    soft-max is imitated (a global `gain` explodes through the four blocks instead).  `ln_wide` draws the LayerNorm gammas
+    from [0.2, 3] and the betas from [-0.5, 0.5]."""
     sd = OrderedDict()
     for key, shape, fan_in, kind in state_dict_spec(angRes, scale, channels):
         n = int(np.prod(shape))
@@ -74,18 +79,22 @@ def synth_state_dict_np(angRes: int = 5, scale: int = 4, seed: int = 0, channels
         if kind == "w":
             b = gain / np.sqrt(fan_in)
             v = (2.0 * u - 1.0) * b
+            if qk_gain != 1.0 and key.endswith("attention.in_proj_weight"):
+                v = v.reshape(shape)
+                v[: 2 * shape[1]] *= qk_gain
         elif kind == "g":
-            v = 1.0 + 0.2 * (u - 0.5)
+            v = (0.2 + 2.8 * u) if ln_wide else 1.0 + 0.2 * (u - 0.5)
         else:
-            v = 0.2 * (u - 0.5)
+            v = (u - 0.5) if ln_wide else 0.2 * (u - 0.5)
         sd[key] = v.astype(np.float32).reshape(shape)
     return sd
 
 
-def synth_state_dict(angRes: int = 5, scale: int = 4, seed: int = 0, channels: int = 64, gain: float = 1.0):
+def synth_state_dict(angRes: int = 5, scale: int = 4, seed: int = 0, channels: int = 64, gain: float = 1.0,
+                     qk_gain: float = 1.0, ln_wide: bool = False):
     import torch
     return OrderedDict((k, torch.from_numpy(v.copy())) for k, v in
-                       synth_state_dict_np(angRes, scale, seed, channels, gain).items())
+                       synth_state_dict_np(angRes, scale, seed, channels, gain, qk_gain, ln_wide).items())
 
 
 def save_checkpoint(path: str, state_dict, epoch: int = 50, module_prefix: bool = False) -> None:

@@ -39,10 +39,10 @@ def import_reference():
     return ref_model, ref_utils
 
 
-def run_case(ref_model, name, A, s, h, B, seed, want_stages):
+def run_case(ref_model, name, A, s, h, B, seed, want_stages, qk_gain=1.0, ln_wide=False):
     args = types.SimpleNamespace(channels=64, angRes=A, scale_factor=s)
     net = ref_model.get_model(args)
-    sd = synth.synth_state_dict(A, s, seed)
+    sd = synth.synth_state_dict(A, s, seed, qk_gain=qk_gain, ln_wide=ln_wide)
     net.load_state_dict(sd, strict=True)
     net.eval()
     lr = torch.from_numpy(synth.synth_lr_mosaic(B, A, h, h, seed))
@@ -68,7 +68,8 @@ def run_case(ref_model, name, A, s, h, B, seed, want_stages):
     if want_stages:
         stages["conv_init"] = cl((first["conv_init_out"] + first["conv_init_in"]).detach())  # LFT.py:66
     path = os.path.join(HERE, f"{name}.npz")
-    np.savez(path, out=out.numpy(), meta=np.array([A, s, h, B, seed]), **stages)
+    meta = [A, s, h, B, seed] + ([int(qk_gain), int(ln_wide)] if (qk_gain != 1.0 or ln_wide) else [])
+    np.savez(path, out=out.numpy(), meta=np.array(meta), **stages)
     print(name, "out", tuple(out.shape), "absmax", float(out.abs().max()), "->", os.path.getsize(path) // 1024, "KiB")
 
 
@@ -122,9 +123,63 @@ def run_tiler_ps(ref_utils, name, A, h0, w0, s, seed, patch, stride):
     print(name, "numU,numV", numU, numV)
 
 
+# BASELINE configs 3 / 4 end to end through the reference's own test loop (test.py:83-101: LFdivide -> one net() call per
+# patch -> LFintegrate -> SAI mosaic): the full 4x SR light field is 26 / 27 MB, so every 7th pixel of every 7th row is
+# committed (7 is coprime to the 64-pixel crop pitch, the 128-pixel patch pitch and the view size: all patches, crop
+# borders and views are sampled).
+LF_CASES = [  # name, A, h0, w0, s, weight seed, light-field seed, qk_gain
+    ("lf_A5_128x128_s4", 5, 128, 128, 4, 0, 2, 1.0),
+    ("lf_A5_108x156_s4", 5, 108, 156, 4, 0, 3, 1.0),
+]
+LF_SUB = 7
+
+
+def run_lf(ref_model, ref_utils, name, A, h0, w0, s, wseed, seed, qk_gain):
+    import time
+    args = types.SimpleNamespace(channels=64, angRes=A, scale_factor=s)
+    net = ref_model.get_model(args)
+    net.load_state_dict(synth.synth_state_dict(A, s, wseed, qk_gain=qk_gain), strict=True)
+    net.eval()
+    lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, seed))
+    t0 = time.time()
+    sub = ref_utils.LFdivide(lf, A, 32, 16)
+    numU, numV = sub.shape[:2]
+    out = torch.zeros(numU, numV, A * 32 * s, A * 32 * s)
+    with torch.no_grad():
+        for u in range(numU):
+            for v in range(numV):
+                out[u, v] = net(sub[u:u + 1, v:v + 1]).squeeze()          # test.py:88-95, B = 1 per call
+    sr = ref_utils.LFintegrate(out, A, 32 * s, 16 * s, h0 * s, w0 * s)
+    sai = sr.permute(0, 2, 1, 3).reshape(A * h0 * s, A * w0 * s)          # test.py:100
+    np.savez(os.path.join(HERE, f"{name}.npz"), meta=np.array([A, h0, w0, s, wseed, seed, int(qk_gain), LF_SUB, numU, numV]),
+             sub=sai[::LF_SUB, ::LF_SUB].contiguous().numpy(),
+             sha256=np.frombuffer(hashlib.sha256(sai.numpy().tobytes()).digest(), dtype=np.uint8))
+    print(name, tuple(sai.shape), "patches", numU * numV, f"{time.time() - t0:.0f} s")
+
+
+# Sharpened attention (VERDICT r1 "weak" item 1): the default synthetic weights leave every soft-max near uniform (max
+# probability 0.08).  qk_gain = 4 / 6 scales Wq and Wk only: max |logit| 22 / 50, max probability > 0.99, mean row
+# maximum 0.37 / 0.6 in all eight attention calls; ln_wide draws LayerNorm gamma from [0.2, 3].
+SHARP_CASES = [  # name, A, s, h, B, seed, stages, qk_gain, ln_wide
+    ("fwd_sharp4_A5_s4_h8_B1", 5, 4, 8, 1, 13, True, 4.0, False),
+    ("fwd_sharp6_A5_s4_h8_B1", 5, 4, 8, 1, 14, True, 6.0, False),
+    ("fwd_sharp4_lnwide_A5_s2_h8_B1", 5, 2, 8, 1, 15, True, 4.0, True),
+    ("fwd_sharp4_A3_s2_h12_B1", 3, 2, 12, 1, 16, False, 4.0, False),
+    ("fwd_sharp4_A5_s4_h32_B1", 5, 4, 32, 1, 17, False, 4.0, False),
+]
+
+
 def main():
     torch.manual_seed(0)
     ref_model, ref_utils = import_reference()
+    if "--lf-only" in sys.argv[1:]:         # the two full light fields (about 10 minutes of CPU time)
+        for c in LF_CASES:
+            run_lf(ref_model, ref_utils, *c)
+        return
+    if "--sharp-only" in sys.argv[1:]:      # add the sharpened-attention goldens without regenerating the others
+        for c in SHARP_CASES:
+            run_case(ref_model, *c)
+        return
     if "--tiler-ps-only" in sys.argv[1:]:   # add the patch/stride goldens without regenerating the others
         for c in TILER_PS_CASES:
             run_tiler_ps(ref_utils, *c)
@@ -135,6 +190,10 @@ def main():
     run_case(ref_model, "fwd_A3_s2_h12_B1", 3, 2, 12, 1, 12, False)
     run_case(ref_model, "fwd_A5_s2_h32_B1", 5, 2, 32, 1, 1, False)
     run_case(ref_model, "fwd_A5_s4_h32_B1", 5, 4, 32, 1, 0, False)
+    for c in SHARP_CASES:
+        run_case(ref_model, *c)
+    for c in LF_CASES:
+        run_lf(ref_model, ref_utils, *c)
     run_tiler(ref_utils, "tiler_A3_40x56_s2", 3, 40, 56, 2, 5, True)
     run_tiler(ref_utils, "tiler_A5_108x156_s4", 5, 108, 156, 4, 3, False)
     run_tiler(ref_utils, "tiler_A5_128x128_s4", 5, 128, 128, 4, 2, False)

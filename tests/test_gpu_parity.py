@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import load_case
 from lft_b200 import capi, synth
 from oracle import lft_oracle as O
 
@@ -25,11 +26,7 @@ def _engine(A, s, sd, prec="fp32"):
 
 
 def _case(golden_dir, name):
-    g = np.load(os.path.join(golden_dir, name + ".npz"))
-    A, s, h, B, seed = (int(x) for x in g["meta"])
-    sd = synth.synth_state_dict(A, s, seed)
-    lr = torch.from_numpy(synth.synth_lr_mosaic(B, A, h, h, seed))
-    return g, A, s, sd, lr
+    return load_case(golden_dir, name)
 
 
 def test_tcgen05_gemm_selftest():
@@ -51,9 +48,16 @@ def test_tcgen05_gemm_selftest():
             assert np.array_equal(D2, D)
 
 
+SHARP = ["fwd_sharp4_A5_s4_h8_B1", "fwd_sharp6_A5_s4_h8_B1", "fwd_sharp4_lnwide_A5_s2_h8_B1", "fwd_sharp4_A3_s2_h12_B1",
+         "fwd_sharp4_A5_s4_h32_B1"]
+
+
 @pytest.mark.parametrize("name", ["fwd_A5_s4_h8_B1", "fwd_A5_s2_h8_B2", "fwd_A3_s2_h12_B1", "fwd_A5_s2_h32_B1",
-                                  "fwd_A5_s4_h32_B1"])
+                                  "fwd_A5_s4_h32_B1"] + SHARP)
 def test_forward_vs_reference_golden(golden_dir, name):
+    """The `fwd_sharp*` cases run peaky soft-maxes (Wq, Wk x 4 / x 6: |logit| up to 22 / 50, max probability > 0.99, wide
+    LayerNorm gammas) - the regime of a trained network - through the ex2.approx soft-max, the online rescale chains and the
+    hi/lo operand split; same 1e-4 gate."""
     g, A, s, sd, lr = _case(golden_dir, name)
     eng = _engine(A, s, sd)
     out = eng.forward(lr.cuda()).cpu().numpy()
@@ -83,6 +87,26 @@ def test_stages_vs_reference_golden_and_oracle(golden_dir):
         assert (z - st[f"spa{i}"]).abs().max() <= TOL_STAGE
     up = eng.stage_upsample((st["spa3"] + st["conv_init"]).cuda(), lrd).cpu()
     assert (up - ref).abs().max() <= TOL_STAGE
+
+
+@pytest.mark.parametrize("name", ["fwd_sharp4_A5_s4_h8_B1", "fwd_sharp6_A5_s4_h8_B1", "fwd_sharp4_lnwide_A5_s2_h8_B1"])
+def test_stages_sharp_softmax_vs_reference_golden(golden_dir, name):
+    """Stage goldens of the reference with peaky soft-maxes: every AngTrans / SpaTrans stage is fed the oracle's input of
+    that stage and compared with the reference's hook capture (layers 0 and 3) or the oracle (layers 1, 2)."""
+    g, A, s, sd, lr = _case(golden_dir, name)
+    st = {}
+    O.forward(sd, lr, A, s, stages=st)
+    eng = _engine(A, s, sd)
+    x = eng.stage_conv_init(lr.cuda()).cpu()
+    assert (x - torch.from_numpy(g["conv_init"])).abs().max() <= TOL_STAGE
+    for i in range(4):
+        xin = st["conv_init"] if i == 0 else st[f"spa{i-1}"]
+        want_a = torch.from_numpy(g[f"ang{i}"]) if f"ang{i}" in g.files else st[f"ang{i}"]
+        want_s = torch.from_numpy(g[f"spa{i}"]) if f"spa{i}" in g.files else st[f"spa{i}"]
+        y = eng.stage_ang(i, xin.cuda()).cpu()
+        assert (y - want_a).abs().max() <= TOL_STAGE, f"ang{i}"
+        z = eng.stage_spa(i, st[f"ang{i}"].cuda()).cpu()
+        assert (z - want_s).abs().max() <= TOL_STAGE, f"spa{i}"
 
 
 def test_angres9_81_tokens_vs_oracle():
@@ -121,18 +145,39 @@ def _psnr(a, b):
     return 10.0 * np.log10(1.0 / max(float(((a - b) ** 2).mean()), 1e-20))
 
 
-def test_bf16_path_psnr_gate(golden_dir):
-    """bf16 path: |PSNR(ref,HR) - PSNR(new,HR)| <= 0.01 dB. HR stand-in: a smooth target
-    close to the reference output (reference + noise at ~32 dB, the paper's 4x operating point)."""
-    g, A, s, sd, lr = _case(golden_dir, "fwd_A5_s4_h32_B1")
-    eng = _engine(A, s, sd, "bf16")
-    out = eng.forward(lr.cuda()).cpu().numpy()
-    ref = g["out"]
-    rng = np.random.default_rng(0)
-    hr = ref + rng.standard_normal(ref.shape).astype(np.float32) * 0.025
-    assert abs(_psnr(ref, hr) - _psnr(out, hr)) <= 0.01
-    assert _psnr(out, ref) > 55.0
-    assert np.abs(out - ref).max() < 2e-2
+def _hr_and_bicubic_lr(A, h, s, seed):
+    """a smooth synthetic HR light field and its bicubic x(1/s) down-sampling (per view, anti-aliased, as
+    the reference's MATLAB data preparation does) -> (hr mosaic [A*h*s, A*h*s], lr mosaic [1,1,A*h,A*h])."""
+    hr = torch.from_numpy(synth.synth_light_field(A, h * s, h * s, seed))
+    v = hr.view(A, h * s, A, h * s).permute(0, 2, 1, 3).reshape(A * A, 1, h * s, h * s)
+    lo = torch.nn.functional.interpolate(v, scale_factor=1.0 / s, mode="bicubic", antialias=True, align_corners=False)
+    lr = lo.view(A, A, h, h).permute(0, 2, 1, 3).reshape(1, 1, A * h, A * h).contiguous()
+    return hr, lr
+
+
+def _psnr_views(x, hr, A):
+    """utils.py:79,85: PSNR per view (data range 1), mean over the views."""
+    H = hr.shape[0] // A
+    d = (np.asarray(x, np.float64).reshape(A, H, A, H) - np.asarray(hr, np.float64).reshape(A, H, A, H)) ** 2
+    return float(np.mean(10.0 * np.log10(1.0 / d.mean(axis=(1, 3)))))
+
+
+@pytest.mark.parametrize("s,qk", [(4, 1.0), (2, 1.0), (4, 4.0)])
+def test_bf16_path_psnr_gate(s, qk):
+    """bf16 path (north_star): |PSNR(ref, HR) - PSNR(new, HR)| <= 0.01 dB with HR = a synthetic light field and LR = its
+    bicubic down-sampling, PSNR per view averaged as utils.py:79,85.  With untrained weights both
+    outputs are far from HR, which makes the delta insensitive; the assertions with teeth are PSNR(new, ref) and the
+    max-abs bound against the fp32 oracle."""
+    A, h = 5, 32
+    sd = synth.synth_state_dict(A, s, 3, qk_gain=qk)
+    hr, lr = _hr_and_bicubic_lr(A, h, s, 31)
+    ref = O.forward(sd, lr, A, s)[0, 0].numpy()
+    fp32 = _engine(A, s, sd).forward(lr.cuda())[0, 0].cpu().numpy()
+    assert np.abs(fp32 - ref).max() <= TOL_FP32
+    out = _engine(A, s, sd, "bf16").forward(lr.cuda())[0, 0].cpu().numpy()
+    assert abs(_psnr_views(ref, hr.numpy(), A) - _psnr_views(out, hr.numpy(), A)) <= 0.01
+    assert _psnr(out, ref) > (55.0 if qk == 1.0 else 45.0)
+    assert np.abs(out - ref).max() < (2e-2 if qk == 1.0 else 6e-2)
 
 
 def test_dropin_module_loads_checkpoint_and_matches(golden_dir, tmp_path):
@@ -264,6 +309,72 @@ def test_full_light_field_vs_oracle_test_loop():
     assert torch.equal(crops, eng.forward_lf_crops(lf.cuda(), 0, 12))
 
 
+def _oracle_light_field_on_gpu(sd, lf, A, s, batch=16):
+    """O.infer_light_field with the per-patch forwards evaluated by the oracle's torch ops on the GPU in true fp32 (TF32
+    off for cuDNN and cuBLAS): the CPU oracle needs ~2 s per patch, a full light field has 64 / 70 of them."""
+    flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        h0, w0 = lf.shape[0] // A, lf.shape[1] // A
+        sub = O.lf_divide(lf, A, 32, 16)
+        nu, nv = sub.shape[:2]
+        flat = sub.view(nu * nv, 1, A * 32, A * 32)
+        out = torch.empty(nu * nv, A * 32 * s, A * 32 * s)
+        with torch.no_grad():
+            for i in range(0, nu * nv, batch):
+                out[i:i + batch] = O.forward(sd, flat[i:i + batch].cuda(), A, s)[:, 0].cpu()
+        sr = O.lf_integrate(out.view(nu, nv, A * 32 * s, A * 32 * s), A, 32 * s, 16 * s, h0 * s, w0 * s)
+        return sr.permute(0, 2, 1, 3).reshape(A * h0 * s, A * w0 * s), flat, out
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = flags
+
+
+@pytest.mark.parametrize("name", ["lf_A5_128x128_s4", "lf_A5_108x156_s4"])
+def test_full_baseline_light_fields_vs_reference_and_oracle(golden_dir, name):
+    """BASELINE configs 3 / 4 at full size: the HCInew-shape (64 patches) and the ragged EPFL-shape (70 patches) 4x light
+    field through LightFieldSR against (a) the reference's own test loop - every 7th pixel of the assembled SR light
+    field, committed by tests/golden/make_golden.py - (b) the oracle's test loop evaluated on the GPU in true fp32 for
+    every pixel, and (c) the CPU oracle for three of the patches."""
+    from lft_b200.lightfield import LightFieldSR
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    A, h0, w0, s, wseed, seed, qk, sub, nu, nv = (int(x) for x in g["meta"])
+    sd = synth.synth_state_dict(A, s, wseed, qk_gain=float(qk))
+    lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, seed))
+    eng = _engine(A, s, sd)
+    assert eng.num_patches(h0, w0) == (nu, nv)
+    got = LightFieldSR(eng)(lf.cuda()).cpu()
+    assert got.shape == (A * h0 * s, A * w0 * s) and torch.isfinite(got).all()
+    err_ref = np.abs(got[::sub, ::sub].numpy() - g["sub"]).max()
+    assert err_ref <= TOL_FP32, err_ref
+    want, flat, out = _oracle_light_field_on_gpu(sd, lf, A, s)
+    assert (got - want).abs().max() <= TOL_FP32
+    pick = [0, nv + 3, nu * nv - 1]                       # corner, interior, last (ragged for the EPFL shape)
+    cpu = O.forward(sd, flat[pick], A, s)[:, 0]
+    assert (cpu - out[pick]).abs().max() <= 2e-5          # the GPU-evaluated oracle is the oracle
+    mine = eng.forward(flat[pick].cuda())[:, 0].cpu()
+    assert (mine - cpu).abs().max() <= TOL_FP32
+
+
+def test_multi_gpu_sharded_light_field_bit_identical():
+    """All visible GPUs (skipped with fewer than two): one HCInew-shape and one ragged EPFL-shape light field sharded
+    patch-wise over the ranks (torchrun, NCCL), crops gathered to rank 0 - by the NCCL gather and by the direct peer
+    stores - must equal the single-GPU result bit for bit (tests/dist_lf_worker.py)."""
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = min(n, 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29500 + os.getpid() % 2000
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tests", "dist_lf_worker.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_LF_OK" in r.stdout, r.stdout[-3000:]
+
+
 def test_config2_2x_batch64_fp32_and_bf16():
     """BASELINE config 2: 5x5 2x, batch of 64 LR patches 32x32/view: oracle on a sample of the batch (fp32 gate),
     bf16 PSNR gate on the same sample, every patch equal to its own B=1 forward."""
@@ -279,10 +390,8 @@ def test_config2_2x_batch64_fp32_and_bf16():
     eng.set_precision("bf16")
     outb = eng.forward(lr[pick].cuda()).cpu().numpy()
     refn = ref.numpy()
-    rng = np.random.default_rng(1)
-    hr = refn + rng.standard_normal(refn.shape).astype(np.float32) * 0.012   # ~38 dB, the 2x operating point
-    assert abs(_psnr(refn, hr) - _psnr(outb, hr)) <= 0.01
-    assert _psnr(outb, refn) > 55.0
+    assert _psnr(outb, refn) > 55.0                     # the PSNR-delta gate proper: test_bf16_path_psnr_gate
+    assert np.abs(outb - refn).max() < 2e-2
 
 
 def test_config5_angres9_batch_chunked():
@@ -302,7 +411,7 @@ def test_config5_angres9_batch_chunked():
 
 def test_eval_loop_dropin(tmp_path):
     """test.py-compatible loop: same SR and same mean PSNR as the oracle's per-patch loop."""
-    from lft_b200.evalloop import test as run_test, psnr_per_view
+    from lft_b200.evalloop import test as run_test, psnr_per_view, ssim_per_view
     from lft_b200.model import get_model
     A, s, h0, w0 = 5, 2, 32, 40
     sd = synth.synth_state_dict(A, s, 8)
@@ -312,11 +421,13 @@ def test_eval_loop_dropin(tmp_path):
     lr = torch.from_numpy(synth.synth_light_field(A, h0, w0, 8))
     hr = torch.from_numpy(synth.synth_light_field(A, h0 * s, w0 * s, 9))
     loader = [(lr[None], hr[None])]
-    mean_psnr, outs = run_test(loader, torch.device("cuda"), net)
+    outs = []
+    mean_psnr, mean_ssim = run_test(loader, torch.device("cuda"), net, outputs=outs)   # (psnr, ssim) like test.py:111
     want, _ = O.infer_light_field(sd, lr, A, s, mode="window", batch=4)
     assert (outs[0] - want).abs().max() <= TOL_FP32
     ref_psnr = float(psnr_per_view(want, hr, A).mean())
     assert abs(mean_psnr - ref_psnr) <= 1e-3
+    assert abs(mean_ssim - float(ssim_per_view(want, hr, A).mean())) <= 1e-4
 
 
 def test_profile_and_launch_count():
@@ -404,3 +515,99 @@ def test_cuda_graph_replay_bit_identical():
     n0 = eng.launch_count()
     eng.forward_graphed(lr)
     assert eng.launch_count() == n0          # replay: no launches issued by the library itself
+
+
+def test_direct_assembly_equals_crops_plus_integrate():
+    """lft_forward_lf_sr (LFintegrate fused into the last kernel, the default of LightFieldSR) writes exactly what
+    lft_forward_lf_ex + lft_integrate_ex write - ragged tilings and non-default patch / stride included - touches every
+    pixel of the SR light field (NaN pre-fill) and, for a patch sub-range, only that range's pixels."""
+    from lft_b200.lightfield import LightFieldSR
+    for (A, s, h0, w0, patch, stride) in [(5, 2, 40, 56, 32, 16), (5, 4, 44, 60, 16, 8), (3, 4, 40, 56, 32, 21),
+                                          (3, 2, 40, 56, 32, 32), (5, 4, 108, 156, 32, 16)]:
+        eng = _engine(A, s, synth.synth_state_dict(A, s, 6))
+        lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, 6)).cuda()
+        want = LightFieldSR(eng, patch=patch, stride=stride, assemble="collective")(lf)
+        got = LightFieldSR(eng, patch=patch, stride=stride)(lf)
+        assert torch.equal(got, want), (A, s, h0, w0, patch, stride)
+        nu, nv = eng.num_patches(h0, w0, patch, stride)
+        sr = torch.full_like(want, float("nan"))
+        eng.forward_lf_sr(lf, 0, nu * nv, sr, patch=patch, stride=stride)
+        assert torch.equal(sr, want)
+        half = (nu * nv) // 2
+        sr = torch.full_like(want, float("nan"))
+        eng.forward_lf_sr(lf, half, nu * nv, sr, patch=patch, stride=stride)
+        part = torch.full_like(want, float("nan"))
+        crops = eng.forward_lf_crops(lf, half, nu * nv, patch=patch, stride=stride)
+        eng.integrate(crops, h0, w0, half, nu * nv, part, patch, stride)
+        assert torch.equal(torch.isnan(sr), torch.isnan(part))
+        assert torch.equal(torch.nan_to_num(sr), torch.nan_to_num(part))
+
+
+def test_weight_reload_and_patch_size_switch_do_not_leak():
+    """50 reloads of the weights and 50 alternations between two patch sizes leave the free device memory where it was
+    (superseded slabs and tables are freed; the per-patch-size position tables are cached per weight generation)."""
+    A, s = 5, 2
+    sds = [synth.synth_state_dict(A, s, 40), synth.synth_state_dict(A, s, 41)]
+    eng = _engine(A, s, sds[0])
+    lr16 = torch.from_numpy(synth.synth_lr_mosaic(1, A, 16, 16, 1)).cuda()
+    lr32 = torch.from_numpy(synth.synth_lr_mosaic(1, A, 32, 32, 1)).cuda()
+    want = {}
+    for i in (0, 1):
+        eng.load_state_dict(sds[i])
+        want[i] = (eng.forward(lr16).clone(), eng.forward(lr32).clone())
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for it in range(50):
+        eng.load_state_dict(sds[it & 1])
+        assert torch.equal(eng.forward(lr16), want[it & 1][0])
+        assert torch.equal(eng.forward(lr32), want[it & 1][1])
+    for it in range(50):
+        assert torch.equal(eng.forward(lr16 if it & 1 else lr32), want[1][0 if it & 1 else 1])
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (8 << 20), f"device memory shrank by {(free0 - free1) >> 20} MiB over 50 reloads"
+
+
+def test_graph_replay_survives_workspace_growth_and_reload():
+    """a captured graph owns its workspace (a later, larger call replaces the engine's shared one) and is dropped
+    when the weights or the precision change (a replay would run on freed slabs / the old pass count)."""
+    A, s = 5, 2
+    sd0, sd1 = synth.synth_state_dict(A, s, 50), synth.synth_state_dict(A, s, 51)
+    eng = _engine(A, s, sd0)
+    lr = torch.from_numpy(synth.synth_lr_mosaic(1, A, 16, 16, 2)).cuda()
+    want0 = eng.forward(lr).clone()
+    assert torch.equal(eng.forward_graphed(lr), want0)
+    big = torch.from_numpy(synth.synth_lr_mosaic(6, A, 32, 32, 3)).cuda()
+    eng.forward(big)                                     # grows (replaces) the shared workspace
+    junk = torch.full((64 << 20,), float("nan"), device="cuda")   # re-use whatever the allocator just released
+    assert torch.equal(eng.forward_graphed(lr), want0)
+    del junk
+    eng.load_state_dict(sd1)
+    want1 = eng.forward(lr).clone()
+    assert not torch.equal(want1, want0)
+    assert torch.equal(eng.forward_graphed(lr), want1)   # re-captured with the new weights
+    eng.set_precision("bf16")
+    wantb = eng.forward(lr).clone()
+    assert torch.equal(eng.forward_graphed(lr), wantb)
+
+
+def test_second_device_and_current_device_untouched():
+    """kernels are configured per device (an engine on cuda:1 needs its own opt-in to > 48 KB of shared memory),
+    API calls do not change the caller's current device, and the engine launches on ITS device's current stream."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    A, s = 5, 2
+    sd = synth.synth_state_dict(A, s, 60)
+    lr = torch.from_numpy(synth.synth_lr_mosaic(2, A, 16, 16, 4))
+    torch.cuda.set_device(0)
+    e0 = _engine(A, s, sd)
+    from lft_b200.engine import Engine
+    e1 = Engine(A, s, device=1)
+    e1.load_state_dict(sd)
+    assert torch.cuda.current_device() == 0
+    out0 = e0.forward(lr.cuda(0))
+    out1 = e1.forward(lr.cuda(1))
+    assert torch.cuda.current_device() == 0
+    torch.cuda.synchronize(0)
+    torch.cuda.synchronize(1)
+    assert torch.equal(out0.cpu(), out1.cpu())

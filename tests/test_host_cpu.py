@@ -105,7 +105,8 @@ def test_c_tiling_counts_match_reference_formula():
             for h0, w0 in ((patch - 2 * bdr, 3 * patch + 1), (bdr, 57), (19, 19), (40, 56), (108, 156), (5, 128)):
                 want = LF.num_patches(h0, w0, patch, stride)
                 rc = lib.lft_lf_num_patches_ex(h0, w0, patch, stride, C.byref(nu), C.byref(nv))
-                if h0 < max(bdr, 1) or w0 < max(bdr, 1) or min(want) < 1:
+                uncovered = want[0] * stride < h0 or want[1] * stride < w0   # the reference's LFintegrate fails (utils.py:155)
+                if h0 < max(bdr, 1) or w0 < max(bdr, 1) or min(want) < 1 or uncovered:
                     assert rc == -1, (h0, w0, patch, stride)
                     continue
                 assert rc == 0, (h0, w0, patch, stride, lib.lft_last_error())
@@ -119,6 +120,19 @@ def test_c_tiling_counts_match_reference_formula():
     assert lib.lft_lf_num_patches(108, 156, C.byref(nu), C.byref(nv)) == 0 and (nu.value, nv.value) == (7, 10)
     for bad in ((64, 64, 33, 16), (64, 64, 3, 1), (64, 64, 32, 0), (64, 64, 16, 17), (3, 64, 32, 16)):
         assert lib.lft_lf_num_patches_ex(*bad, C.byref(nu), C.byref(nv)) == -1, bad
+
+
+def test_tiling_rejects_uncovered_last_row():
+    """an odd (patch - stride) can leave numU*stride == h0 - 1 (patch 32, stride 21, h0 43): the reference's
+    LFintegrate raises a shape mismatch there (utils.py:155); the C side must refuse instead of leaving the last SR rows
+    unwritten.  Neighbouring sizes that do cover the view are accepted."""
+    lib = capi.load()
+    nu, nv = C.c_int32(), C.c_int32()
+    assert lib.lft_lf_num_patches_ex(43, 43, 32, 21, C.byref(nu), C.byref(nv)) == -1
+    assert b"LFintegrate" in lib.lft_last_error()
+    assert lib.lft_lf_num_patches_ex(43, 64, 32, 21, C.byref(nu), C.byref(nv)) == -1
+    assert lib.lft_lf_num_patches_ex(42, 40, 32, 21, C.byref(nu), C.byref(nv)) == 0 and (nu.value, nv.value) == (2, 2)
+    assert lib.lft_lf_num_patches_ex(44, 44, 32, 21, C.byref(nu), C.byref(nv)) == 0 and nu.value * 21 >= 44
 
 
 def _gloo_worker(rank, world, port, q):
@@ -188,7 +202,8 @@ def test_psnr_per_view_matches_reference_definition():
 
 def test_ssim_per_view_against_direct_convolution():
     """ssim_per_view (scipy separable filter) against an independent direct 11 x 11 evaluation of the same definition
-    (Gaussian sigma 1.5, reflect borders, population covariances, data range 2) on the interior pixels."""
+    (Gaussian sigma 1.5, reflect borders, sample covariances = x 121 / 120 as scikit-image's default, data range 2) on the
+    interior pixels."""
     from lft_b200.evalloop import ssim_per_view
     A, H, W = 2, 24, 30
     g = torch.Generator().manual_seed(4)
@@ -208,8 +223,9 @@ def test_ssim_per_view_against_direct_convolution():
                 for x in range(5, W - 5):
                     wa, wb = a[y - 5:y + 6, x - 5:x + 6], b[y - 5:y + 6, x - 5:x + 6]
                     ua, ub = (k2 * wa).sum(), (k2 * wb).sum()
-                    va, vb = (k2 * wa * wa).sum() - ua * ua, (k2 * wb * wb).sum() - ub * ub
-                    vab = (k2 * wa * wb).sum() - ua * ub
+                    n = 121.0 / 120.0
+                    va, vb = n * ((k2 * wa * wa).sum() - ua * ua), n * ((k2 * wb * wb).sum() - ub * ub)
+                    vab = n * ((k2 * wa * wb).sum() - ua * ub)
                     vals.append((2 * ua * ub + c1) * (2 * vab + c2) / ((ua * ua + ub * ub + c1) * (va + vb + c2)))
             assert abs(got[u, v] - np.mean(vals)) < 1e-9
     same = ssim_per_view(hr, hr, A)

@@ -10,16 +10,17 @@ import torch
 from lft_b200 import synth
 from oracle import lft_oracle as O
 
-FWD_CASES = ["fwd_A5_s4_h8_B1", "fwd_A5_s2_h8_B2", "fwd_A3_s2_h12_B1", "fwd_A5_s2_h32_B1"]
+from conftest import load_case
+
+FWD_CASES = ["fwd_A5_s4_h8_B1", "fwd_A5_s2_h8_B2", "fwd_A3_s2_h12_B1", "fwd_A5_s2_h32_B1",
+             # sharpened soft-max (Wq, Wk x 4 / x 6: |logit| up to 22 / 50, max probability > 0.99), wide LayerNorm gammas
+             "fwd_sharp4_A5_s4_h8_B1", "fwd_sharp6_A5_s4_h8_B1", "fwd_sharp4_lnwide_A5_s2_h8_B1", "fwd_sharp4_A3_s2_h12_B1",
+             "fwd_sharp4_A5_s4_h32_B1"]
 TOL = 2e-5  # fp32 op-order noise between the restatement and the reference modules
 
 
 def _load(golden_dir, name):
-    g = np.load(os.path.join(golden_dir, name + ".npz"))
-    A, s, h, B, seed = (int(x) for x in g["meta"])
-    sd = synth.synth_state_dict(A, s, seed)
-    lr = torch.from_numpy(synth.synth_lr_mosaic(B, A, h, h, seed))
-    return g, A, s, sd, lr
+    return load_case(golden_dir, name)
 
 
 @pytest.mark.parametrize("name", FWD_CASES)
