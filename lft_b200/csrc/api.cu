@@ -179,21 +179,24 @@ static int finalize(Handle* h) {
   };
   // LayerNorm folded into the following linear layer: LN(z) W^T = rstd (z W'^T - mean u) + c with
   // W' = W diag(gamma), u = W' 1 (summed over the bf16 hi+lo values the MMA really uses), c = W beta.
+  // u[0] sums hi + lo (what three passes multiply by), u[1] hi only (the single bf16 pass)
   auto fold_pack = [&](const float* w, int row0, int N, int K, const float* g, const float* b, const uint8_t** dst,
-                       std::vector<float>& u, std::vector<float>& c, std::vector<float>* keep) -> int {
+                       std::vector<float>* u, std::vector<float>& c, std::vector<float>* keep) -> int {
     std::vector<float> wf((size_t)N * K);
     for (int n = 0; n < N; ++n)
       for (int k = 0; k < K; ++k) wf[(size_t)n * K + k] = w[(size_t)(row0 + n) * K + k] * g[k];
     for (int n = 0; n < N; ++n) {
-      double su = 0.0, sc = 0.0;
+      double su = 0.0, sh = 0.0, sc = 0.0;
       for (int k = 0; k < K; ++k) {
         const float x = wf[(size_t)n * K + k];
         const uint16_t hi = f2bf(x);
         const uint16_t lo = f2bf(x - bf2f(hi));
         su += (double)bf2f(hi) + (double)bf2f(lo);
+        sh += (double)bf2f(hi);
         sc += (double)w[(size_t)(row0 + n) * K + k] * (double)b[k];
       }
-      u.push_back((float)su);
+      u[0].push_back((float)su);
+      u[1].push_back((float)sh);
       c.push_back((float)sc);
     }
     const float* wp = wf.data();
@@ -207,27 +210,32 @@ static int finalize(Handle* h) {
     std::string p = "altblock." + std::to_string(i) + ".ang_trans.";
     const float* in_w = W(p + "attention.in_proj_weight");
     {
-      std::vector<float> uqk, cqk, u1, c1, wqk_fold;
+      std::vector<float> uqk[2], cqk, u1[2], c1, wqk_fold;
       if ((rc = fold_pack(in_w, 0, 128, C, W(p + "norm.weight"), W(p + "norm.bias"), &L.a_wqk, uqk, cqk, &wqk_fold)))
         return rc;
       if ((rc = fold_pack(W(p + "feed_forward.1.weight"), 0, 128, C, W(p + "feed_forward.0.weight"),
                           W(p + "feed_forward.0.bias"), &L.a_w1, u1, c1, nullptr)))
         return rc;
-      std::vector<float> tab;
-      tab.insert(tab.end(), uqk.begin(), uqk.end());
-      tab.insert(tab.end(), cqk.begin(), cqk.end());
-      tab.insert(tab.end(), u1.begin(), u1.end());
-      tab.insert(tab.end(), c1.begin(), c1.end());
-      L.a_tab = tab;
       const int NA = A * A;
-      std::vector<float> peqk((size_t)NA * 128);  // chunk-planar [n/4][a][4]
-      for (int a = 0; a < NA; ++a)
-        for (int n = 0; n < 128; ++n) {
-          double acc = 0.0;
-          for (int k = 0; k < C; ++k) acc += (double)pe_a[(size_t)a * C + k] * (double)wqk_fold[(size_t)n * C + k];
-          peqk[((size_t)(n / 4) * NA + a) * 4 + (n % 4)] = (float)acc;
-        }
-      if ((rc = upload_f32(h, peqk, &L.a_peqk))) return rc;
+      for (int m = 0; m < 2; ++m) {
+        std::vector<float> tab;
+        tab.insert(tab.end(), uqk[m].begin(), uqk[m].end());
+        tab.insert(tab.end(), cqk.begin(), cqk.end());
+        tab.insert(tab.end(), u1[m].begin(), u1[m].end());
+        tab.insert(tab.end(), c1.begin(), c1.end());
+        L.a_tab[m] = tab;
+        std::vector<float> peqk((size_t)NA * 128);  // chunk-planar [n/4][a][4]; bf16 mode: with the weights that mode multiplies by
+        for (int a = 0; a < NA; ++a)
+          for (int n = 0; n < 128; ++n) {
+            double acc = 0.0;
+            for (int k = 0; k < C; ++k) {
+              const float wv = wqk_fold[(size_t)n * C + k];
+              acc += (double)pe_a[(size_t)a * C + k] * (double)(m ? bf2f(f2bf(wv)) : wv);
+            }
+            peqk[((size_t)(n / 4) * NA + a) * 4 + (n % 4)] = (float)acc;
+          }
+        if ((rc = upload_f32(h, peqk, &L.a_peqk[m]))) return rc;
+      }
     }
     if ((rc = lin_pack(in_w, 128, 64, C, 0, C, &L.a_wv))) return rc;
     if ((rc = lin_pack(W(p + "attention.out_proj.weight"), 0, 64, C, 0, C, &L.a_wo))) return rc;
@@ -244,21 +252,23 @@ static int finalize(Handle* h) {
     if ((rc = conv_pack(W(p + "MLP.weight"), 128, &L.s_wmlp))) return rc;  // [128][64*9]: c*9+tap (LFT.py:167)
     in_w = W(p + "attention.in_proj_weight");
     {
-      std::vector<float> uq, cq, uk, ck, u1, c1;
+      std::vector<float> uq[2], cq, uk[2], ck, u1[2], c1;
       const float *g1 = W(p + "norm.weight"), *b1 = W(p + "norm.bias");
       const float *g2 = W(p + "feed_forward.0.weight"), *b2 = W(p + "feed_forward.0.bias");
       if ((rc = fold_pack(in_w, 0, 128, S, g1, b1, &L.s_wq, uq, cq, nullptr))) return rc;
       if ((rc = fold_pack(in_w, 128, 128, S, g1, b1, &L.s_wk, uk, ck, nullptr))) return rc;
       if ((rc = fold_pack(W(p + "feed_forward.1.weight"), 0, 128, S, g2, b2, &L.s_w1a, u1, c1, nullptr))) return rc;
       if ((rc = fold_pack(W(p + "feed_forward.1.weight"), 128, 128, S, g2, b2, &L.s_w1b, u1, c1, nullptr))) return rc;
-      std::vector<float> tab;
-      tab.insert(tab.end(), uq.begin(), uq.end());
-      tab.insert(tab.end(), uk.begin(), uk.end());
-      tab.insert(tab.end(), cq.begin(), cq.end());
-      tab.insert(tab.end(), ck.begin(), ck.end());
-      tab.insert(tab.end(), u1.begin(), u1.end());
-      tab.insert(tab.end(), c1.begin(), c1.end());
-      L.s_tab = tab;
+      for (int m = 0; m < 2; ++m) {
+        std::vector<float> tab;
+        tab.insert(tab.end(), uq[m].begin(), uq[m].end());
+        tab.insert(tab.end(), uk[m].begin(), uk[m].end());
+        tab.insert(tab.end(), cq.begin(), cq.end());
+        tab.insert(tab.end(), ck.begin(), ck.end());
+        tab.insert(tab.end(), u1[m].begin(), u1[m].end());
+        tab.insert(tab.end(), c1.begin(), c1.end());
+        L.s_tab[m] = tab;
+      }
     }
     if ((rc = lin_pack(in_w, 256, 128, S, 0, S, &L.s_wv))) return rc;
     if ((rc = lin_pack(W(p + "attention.out_proj.weight"), 0, 128, S, 0, S, &L.s_wo))) return rc;
@@ -307,7 +317,10 @@ int ensure_spa_pe(Handle* h, int P) {
   {
     auto it = h->pe_cache.find(P);
     if (it != h->pe_cache.end()) {
-      for (int i = 0; i < kLayers; ++i) { h->layer[i].s_pe = it->second.pe[i]; h->layer[i].s_pev = it->second.pev[i]; }
+      for (int i = 0; i < kLayers; ++i) {
+        h->layer[i].s_pe = it->second.pe[i];
+        for (int m = 0; m < 2; ++m) h->layer[i].s_pev[m] = it->second.pev[i][m];
+      }
       h->pe_P = P;
       return 0;
     }
@@ -347,17 +360,24 @@ int ensure_spa_pe(Handle* h, int P) {
     // PE_s Wv^T: V = tok Wv^T is computed from the operand z = tok + PE_s, so this constant is subtracted
     const float* wv = h->host_w["altblock." + std::to_string(i) + ".spa_trans.attention.in_proj_weight"].data() +
                       (size_t)256 * S;
-    std::vector<float> pvt((size_t)PPn * S);
-    for (int t = 0; t < PPn; ++t)
-      for (int n = 0; n < S; ++n) {
-        double a = 0.0;
-        for (int k = 0; k < S; ++k) a += (double)tab[(size_t)t * S + k] * (double)wv[(size_t)n * S + k];
-        pvt[((size_t)(n / 4) * PPn + t) * 4 + (n % 4)] = (float)a;
-      }
-    if ((rc = upload_f32(h, pvt, &h->layer[i].s_pev))) return rc;
+    for (int m = 0; m < 2; ++m) {  // bf16 mode: with the bf16-rounded Wv that mode multiplies z = tok + PE_s by
+      std::vector<float> wvm((size_t)S * S);
+      for (size_t j = 0; j < wvm.size(); ++j) wvm[j] = m ? bf2f(f2bf(wv[j])) : wv[j];
+      std::vector<float> pvt((size_t)PPn * S);
+      for (int t = 0; t < PPn; ++t)
+        for (int n = 0; n < S; ++n) {
+          double a = 0.0;
+          for (int k = 0; k < S; ++k) a += (double)tab[(size_t)t * S + k] * (double)wvm[(size_t)n * S + k];
+          pvt[((size_t)(n / 4) * PPn + t) * 4 + (n % 4)] = (float)a;
+        }
+      if ((rc = upload_f32(h, pvt, &h->layer[i].s_pev[m]))) return rc;
+    }
   }
   SpaPe& e = h->pe_cache[P];
-  for (int i = 0; i < kLayers; ++i) { e.pe[i] = h->layer[i].s_pe; e.pev[i] = h->layer[i].s_pev; }
+  for (int i = 0; i < kLayers; ++i) {
+    e.pe[i] = h->layer[i].s_pe;
+    for (int m = 0; m < 2; ++m) e.pev[i][m] = h->layer[i].s_pev[m];
+  }
   h->pe_P = P;
   return 0;
 }

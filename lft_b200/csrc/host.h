@@ -49,15 +49,18 @@ struct Layer {
   // AngTrans (LFT.py:194-238)
   const uint8_t *a_wqk = nullptr, *a_wv = nullptr, *a_wo = nullptr, *a_w1 = nullptr, *a_w2 = nullptr;
   const float* a_ln = nullptr;    // [norm.w | norm.b | ff0.w | ff0.b] x 64
-  std::vector<float> a_tab;       // LN-folded epilogue constants [u_qk 128 | c_qk 128 | u_1 128 | c_1 128] (host; kernel param)
-  const float* a_peqk = nullptr;  // [A*A][128]  PE_a W'qk^T
+  // Constants that must agree with the weights the MMAs really multiply by exist once per precision mode
+  // ([0]: fp32 mode, bf16 hi + lo weights; [1]: bf16 mode, hi weights only): the LN fold subtracts mean * u with
+  // u = sum_k W'[n,k], which cancels the row mean only if it sums exactly the values the tensor core used.
+  std::vector<float> a_tab[2];    // LN-folded epilogue constants [u_qk 128 | c_qk 128 | u_1 128 | c_1 128] (host; kernel param)
+  const float* a_peqk[2] = {nullptr, nullptr};  // [A*A][128]  PE_a W'qk^T
   // SpaTrans (LFT.py:118-191)
   const uint8_t *s_wmlp = nullptr, *s_wq = nullptr, *s_wk = nullptr, *s_wv = nullptr, *s_wo = nullptr;
   const uint8_t *s_w1a = nullptr, *s_w1b = nullptr, *s_w2a = nullptr, *s_w2b = nullptr, *s_wlin = nullptr;
   const float* s_ln = nullptr;  // [norm.w | norm.b | ff0.w | ff0.b] x 128
   const float* s_pe = nullptr;    // [P*P][128] SAI2Token(spa_position) for the current patch size (points into Handle::pe_cache)
-  const float* s_pev = nullptr;   // chunk-planar [32][P*P][4]: PE_s Wv^T, likewise
-  std::vector<float> s_tab;       // [u_q 128 | u_k 128 | c_q 128 | c_k 128 | u_1 256 | c_1 256] (host; kernel params)
+  const float* s_pev[2] = {nullptr, nullptr};   // chunk-planar [32][P*P][4]: PE_s Wv^T, likewise (per precision mode)
+  std::vector<float> s_tab[2];    // [u_q 128 | u_k 128 | c_q 128 | c_k 128 | u_1 256 | c_1 256] (host; kernel params)
 
 };
 
@@ -70,7 +73,7 @@ struct ProfEvent {
 // spatial position tables of one patch size (per layer), kept for the life of the weights they were built from
 struct SpaPe {
   const float* pe[kLayers] = {nullptr, nullptr, nullptr, nullptr};
-  const float* pev[kLayers] = {nullptr, nullptr, nullptr, nullptr};
+  const float* pev[kLayers][2] = {};
 };
 
 // RAII: make `dev` current for the duration of an API call and restore the caller's device afterwards (the library must not
@@ -109,6 +112,7 @@ struct Handle {
   int64_t launches = 0;
   int num_sms = 148;
   int passes() const { return cfg.precision == LFT_PREC_FP32 ? 3 : 1; }
+  int mode() const { return cfg.precision == LFT_PREC_FP32 ? 0 : 1; }  // index of the per-precision constant tables
 };
 
 int upload(Handle* h, const void* src, size_t bytes, void** dst);

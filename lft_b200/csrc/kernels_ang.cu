@@ -662,10 +662,10 @@ int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, Reg
   const unsigned grid = ntiles < 2u * h->num_sms ? ntiles : 2u * h->num_sms;  // persistent: two CTAs per SM
   const Layer& L = h->layer[layer];
   Tab512 ta;
-  memcpy(ta.v, L.a_tab.data(), sizeof(ta.v));
+  memcpy(ta.v, L.a_tab[h->mode()].data(), sizeof(ta.v));
   Scope sc(h, K_ANG, st, npix * N);
 #define LFT_ANG_LAUNCH(NV)                                                                                          \
-  k_ang<NV><<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, ta, L.a_peqk, \
+  k_ang<NV><<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, ta, L.a_peqk[h->mode()], \
                                                h->pe_ang, N, P, npix, h->passes(), (int)ntiles, rg)
   if (N == 25) LFT_ANG_LAUNCH(25);
   else if (N == 9) LFT_ANG_LAUNCH(9);

@@ -738,11 +738,11 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
   {
     const long long G = V * (e.rn + 1) * (e.rn + 1);
     Tab512 tq;
-    memcpy(tq.v, L.s_tab.data(), sizeof(tq.v));  // [u_q | u_k | c_q | c_k]
+    memcpy(tq.v, L.s_tab[h->mode()].data(), sizeof(tq.v));  // [u_q | u_k | c_q | c_k]
     Scope sc(h, K_SPA_QKV, st, V * kv.rn * kv.rn);
     const unsigned ntiles = (unsigned)((G + 127) / 128);
     const unsigned pg = ntiles < 2u * h->num_sms ? ntiles : 2u * h->num_sms;  // persistent: two CTAs per SM
-    k_spa_embed_qkv<<<pg, kThreads2, kSmemSpa, st>>>(in, L.s_wmlp, L.s_pe, L.s_pev, tq, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q,
+    k_spa_embed_qkv<<<pg, kThreads2, kSmemSpa, st>>>(in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q,
                                                      w.k, w.v, (int)V, P, h->passes(), (int)ntiles, e, kv);
     if ((rc = sc.finish())) return rc;
   }
@@ -754,7 +754,7 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
   }
   {
     Tab512 tf;
-    memcpy(tf.v, L.s_tab.data() + 512, sizeof(tf.v));  // [u_1 256 | c_1 256]
+    memcpy(tf.v, L.s_tab[h->mode()].data() + 512, sizeof(tf.v));  // [u_1 256 | c_1 256]
     const long long T = V * need.rn * need.rn;
     Scope sc(h, K_SPA_FFN, st, T);
     k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,

@@ -35,6 +35,11 @@ constexpr uint32_t kLbo64 = 128 * 16;
 //   barriers (every one has its own per-buffer instance so that no thread can arrive twice on one phase):
 //     aux[0] A1 + W3 staged (256) | aux[2], aux[3] D1[b] full (commit) | a_ready, aux[1] A2[b] ready (256) |
 //     mma_done, full[4] D2[c] full (commit) | empty[4], empty[5] D2[c] drained (256).
+// Precision: G2 is the last contraction of the network - its result is the SR pixel, with no normalisation after it - and it
+// is tiny (N = 16).  It therefore runs the three-pass hi/lo product in BOTH precision modes: in bf16 mode the rounding of
+// lrelu(D1) and of the 576 tap weights to bf16 alone accounted for most of the output error (3e-4 rms of 4.3e-4) and for a
+// constant offset of 2e-4 (the rounding errors of the tap weights times the positive mean of the LeakyReLU outputs), which
+// is what the PSNR-delta gate is most sensitive to.  G1 and everything upstream follow the selected mode.
 //   G1(ij+2) overwrites X[b] that G2(ij) reads as its A operand: the MMA warp waits for G2(ij)'s commit before issuing it (the
 //   wait is off the critical path, G1(ij+2) is needed two iterations later).
 __global__ void __launch_bounds__(kThreads2, 2)
@@ -102,12 +107,11 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
       if (elect_one()) {
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) umma_bf16_ts(d2, a_hi + j * 8, umma_desc_from(bh + j * 32), idesc, j ? 1u : 0u);
-        if (passes == 3) {
+        // G2 always runs all three passes (see the header comment): 12 N = 16 MMAs per sub-pixel
 #pragma unroll
-          for (uint32_t j = 0; j < 4; ++j) umma_bf16_ts(d2, a_lo + j * 8, umma_desc_from(bh + j * 32), idesc, 1u);
+        for (uint32_t j = 0; j < 4; ++j) umma_bf16_ts(d2, a_lo + j * 8, umma_desc_from(bh + j * 32), idesc, 1u);
 #pragma unroll
-          for (uint32_t j = 0; j < 4; ++j) umma_bf16_ts(d2, a_hi + j * 8, umma_desc_from(bl + j * 32), idesc, 1u);
-        }
+        for (uint32_t j = 0; j < 4; ++j) umma_bf16_ts(d2, a_hi + j * 8, umma_desc_from(bl + j * 32), idesc, 1u);
         umma_commit(d2_full(b));
       }
       __syncwarp();
@@ -214,8 +218,8 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < 32; ++i) d[i] = lrelu02(d[i]);
-        a_tmem_store16(trow + 64 * bsel, trow + 64 * bsel + 32, 32 * q, d, passes == 3);
-        a_tmem_store16(trow + 64 * bsel, trow + 64 * bsel + 32, 32 * q + 16, d + 16, passes == 3);
+        a_tmem_store16(trow + 64 * bsel, trow + 64 * bsel + 32, 32 * q, d, true);   // hi + lo in both precision modes
+        a_tmem_store16(trow + 64 * bsel, trow + 64 * bsel + 32, 32 * q + 16, d + 16, true);
       }
       tmem_wait_st();
       tc_fence_before();

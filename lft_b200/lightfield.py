@@ -186,7 +186,9 @@ class HostPipeline:
 
     def __init__(self, net_or_engine, depth: int = 2, max_ws_bytes: Optional[int] = None, patch: int = PATCH,
                  stride: int = STRIDE):
-        self._sr = LightFieldSR(net_or_engine, max_ws_bytes, patch, stride)
+        # a ready LightFieldSR (e.g. one with a multi-GPU assembly mode chosen) is used as is
+        self._sr = (net_or_engine if isinstance(net_or_engine, LightFieldSR)
+                    else LightFieldSR(net_or_engine, max_ws_bytes, patch, stride))
         self._depth = depth
         self._slots: List[dict] = []
         self._copy: Optional[torch.cuda.Stream] = None   # device -> host
