@@ -190,6 +190,154 @@ LFT_DEVINL void ang_singles25(uint32_t tq, uint32_t to_hi, uint32_t to_lo, int l
   }
 }
 
+// One (pixel, head) item of the A = 5 attention for one query: all 25 scores first (independent dot products), one maximum,
+// then the weighted sum - no online rescaling (25 scores fit in registers).  kb / vb: the pixel's first key in the planes,
+// key t at kb[5 t] (first 4 dims) and kb[5 t + 128] (last 4 dims).
+LFT_DEVINL void ang_attn_item25(const f32x2* q, const ulonglong2* __restrict__ kb, const ulonglong2* __restrict__ vb, float* o) {
+  float sc[25];
+#pragma unroll
+  for (int t = 0; t < 25; ++t) sc[t] = dot8(q, kb[5 * t], kb[5 * t + 128]);
+  float mx = sc[0];
+#pragma unroll
+  for (int t = 1; t < 25; ++t) mx = fmaxf(mx, sc[t]);
+  float l = 0.f;
+  f32x2 acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+  for (int t = 0; t < 25; ++t) {
+    const float pw = fast_exp2(sc[t] - mx);
+    l += pw;
+    const f32x2 pp = pack2(pw, pw);
+    const ulonglong2 v0 = vb[5 * t], v1 = vb[5 * t + 128];
+    acc[0] = fma2(pp, v0.x, acc[0]); acc[1] = fma2(pp, v0.y, acc[1]);
+    acc[2] = fma2(pp, v1.x, acc[2]); acc[3] = fma2(pp, v1.y, acc[3]);
+  }
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float a, b;
+    unpack2(acc[e], a, b);
+    o[2 * e] = a * inv;
+    o[2 * e + 1] = b * inv;
+  }
+}
+
+// A = 5 (25 views per pixel, 5 pixels per tile): the attention of a tile is re-mapped from the row owners to
+// (pixel, head) work items so that a WARP works on ONE pixel and one head with lane = query view: all lanes then read the
+// same key / value at the same time and every shared-memory load is a broadcast (one wavefront per 16 bytes per warp instead
+// of one per quarter-warp and row - the row-owner formulation, even with two views sharing each read, was bound by exactly that
+// traffic: 126 M wavefronts per launch, ~80 % of the kernel).  Rows stay view-major (global accesses of the owners stay
+// coalesced); Q, K and V leave the accumulators through shared memory, one head half (4 heads) at a time:
+//   R2: K [rel head 4][half 2][kv row 128][16 B] 16 KB | V 16 KB         (kv row = view * 5 + pixel)
+//   R1: Q / O of head half 0 (16 KB, same layout, O overwrites Q in place) | of head half 1 (16 KB)
+// per half g: export (thread 0 of a row: K, thread 1: V and Q, both with the LayerNorm-fold correction) | barrier | 20 items
+// (pixel, rel head) over the 8 warps | barrier.  The O operand of the output projection (TS form, TMEM columns [64,128))
+// overlaps K accumulator columns of the other half, so half 0's results stay in shared memory until half 1 has been
+// exported.
+LFT_DEVINL void ang_attention25(uint32_t trow, int warp, int lane, int q, int kvrow, float rstd, float mr,
+                                const float4* __restrict__ pq4, const float4* tab4, uint8_t* planes, bool fp32_mode) {
+  constexpr int N = 25;
+  uint8_t* qo_ptr = planes;           // R1
+  uint8_t* ks_ptr = planes + 32768;   // R2
+  uint8_t* vs_ptr = ks_ptr + 16384;
+  const float scale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e)/sqrt(8), folded into Q (softmax via exp2)
+  // results of head half g: shared memory -> bf16 hi/lo TS-form operand; the two threads of a row take two heads each
+  auto convert = [&](int g) {
+    const uint8_t* src = qo_ptr + g * 16384 + kvrow * 16;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int rh = 2 * q + hh;
+      float o[8];
+      *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(src + (rh * 2) * 2048);
+      *reinterpret_cast<float4*>(o + 4) = *reinterpret_cast<const float4*>(src + (rh * 2 + 1) * 2048);
+      uint4 hi, lo;
+      split8(o, hi, lo, fp32_mode);
+      tmem_st4u(trow + 64 + 16 * g + 4 * rh, hi);
+      if (fp32_mode) tmem_st4u(trow + 96 + 16 * g + 4 * rh, lo);
+    }
+  };
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    float kv[16];
+    LFT_TL(12 + 4 * g);
+    if (q == 0) {  // K of heads 4g..4g+3 (accumulator columns 64 + 32g ..), corrected
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col = 64 + 32 * g + 16 * c;
+        tmem_ld16(trow + col, kv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
+          const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
+          const float4 r = make_float4(fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x)),
+                                       fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y)),
+                                       fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z)),
+                                       fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w)));
+          *reinterpret_cast<float4*>(ks_ptr + ((2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) = r;
+        }
+      }
+    } else {       // V (raw) and Q (corrected, pre-scaled) of the same heads
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld16(trow + 128 + 32 * g + 16 * c, kv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(vs_ptr + ((2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) =
+              make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col = 32 * g + 16 * c;
+        tmem_ld16(trow + col, kv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
+          const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
+          const float4 r = make_float4(scale * fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x)),
+                                       scale * fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y)),
+                                       scale * fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z)),
+                                       scale * fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w)));
+          *reinterpret_cast<float4*>(qo_ptr + g * 16384 + ((2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) = r;
+        }
+      }
+    }
+    LFT_TL(13 + 4 * g);
+    tc_fence_before();
+    rows_bar_sync256();  // planes of half g complete; for g = 1: every Q / K / V accumulator column has been consumed
+    tc_fence_after();
+    LFT_TL(14 + 4 * g);
+    if (g == 1) convert(0);
+    const uint8_t* qo_g = qo_ptr + g * 16384;
+#pragma unroll 1
+    for (int it = warp; it < 20; it += 8) {  // items (rel head, pixel); lane = query view (lanes 25..31 shadow view 24)
+      const int rh = it / 5, p = it - 5 * rh;
+      const int a = lane < N ? lane : N - 1;
+      uint8_t* qrow = const_cast<uint8_t*>(qo_g) + (rh * 2) * 2048 + (a * 5 + p) * 16;
+      f32x2 qq[1][4];
+      {
+        const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(qrow);
+        const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(qrow + 2048);
+        qq[0][0] = q0.x; qq[0][1] = q0.y; qq[0][2] = q1.x; qq[0][3] = q1.y;
+      }
+      const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(ks_ptr + rh * 4096) + p;
+      const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(vs_ptr + rh * 4096) + p;
+      float o[1][8];
+#ifdef LFT_ANG_ONLINE
+      ang_attn_head<1, 25, 5, 5>(qq, kb, vb, o);
+#else
+      ang_attn_item25(qq[0], kb, vb, o[0]);
+#endif
+      if (lane < N) {  // O overwrites Q in place (only this lane ever read it)
+        *reinterpret_cast<float4*>(qrow) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+        *reinterpret_cast<float4*>(qrow + 2048) = make_float4(o[0][4], o[0][5], o[0][6], o[0][7]);
+      }
+    }
+    LFT_TL(15 + 4 * g);
+    rows_bar_sync256();  // results of half g complete; K / V planes free for the next half
+  }
+  LFT_TL(20);
+  convert(1);
+}
+
 // NV > 0: compile-time number of views (scores kept in registers, single QK pass); NV == 0: runtime N.
 template <int NV>
 __global__ void __launch_bounds__(kThreads2, 2)
@@ -370,6 +518,13 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       const float mr = mean * rstd;
       const float4* pq4 = reinterpret_cast<const float4*>(peqk) + aa;  // [chunk 32][N][4]: Q chunks 0..15, K 16..31
       const float4* tab4 = reinterpret_cast<const float4*>(tab.v);    // [u_qk 128 | c_qk 128 | u_1 128 | c_1 128] (constant bank)
+      if constexpr (NV == 25) {
+        ang_attention25(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes, passes == 3);
+        LFT_TL(4);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+      } else {
       float kv[16];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {  // K columns 64 + 32q + 16c
@@ -516,6 +671,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(a_ready);
+      }  // !kPair
       }  // NV != 25
     }
 
