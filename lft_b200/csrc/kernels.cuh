@@ -11,9 +11,17 @@ constexpr int kThreads = 192;
 constexpr int kWarpProducer = 4;
 constexpr int kWarpMma = 5;
 constexpr int kCtlBytes = 256;
-// conv staging: rows <-> positions g0-kConvOff .. g0-kConvOff+kConvRows-1 (P <= 32 -> |shift| <= 34)
-constexpr int kConvRows = 201;  // odd: k-chunk planes start in different banks
-constexpr int kConvOff = 36;
+// conv staging: rows <-> positions g0-kOff .. g0-kOff+kRows-1; a tap shifts by at most P + 2 positions.
+//   BIG = false: patches up to 32 x 32 (|shift| <= 34), three ring stages - the default tiling of test.py
+//   BIG = true : patches up to 64 x 64 (|shift| <= 66): the window needs 261 rows (66.8 KB for hi + lo), so the weight ring
+//                shrinks to two stages to keep two CTAs per SM (--patch_size_for_test 64)
+template <bool BIG>
+struct ConvGeom {
+  static constexpr int kRows = BIG ? 261 : 201;  // odd: k-chunk planes start in different banks
+  static constexpr int kOff = BIG ? 66 : 36;
+  static constexpr int kNST = BIG ? 2 : 3;
+  static constexpr int kMaxP = BIG ? 64 : 32;
+};
 
 struct Ctl {
   uint64_t full[8];
@@ -101,8 +109,10 @@ LFT_DEVINL long long t32_off(long long t, int chunk, int C4) {
 // one lane per row (T32 source: a warp reads 512 contiguous bytes per chunk), bf16 hi/lo, chunk-major.
 // The position space covers the region `e` of every view: rows of e.rn + 1 positions (+ one pad row), VS = (e.rn + 1)^2;
 // position (yy, xx) <-> pixel (e.r0 + yy, e.r0 + xx).
+template <bool BIG>
 LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, uint32_t a_lo, long long g0, long long G,
                                   long long VS, int P, Region e, int tid, bool fp32_mode) {
+  constexpr int kConvRows = ConvGeom<BIG>::kRows, kConvOff = ConvGeom<BIG>::kOff;
   const int P1 = e.rn + 1;
   for (int r = tid; r < kConvRows; r += kRowThreads2) {
     const long long g = g0 - kConvOff + r;
@@ -129,8 +139,10 @@ LFT_DEVINL void conv_stage_window(const float* __restrict__ in, uint32_t a_hi, u
 }
 
 // L2 prefetch of the rows conv_stage_window will read for the tile at g0 (same row <-> thread mapping)
+template <bool BIG>
 LFT_DEVINL void conv_prefetch_window(const float* __restrict__ in, long long g0, long long G, long long VS, int P, Region e,
                                      int tid) {
+  constexpr int kConvRows = ConvGeom<BIG>::kRows, kConvOff = ConvGeom<BIG>::kOff;
   const int P1 = e.rn + 1;
   for (int r = tid; r < kConvRows; r += kRowThreads2) {
     const long long g = g0 - kConvOff + r;

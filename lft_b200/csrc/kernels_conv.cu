@@ -79,8 +79,10 @@ LFT_DEVINL void conv0_channels(const W0Tab& w0, const float* t, float* o) {  // 
 }
 
 // conv_stage_window with conv_init0 computed in place of the loads
+template <bool BIG>
 LFT_DEVINL void conv_stage_window_lr(const float* __restrict__ lr, const W0Tab& w0, int A, uint32_t a_hi, uint32_t a_lo,
                                      long long g0, long long G, long long VS, int P, int tid, bool fp32_mode) {
+  constexpr int kConvRows = ConvGeom<BIG>::kRows, kConvOff = ConvGeom<BIG>::kOff;
   const int P1 = P + 1;
   for (int r = tid; r < kConvRows; r += kRowThreads2) {
     const long long g = g0 - kConvOff + r;
@@ -125,13 +127,14 @@ LFT_DEVINL void conv_stage_window_lr(const float* __restrict__ lr, const W0Tab& 
 // tile k's epilogue (accumulator loads, LeakyReLU / residual, stores) UNDER tile k+1's MMAs.  a_ready and mma_done complete one
 // phase per tile (parity k&1).  The accumulator of tile k is overwritten by tile k+2, whose MMAs are gated by a_ready arrivals
 // every row owner makes after its epilogue of tile k; the window is overwritten only after mma_done of the tile that read it.
-template <int N>
+template <int N, bool BIG>
 __global__ void __launch_bounds__(kThreads2, 2)
 k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* __restrict__ out,
           const float* __restrict__ res, int V, int P, int passes, int epi, const float* __restrict__ lr,
           const __grid_constant__ W0Tab w0, int A, const uint8_t* __restrict__ wst, int ntiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int NST = 3;
+  constexpr int NST = ConvGeom<BIG>::kNST;
+  constexpr int kConvRows = ConvGeom<BIG>::kRows, kConvOff = ConvGeom<BIG>::kOff;
   // fp32 mode streams STACKED slabs: per tap one [128 x 64] B operand (rows 0..63 hi, 64..127 lo), so that A_hi is read once
   // for A_hi*W_hi and A_hi*W_lo (one N = 128 MMA per k step, accumulator columns [0,64) | [64,128)) and A_lo*W_hi adds into
   // [0,64) with an N = 64 MMA on the same slab: 14 KB instead of 18 KB of operands and 112 instead of 144 pipe cycles per k step.
@@ -215,9 +218,9 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
     auto stage = [&](int k) {
       const long long g0 = (long long)(first + k * step) * 128;
       if (N == 64 && in == nullptr)
-        conv_stage_window_lr(lr, w0, A, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
+        conv_stage_window_lr<BIG>(lr, w0, A, a_hi, a_lo, g0, G, VS, P, tid, passes == 3);
       else
-        conv_stage_window(in, a_hi, a_lo, g0, G, VS, P, Region{0, P}, tid, passes == 3);
+        conv_stage_window<BIG>(in, a_hi, a_lo, g0, G, VS, P, Region{0, P}, tid, passes == 3);
       fence_proxy_async_smem();
       mbar_arrive(a_ready);
     };
@@ -280,7 +283,7 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
       }
       // pull the window of tile k+2 into L2 while tile k+1's MMAs run (-4.6 %; the same hint in k_spa_embed_qkv, whose
       // staging is already hidden under its Q MMA, changed nothing)
-      if (in != nullptr && k + 2 < ntl) conv_prefetch_window(in, (long long)(first + (k + 2) * step) * 128, G, VS, P, Region{0, P}, tid);
+      if (in != nullptr && k + 2 < ntl) conv_prefetch_window<BIG>(in, (long long)(first + (k + 2) * step) * 128, G, VS, P, Region{0, P}, tid);
     }
     tc_fence_before();
   }
@@ -506,10 +509,12 @@ int launch_mma_bench(int N, int K, int reps, int mode, int grid, int smem_bytes,
 }
 
 // ------------------------------------------------------------------------------------------------ host
-constexpr size_t kSmemConv64 = kCtlBytes + 2 * kConvRows * 128 + 3 * 128 * 128;
+template <bool BIG>
+constexpr size_t smem_conv64() { return kCtlBytes + 2 * ConvGeom<BIG>::kRows * 128 + ConvGeom<BIG>::kNST * 128 * 128; }
 
 int configure_conv() {
-  CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemConv64));
+  CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_conv64<false>()));
+  CUDA_TRY(cudaFuncSetAttribute(k_conv3x3<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_conv64<true>()));
   CUDA_TRY(cudaFuncSetAttribute(k_gemm_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return 0;
 }
@@ -526,7 +531,10 @@ int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, const u
   memcpy(w0.w, h->w_conv0_host.data(), sizeof(w0.w));
   Scope sc(h, K_CONV64, st, (long long)V * P * P);
   if (N != 64) return fail(LFT_ERR_ARG, "launch_conv3x3: only the 64 -> 64 conv stack uses this kernel (the 64 -> 128 token embedding is part of k_spa_embed_qkv)");
-  k_conv3x3<64><<<grid, kThreads2, kSmemConv64, st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst, (int)ntiles);
+  if (P <= ConvGeom<false>::kMaxP)
+    k_conv3x3<64, false><<<grid, kThreads2, smem_conv64<false>(), st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst, (int)ntiles);
+  else
+    k_conv3x3<64, true><<<grid, kThreads2, smem_conv64<true>(), st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst, (int)ntiles);
   return sc.finish();
 }
 

@@ -23,6 +23,11 @@ namespace lft {
 constexpr int kSpaNST = 3;
 constexpr uint32_t kSpaStage = 128 * 128;
 constexpr size_t kSmemSpa = kCtlBytes + 65536 + kSpaNST * kSpaStage;
+// k_spa_embed_qkv<BIG>: conv window (hi + lo) followed by the weight ring; BIG (patches up to 64 x 64): 66.8 KB + two stages
+template <bool BIG>
+constexpr uint32_t embed_window_bytes() { return BIG ? 2u * ConvGeom<true>::kRows * 128u : 65536u; }
+template <bool BIG>
+constexpr size_t smem_embed() { return kCtlBytes + embed_window_bytes<BIG>() + ConvGeom<BIG>::kNST * kSpaStage; }
 constexpr uint32_t kLbo = 128 * 16;
 
 LFT_DEVINL long long planar_off(long long v, int head, int y, int j, int x, int P) {
@@ -55,6 +60,7 @@ LFT_DEVINL void a_store16(uint32_t A, int kc0, int m, const float* x, bool fp32_
 // arithmetic and stores, which then run under the next MMA.  Set-up / tear-down / window fill leave the per-tile chain.  Barriers: F = aux[0] (256) window of the next tile staged; a_ready (256): z ready, Q / K / V drained
 // (4 arrivals per tile, each separated from the next by a wait on an MMA that needed the previous phase complete);
 // mma_done: conv, Q, K, V (4 commits per tile).
+template <bool BIG>
 __global__ void __launch_bounds__(kThreads2, 2)
 k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp, const float* __restrict__ pe,
                   const float* __restrict__ pev, const __grid_constant__ Tab512 tab, const uint8_t* __restrict__ wq,
@@ -65,10 +71,12 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
   // stored.  Full view: e = o = {0, P}.  On the light-field path e is the region the conv inputs are valid on and o = e
   // shrunk by one pixel wherever e's border is not the view border (there the zero padding is not the true neighbour).
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NST = ConvGeom<BIG>::kNST;
+  constexpr int kConvRows = ConvGeom<BIG>::kRows, kConvOff = ConvGeom<BIG>::kOff;
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t U = smem_u32(smem) + kCtlBytes;
   const uint32_t c_hi = U, c_lo = U + kConvRows * 128;
-  const uint32_t ring = U + 65536;
+  const uint32_t ring = U + embed_window_bytes<BIG>();
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
   const uint32_t f_ready = smem_u32(&ctl->aux[0]);
@@ -76,22 +84,22 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
   const int P1 = e.rn + 1;
   const long long VS = (long long)P1 * P1;
   const long long G = (long long)V * VS;
-  cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
+  cta_setup<NST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
   const GemmPhase g_c{wmlp, 128, 9}, g_q{wq, 128, 2}, g_k{wk, 128, 2}, g_v{wv, 128, 2};
   const int first = blockIdx.x, step = gridDim.x;
   const int ntl = first < ntiles ? (ntiles - first + step - 1) / step : 0;
 
   if (warp == kWarpProducer2) {
-    RingState<kSpaNST> rs;
+    RingState<NST> rs;
     for (int k = 0; k < ntl; ++k) {
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes);
-      ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes);
+      ring_produce<NST>(rs, ring, kSpaStage, full0, empty0, g_c, passes);
+      ring_produce<NST>(rs, ring, kSpaStage, full0, empty0, g_q, passes);
+      ring_produce<NST>(rs, ring, kSpaStage, full0, empty0, g_k, passes);
+      ring_produce<NST>(rs, ring, kSpaStage, full0, empty0, g_v, passes);
     }
   } else if (warp == kWarpMma2) {
-    RingState<kSpaNST> rs;
+    RingState<NST> rs;
     uint32_t rpar = 0;
     auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
     const uint32_t ta_hi = tmem + 128, ta_lo = tmem + 192;
@@ -99,20 +107,20 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       mbar_wait(f_ready, k & 1);
       if (k > 0) { mbar_wait(a_ready, rpar); rpar ^= 1; }  // V of the previous tile drained: D[0,128) is free
       tc_fence_after();
-      ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
+      ring_consume_mma<NST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
                                 c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
       umma_commit_elected(mma_done);
       mbar_wait(a_ready, rpar); rpar ^= 1;
       tc_fence_after();
-      ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, ta_hi, ta_lo, tmem + 0, true);
+      ring_consume_mma_ts<NST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, ta_hi, ta_lo, tmem + 0, true);
       umma_commit_elected(mma_done);
       mbar_wait(a_ready, rpar); rpar ^= 1;
       tc_fence_after();
-      ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, ta_hi, ta_lo, tmem + 0, true);
+      ring_consume_mma_ts<NST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, ta_hi, ta_lo, tmem + 0, true);
       umma_commit_elected(mma_done);
       mbar_wait(a_ready, rpar); rpar ^= 1;
       tc_fence_after();
-      ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, ta_hi, ta_lo, tmem + 0, true);
+      ring_consume_mma_ts<NST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, ta_hi, ta_lo, tmem + 0, true);
       umma_commit_elected(mma_done);
     }
   } else {
@@ -127,7 +135,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       tc_fence_after();
     };
     auto stage = [&](int k) {
-      conv_stage_window(feat, c_hi, c_lo, (long long)(first + k * step) * 128, G, VS, P, e, tid, passes == 3);
+      conv_stage_window<BIG>(feat, c_hi, c_lo, (long long)(first + k * step) * 128, G, VS, P, e, tid, passes == 3);
       fence_proxy_async_smem();
       mbar_arrive(f_ready);
     };
@@ -278,8 +286,8 @@ LFT_DEVINL void axpy16(f32x2* o, float p, const ulonglong2& a, const ulonglong2&
 #define LFT_ATTN_RB 8
 #endif
 constexpr int kAttnRB = LFT_ATTN_RB;       // query rows per CTA (A/B: 16 stages 20 key rows for 16 instead of 12 for 8)
-constexpr int kAttnThreads = kAttnRB * 16;  // 32 x-lanes x RB/2 row pairs
-constexpr size_t kSmemAttn = 2 * (kAttnRB + 4) * 4 * 32 * 16 + 16;
+constexpr int kAttnThreads = kAttnRB * 16;  // 32 x-lanes x RB/2 row pairs; wider rows (P > 32) take several passes
+constexpr size_t smem_attn(int P) { return 2 * (size_t)(kAttnRB + 4) * 4 * P * 16 + 16; }  // K and V rows [r0-2, r0+RB+2)
 
 __global__ void __launch_bounds__(kAttnThreads)
 k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ Vv,
@@ -310,15 +318,19 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
     bulk_g2s(smem_u32(ks), K + src, nbytes, bar);
     bulk_g2s(smem_u32(vs), Vv + src, nbytes, bar);
   }
-  const int x = qr.r0 + (int)(threadIdx.x % (unsigned)qr.rn);
-  const int rp = threadIdx.x / (unsigned)qr.rn;
-  const int y0 = r0 + 2 * rp;
-  const bool active = (rp < kAttnRB / 2) && (y0 < rend);
-  const bool two = active && (y0 + 1) < rend;
   const long long rowstride = (long long)P * 16;  // floats between consecutive y
   const int jstride = P * 4;                      // floats between the 4 pieces of one (y, x)
-  const long long base = planar_off(v, head, 0, 0, x, P);
   const float qs = 0.25f * 1.4426950408889634f;   // log2(e)/sqrt(16): softmax through exp2
+  bool staged = false;
+  // query pair idx = (row pair rp, column): one pass for regions up to 32 wide, two for 64
+#pragma unroll 1
+  for (int idx = threadIdx.x; idx < (kAttnRB / 2) * qr.rn; idx += kAttnThreads) {
+  const int rp = idx / qr.rn;
+  const int x = qr.r0 + idx - rp * qr.rn;
+  const int y0 = r0 + 2 * rp;
+  const bool active = y0 < rend;
+  const bool two = active && (y0 + 1) < rend;
+  const long long base = planar_off(v, head, 0, 0, x, P);
   f32x2 q0[8], q1[8];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -335,7 +347,7 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
   f32x2 o0[8], o1[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { o0[e] = 0ull; o1[e] = 0ull; }
-  mbar_wait(bar, 0);
+  if (!staged) { mbar_wait(bar, 0); staged = true; }
   if (active) {
 #pragma unroll
     for (int kr = 0; kr < 6; ++kr) {
@@ -417,6 +429,8 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
       }
     }
   }
+  }  // query pairs
+  if (!staged) mbar_wait(bar, 0);  // threads without a query still wait for the copies before the CTA may exit
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -712,9 +726,10 @@ int debug_timeline_spa(long long* out) {
 }
 
 int configure_spa() {
-  CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_embed<false>()));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_embed<true>()));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
-  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAttn));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
   return 0;
 }
 
@@ -742,14 +757,20 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     Scope sc(h, K_SPA_QKV, st, V * kv.rn * kv.rn);
     const unsigned ntiles = (unsigned)((G + 127) / 128);
     const unsigned pg = ntiles < 2u * h->num_sms ? ntiles : 2u * h->num_sms;  // persistent: two CTAs per SM
-    k_spa_embed_qkv<<<pg, kThreads2, kSmemSpa, st>>>(in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq, L.s_wk, L.s_wv, w.tok, w.q,
-                                                     w.k, w.v, (int)V, P, h->passes(), (int)ntiles, e, kv);
+    if (P <= ConvGeom<false>::kMaxP)
+      k_spa_embed_qkv<false><<<pg, kThreads2, smem_embed<false>(), st>>>(in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq,
+                                                                         L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P,
+                                                                         h->passes(), (int)ntiles, e, kv);
+    else
+      k_spa_embed_qkv<true><<<pg, kThreads2, smem_embed<true>(), st>>>(in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq,
+                                                                       L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P,
+                                                                       h->passes(), (int)ntiles, e, kv);
     if ((rc = sc.finish())) return rc;
   }
   {
     Scope sc(h, K_SPA_ATTN, st, V * need.rn * need.rn);
     const int nblk = (need.rn + kAttnRB - 1) / kAttnRB;
-    k_spa_attn<<<(unsigned)(V * 8 * nblk), kAttnThreads, kSmemAttn, st>>>(w.q, w.k, w.v, w.o, P, need);
+    k_spa_attn<<<(unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st>>>(w.q, w.k, w.v, w.o, P, need);
     if ((rc = sc.finish())) return rc;
   }
   {

@@ -99,7 +99,7 @@ static int num_patches_1d(int n0, int P, int S, int bdr) {
 }
 
 static int tiling(int h0, int w0, int P, int S, int* numU, int* numV) {
-  if (P < 4 || P > 32) return fail(LFT_ERR_ARG, "patch size %d unsupported (4..32)", P);
+  if (P < 4 || P > 64) return fail(LFT_ERR_ARG, "patch size %d unsupported (4..64)", P);
   if (S < 1 || S > P) return fail(LFT_ERR_ARG, "stride %d outside [1, patch size %d]", S, P);
   const int bdr = (P - S) / 2;
   if (h0 < 1 || w0 < 1 || h0 < bdr || w0 < bdr)
@@ -123,7 +123,7 @@ static int check_ready(Handle* h, int B, int P) {
   if (!h) return fail(LFT_ERR_ARG, "null handle");
   if (!h->finalized) return fail(LFT_ERR_STATE, "weights not finalized (call lft_finalize_weights)");
   if (B < 1) return fail(LFT_ERR_ARG, "B must be >= 1");
-  if (P < 4 || P > 32) return fail(LFT_ERR_ARG, "patch size P=%d unsupported (4..32, square patches only)", P);
+  if (P < 4 || P > 64) return fail(LFT_ERR_ARG, "patch size P=%d unsupported (4..64, square patches only)", P);
   return ensure_spa_pe(h, P);
 }
 

@@ -99,6 +99,13 @@ def run_tiler(ref_utils, name, A, h0, w0, s, seed, store_full):
 # test.py:83,96 pass args.patch_size_for_test / args.stride_for_test (option.py:16-17) to the tiler: hash-only goldens
 # for non-default values, incl. an odd patch-stride difference (LR border 5 but SR crop offset 11*s//2), no overlap
 # (stride == patch) and a view smaller than one patch (h0 + 2*bdr < patch: one zero-padded patch row).
+# Patches larger than 32 x 32 (--patch_size_for_test 48 / 64): the reference's PositionEncoding and gen_mask are
+# size-generic (LFT.py:91-115,147-162); dense 4096 x 4096 attention limits the golden to a few views on the CPU.
+BIG_PATCH_CASES = [  # name, A, s, h, B, seed, stages
+    ("fwd_A2_s2_h64_B1", 2, 2, 64, 1, 21, False),
+    ("fwd_A3_s4_h48_B1", 3, 4, 48, 1, 22, False),
+]
+
 TILER_PS_CASES = [  # name, A, h0, w0, s, seed, patch, stride
     ("tilerps_A3_40x56_s2_p32_s24", 3, 40, 56, 2, 5, 32, 24),
     ("tilerps_A3_40x56_s2_p32_s32", 3, 40, 56, 2, 5, 32, 32),
@@ -106,6 +113,10 @@ TILER_PS_CASES = [  # name, A, h0, w0, s, seed, patch, stride
     ("tilerps_A3_40x56_s4_p32_s21", 3, 40, 56, 4, 8, 32, 21),
     ("tilerps_A3_12x50_s2_p32_s16", 3, 12, 50, 2, 9, 32, 16),
     ("tilerps_A2_33x47_s2_p24_s10", 2, 33, 47, 2, 10, 24, 10),
+    ("tilerps_A3_80x96_s2_p64_s32", 3, 80, 96, 2, 11, 64, 32),
+    ("tilerps_A3_80x96_s2_p64_s48", 3, 80, 96, 2, 11, 64, 48),
+    ("tilerps_A5_128x128_s4_p64_s48", 5, 128, 128, 4, 2, 64, 48),
+    ("tilerps_A5_108x156_s4_p48_s32", 5, 108, 156, 4, 3, 48, 32),
 ]
 
 
@@ -172,6 +183,12 @@ SHARP_CASES = [  # name, A, s, h, B, seed, stages, qk_gain, ln_wide
 def main():
     torch.manual_seed(0)
     ref_model, ref_utils = import_reference()
+    if "--big-patch-only" in sys.argv[1:]:
+        for c in BIG_PATCH_CASES:
+            run_case(ref_model, *c)
+        for c in TILER_PS_CASES[6:]:
+            run_tiler_ps(ref_utils, *c)
+        return
     if "--lf-only" in sys.argv[1:]:         # the two full light fields (about 10 minutes of CPU time)
         for c in LF_CASES:
             run_lf(ref_model, ref_utils, *c)
@@ -194,6 +211,8 @@ def main():
         run_case(ref_model, *c)
     for c in LF_CASES:
         run_lf(ref_model, ref_utils, *c)
+    for c in BIG_PATCH_CASES:
+        run_case(ref_model, *c)
     run_tiler(ref_utils, "tiler_A3_40x56_s2", 3, 40, 56, 2, 5, True)
     run_tiler(ref_utils, "tiler_A5_108x156_s4", 5, 108, 156, 4, 3, False)
     run_tiler(ref_utils, "tiler_A5_128x128_s4", 5, 128, 128, 4, 2, False)

@@ -53,7 +53,7 @@ SHARP = ["fwd_sharp4_A5_s4_h8_B1", "fwd_sharp6_A5_s4_h8_B1", "fwd_sharp4_lnwide_
 
 
 @pytest.mark.parametrize("name", ["fwd_A5_s4_h8_B1", "fwd_A5_s2_h8_B2", "fwd_A3_s2_h12_B1", "fwd_A5_s2_h32_B1",
-                                  "fwd_A5_s4_h32_B1"] + SHARP)
+                                  "fwd_A5_s4_h32_B1", "fwd_A2_s2_h64_B1", "fwd_A3_s4_h48_B1"] + SHARP)
 def test_forward_vs_reference_golden(golden_dir, name):
     """The `fwd_sharp*` cases run peaky soft-maxes (Wq, Wk x 4 / x 6: |logit| up to 22 / 50, max probability > 0.99, wide
     LayerNorm gammas) - the regime of a trained network - through the ex2.approx soft-max, the online rescale chains and the
@@ -245,7 +245,8 @@ def test_device_tiler_bit_exact(A, h0, w0, s, seed):
 
 @pytest.mark.parametrize("A,h0,w0,s,seed,patch,stride", [
     (3, 40, 56, 2, 5, 32, 24), (3, 40, 56, 2, 5, 32, 32), (5, 44, 60, 4, 7, 16, 8), (3, 40, 56, 4, 8, 32, 21),
-    (3, 12, 50, 2, 9, 32, 16), (2, 33, 47, 2, 10, 24, 10)])
+    (3, 12, 50, 2, 9, 32, 16), (2, 33, 47, 2, 10, 24, 10), (3, 80, 96, 2, 11, 64, 32), (3, 80, 96, 2, 11, 64, 48),
+    (5, 128, 128, 4, 2, 64, 48), (5, 108, 156, 4, 3, 48, 32)])
 def test_device_tiler_patch_stride_bit_exact(A, h0, w0, s, seed, patch, stride):
     """lft_divide_ex / lft_integrate_ex for test.py's --patch_size_for_test / --stride_for_test (same cases as the
     reference-hashed goldens `tests/golden/tilerps_*`, which pin the oracle used here)."""
@@ -309,7 +310,7 @@ def test_full_light_field_vs_oracle_test_loop():
     assert torch.equal(crops, eng.forward_lf_crops(lf.cuda(), 0, 12))
 
 
-def _oracle_light_field_on_gpu(sd, lf, A, s, batch=16):
+def _oracle_light_field_on_gpu(sd, lf, A, s, batch=16, patch=32, stride=16):
     """O.infer_light_field with the per-patch forwards evaluated by the oracle's torch ops on the GPU in true fp32 (TF32
     off for cuDNN and cuBLAS): the CPU oracle needs ~2 s per patch, a full light field has 64 / 70 of them."""
     flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
@@ -317,14 +318,14 @@ def _oracle_light_field_on_gpu(sd, lf, A, s, batch=16):
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
         h0, w0 = lf.shape[0] // A, lf.shape[1] // A
-        sub = O.lf_divide(lf, A, 32, 16)
+        sub = O.lf_divide(lf, A, patch, stride)
         nu, nv = sub.shape[:2]
-        flat = sub.view(nu * nv, 1, A * 32, A * 32)
-        out = torch.empty(nu * nv, A * 32 * s, A * 32 * s)
+        flat = sub.view(nu * nv, 1, A * patch, A * patch)
+        out = torch.empty(nu * nv, A * patch * s, A * patch * s)
         with torch.no_grad():
             for i in range(0, nu * nv, batch):
                 out[i:i + batch] = O.forward(sd, flat[i:i + batch].cuda(), A, s)[:, 0].cpu()
-        sr = O.lf_integrate(out.view(nu, nv, A * 32 * s, A * 32 * s), A, 32 * s, 16 * s, h0 * s, w0 * s)
+        sr = O.lf_integrate(out.view(nu, nv, A * patch * s, A * patch * s), A, patch * s, stride * s, h0 * s, w0 * s)
         return sr.permute(0, 2, 1, 3).reshape(A * h0 * s, A * w0 * s), flat, out
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = flags
@@ -354,6 +355,40 @@ def test_full_baseline_light_fields_vs_reference_and_oracle(golden_dir, name):
     assert (cpu - out[pick]).abs().max() <= 2e-5          # the GPU-evaluated oracle is the oracle
     mine = eng.forward(flat[pick].cuda())[:, 0].cpu()
     assert (mine - cpu).abs().max() <= TOL_FP32
+
+
+@pytest.mark.parametrize("A,s,h,B", [(3, 2, 64, 2), (5, 4, 48, 1), (5, 2, 64, 1), (5, 4, 33, 2), (9, 2, 40, 1)])
+def test_large_patches_vs_oracle(A, s, h, B):
+    """patches larger than 32 x 32 (the wide conv window of k_conv3x3 / k_spa_embed_qkv, the multi-pass window
+    attention, 4096-entry position tables) against the CPU oracle; 33 is the first size on the wide path."""
+    sd = synth.synth_state_dict(A, s, 30 + A)
+    lr = torch.from_numpy(synth.synth_lr_mosaic(B, A, h, h, 30 + h))
+    ref = O.forward(sd, lr, A, s)
+    eng = _engine(A, s, sd)
+    out = eng.forward(lr.cuda())
+    assert (out.cpu() - ref).abs().max() <= TOL_FP32
+    if B > 1:
+        assert torch.equal(eng.forward(lr[1:2].cuda())[0], out[1])
+
+
+@pytest.mark.parametrize("A,s,h0,w0,patch,stride", [(3, 2, 80, 96, 64, 32), (3, 2, 80, 96, 64, 48), (5, 4, 108, 156, 48, 32)])
+def test_full_light_field_large_patches(A, s, h0, w0, patch, stride):
+    """test.py:83-101 with --patch_size_for_test 64 / 48: LightFieldSR against the oracle's test loop (patch forwards
+    evaluated by the oracle's ops on the GPU in true fp32), and the crop path against the crops of forward(divide)."""
+    from lft_b200.lightfield import LightFieldSR
+    sd = synth.synth_state_dict(A, s, 12)
+    lf = torch.from_numpy(synth.synth_light_field(A, h0, w0, 12))
+    eng = _engine(A, s, sd)
+    got = LightFieldSR(eng, patch=patch, stride=stride)(lf.cuda())
+    want, flat, out = _oracle_light_field_on_gpu(sd, lf, A, s, batch=4, patch=patch, stride=stride)
+    assert (got.cpu() - want).abs().max() <= TOL_FP32
+    n = flat.shape[0]
+    full = eng.forward(flat[:3].cuda())
+    Ps = patch * s
+    c, b = stride * s, (Ps - stride * s) // 2
+    crops = full.view(3, A, Ps, A, Ps)[:, :, b:b + c, :, b:b + c].permute(0, 1, 3, 2, 4).contiguous()
+    assert torch.equal(crops, eng.forward_lf_crops(lf.cuda(), 0, 3, patch=patch, stride=stride))
+    assert n == eng.num_patches(h0, w0, patch, stride)[0] * eng.num_patches(h0, w0, patch, stride)[1]
 
 
 def test_multi_gpu_sharded_light_field_bit_identical():

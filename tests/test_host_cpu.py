@@ -97,7 +97,7 @@ def test_c_tiling_counts_match_reference_formula():
     lib = capi.load()
     nu, nv = C.c_int32(), C.c_int32()
     checked = 0
-    for patch in (4, 8, 16, 24, 31, 32):
+    for patch in (4, 8, 16, 24, 31, 32, 48, 64):
         for stride in sorted({1, 2, patch // 2, patch - 3, patch - 1, patch}):
             if stride < 1:
                 continue
@@ -118,7 +118,7 @@ def test_c_tiling_counts_match_reference_formula():
     assert checked > 100
     # the two-argument entry point is the reference default (32, 16)
     assert lib.lft_lf_num_patches(108, 156, C.byref(nu), C.byref(nv)) == 0 and (nu.value, nv.value) == (7, 10)
-    for bad in ((64, 64, 33, 16), (64, 64, 3, 1), (64, 64, 32, 0), (64, 64, 16, 17), (3, 64, 32, 16)):
+    for bad in ((64, 64, 65, 16), (64, 64, 3, 1), (64, 64, 32, 0), (64, 64, 16, 17), (3, 64, 32, 16)):
         assert lib.lft_lf_num_patches_ex(*bad, C.byref(nu), C.byref(nv)) == -1, bad
 
 

@@ -15,7 +15,9 @@ from conftest import load_case
 FWD_CASES = ["fwd_A5_s4_h8_B1", "fwd_A5_s2_h8_B2", "fwd_A3_s2_h12_B1", "fwd_A5_s2_h32_B1",
              # sharpened soft-max (Wq, Wk x 4 / x 6: |logit| up to 22 / 50, max probability > 0.99), wide LayerNorm gammas
              "fwd_sharp4_A5_s4_h8_B1", "fwd_sharp6_A5_s4_h8_B1", "fwd_sharp4_lnwide_A5_s2_h8_B1", "fwd_sharp4_A3_s2_h12_B1",
-             "fwd_sharp4_A5_s4_h32_B1"]
+             "fwd_sharp4_A5_s4_h32_B1",
+             # patches larger than 32 x 32 (--patch_size_for_test 64 / 48)
+             "fwd_A2_s2_h64_B1", "fwd_A3_s4_h48_B1"]
 TOL = 2e-5  # fp32 op-order noise between the restatement and the reference modules
 
 
@@ -26,7 +28,7 @@ def _load(golden_dir, name):
 @pytest.mark.parametrize("name", FWD_CASES)
 @pytest.mark.parametrize("mode", ["window", "dense"])
 def test_forward_matches_reference(golden_dir, name, mode):
-    if mode == "dense" and "h32" in name:
+    if mode == "dense" and ("h32" in name or "h48" in name or "h64" in name):
         pytest.skip("dense 1024x1024 path covered by the h8/h12 cases; keeps the CPU suite short")
     g, A, s, sd, lr = _load(golden_dir, name)
     stages = {}
@@ -77,7 +79,9 @@ def test_tiler_matches_reference(golden_dir, name):
 
 
 TILER_PS = ["tilerps_A3_40x56_s2_p32_s24", "tilerps_A3_40x56_s2_p32_s32", "tilerps_A5_44x60_s4_p16_s8",
-            "tilerps_A3_40x56_s4_p32_s21", "tilerps_A3_12x50_s2_p32_s16", "tilerps_A2_33x47_s2_p24_s10"]
+            "tilerps_A3_40x56_s4_p32_s21", "tilerps_A3_12x50_s2_p32_s16", "tilerps_A2_33x47_s2_p24_s10",
+            "tilerps_A3_80x96_s2_p64_s32", "tilerps_A3_80x96_s2_p64_s48", "tilerps_A5_128x128_s4_p64_s48",
+            "tilerps_A5_108x156_s4_p48_s32"]
 
 
 @pytest.mark.parametrize("name", TILER_PS)

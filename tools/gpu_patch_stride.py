@@ -1,6 +1,7 @@
 """Full light-field inference at test.py's --patch_size_for_test / --stride_for_test settings (option.py:16-17): the
 reference default (32, 16) keeps the central 16x16 of every 32x32 patch, i.e. computes 4x the pixels it keeps; larger
-strides trade border context for throughput.  Prints a markdown table (copied to profiles/r01_patch_stride.md):
+strides trade border context for throughput; larger patches (48, 64: SURVEY 8f-3) keep the border and cut the redundancy.
+Prints a markdown table (copied to profiles/r02_patch_stride.md):
 patches per light field, ms, integrated SR MP/s, and the PSNR of each setting's output against the default's
 (the outputs differ because each patch sees less context - this is the reference's own behaviour with the same flags,
 checked against the oracle in tests/test_gpu_parity.py::test_full_light_field_patch_stride_vs_oracle)."""
@@ -29,7 +30,7 @@ def timed(fn, reps=10):
 
 base = None
 print("| patch | stride | border | patches / LF | ms / LF | integrated SR MP/s | PSNR vs (32,16) output [dB] |\n|---|---|---|---|---|---|---|")
-for patch, stride in ((32, 16), (32, 20), (32, 24), (32, 28), (32, 32), (16, 8), (24, 16)):
+for patch, stride in ((32, 16), (32, 20), (32, 24), (32, 28), (32, 32), (16, 8), (24, 16), (48, 32), (64, 32), (64, 40), (64, 48), (64, 56), (64, 64)):
     sr = LightFieldSR(eng, patch=patch, stride=stride)
     out = sr(lf)
     nu, nv = eng.num_patches(h0, w0, patch, stride)
