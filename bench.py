@@ -324,7 +324,9 @@ def main():
                               "light-field path run on the pixels the kept crop depends on only)",
                      "share_of_step": kinds[top]["ms"] / args.steps / step_kernel_ms,
                      "traffic": traffic if world == 1 else None,
-                     "traffic_unit": f"bytes/launch at N=1 (dram read+write, ncu --set full, profiles/{traffic_src})",
+                     "traffic_unit": f"bytes/launch at N=1 (dram read+write, ncu --set full, profiles/{traffic_src}); the captured launch is "
+                                     f"the first block's, which processes all {TOKENS_PER_LF} tokens of the light field (units_per_launch above "
+                                     "is the mean over the four blocks)",
                      "peak_source": pk["src"],
                      "note": ("fp32 path issues 3 bf16 MMAs per product (hi*hi+lo*hi+hi*lo): attainable frac <= 1/3"
                               if args.precision == "fp32" else "single bf16 MMA per product")})

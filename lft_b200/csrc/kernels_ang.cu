@@ -222,11 +222,16 @@ LFT_DEVINL void ang_attn_item25(const f32x2* q, const ulonglong2* __restrict__ k
 }
 
 // A = 5 (25 views per pixel, 5 pixels per tile): the attention of a tile is re-mapped from the row owners to
-// (pixel, head) work items so that a WARP works on ONE pixel and one head with lane = query view: all lanes then read the
-// same key / value at the same time and every shared-memory load is a broadcast (one wavefront per 16 bytes per warp instead
-// of one per quarter-warp and row - the row-owner formulation, even with two views sharing each read, was bound by exactly that
-// traffic: 126 M wavefronts per launch, ~80 % of the kernel).  Rows stay view-major (global accesses of the owners stay
-// coalesced); Q, K and V leave the accumulators through shared memory, one head half (4 heads) at a time:
+// (pixel, head) work items: a WARP works on ONE pixel and one head with lane = query view, so all lanes read the same key /
+// value at the same time (uniform-address LDS.128) and no query pairing, partner shuffles or "single view" pass are needed.
+// Measured against the paired row-owner formulation of round 1 (profiles/r02_counters.md): the same time per launch within
+// 3 % (1.11 vs 1.08 ms under ncu), 156 M instead of 126 M shared-memory wavefronts (a uniform 16-byte load still costs two
+// wavefronts; 25 of 32 lanes are used and 20 items leave 8 warps a third, partly filled round), L1/shared pipe 69 %, issue
+// 44 %: the per-pixel 25 x 25 x 8 attention stays bound by the shared-memory pipe whichever way the work is mapped - each
+// key / value row must reach 25 queries through it.  Kept because it is the simpler formulation (and the basis for a
+// tensor-core S = Q K^T, which needs the same data movement).
+// Rows stay view-major (global accesses of the owners stay coalesced); Q, K and V leave the accumulators through shared
+// memory, one head half (4 heads) at a time:
 //   R2: K [rel head 4][half 2][kv row 128][16 B] 16 KB | V 16 KB         (kv row = view * 5 + pixel)
 //   R1: Q / O of head half 0 (16 KB, same layout, O overwrites Q in place) | of head half 1 (16 KB)
 // per half g: export (thread 0 of a row: K, thread 1: V and Q, both with the LayerNorm-fold correction) | barrier | 20 items

@@ -104,24 +104,34 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     auto shift = [P1](uint32_t t) { return ((int)(t / 3) - 1) * P1 + ((int)(t % 3) - 1); };
     const uint32_t ta_hi = tmem + 128, ta_lo = tmem + 192;
     for (int k = 0; k < ntl; ++k) {
+      LFT_TL2(10);
       mbar_wait(f_ready, k & 1);
+      LFT_TL2(11);
       if (k > 0) { mbar_wait(a_ready, rpar); rpar ^= 1; }  // V of the previous tile drained: D[0,128) is free
       tc_fence_after();
+      LFT_TL2(12);
       ring_consume_mma<NST>(rs, ring, kSpaStage, full0, empty0, g_c, passes, c_hi + kConvOff * 16,
                                 c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
       umma_commit_elected(mma_done);
+      LFT_TL2(13);
       mbar_wait(a_ready, rpar); rpar ^= 1;
       tc_fence_after();
+      LFT_TL2(14);
       ring_consume_mma_ts<NST>(rs, ring, kSpaStage, full0, empty0, g_q, passes, ta_hi, ta_lo, tmem + 0, true);
       umma_commit_elected(mma_done);
+      LFT_TL2(15);
       mbar_wait(a_ready, rpar); rpar ^= 1;
       tc_fence_after();
+      LFT_TL2(16);
       ring_consume_mma_ts<NST>(rs, ring, kSpaStage, full0, empty0, g_k, passes, ta_hi, ta_lo, tmem + 0, true);
       umma_commit_elected(mma_done);
+      LFT_TL2(17);
       mbar_wait(a_ready, rpar); rpar ^= 1;
       tc_fence_after();
+      LFT_TL2(18);
       ring_consume_mma_ts<NST>(rs, ring, kSpaStage, full0, empty0, g_v, passes, ta_hi, ta_lo, tmem + 0, true);
       umma_commit_elected(mma_done);
+      LFT_TL2(19);
     }
   } else {
     const int m = (warp & 3) * 32 + lane, q = warp >> 2;
@@ -141,6 +151,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     };
     if (ntl > 0) stage(0);
     for (int k = 0; k < ntl; ++k) {
+      LFT_TL2(0);
       const long long g = (long long)(first + k * step) * 128 + m;
       bool ok = false;
       long long v = 0;
@@ -158,8 +169,11 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
 #ifdef LFT_EXPERIMENT_NOSTORE
       ok = false;  // timing experiment: no global stores at all
 #endif
+#ifdef LFT_EXPERIMENT_SMALLSTORE
+      v = v & 7;   // timing experiment (wrong results): every store lands in the first 8 views' planes (L2-resident, 5 MB)
+#endif
       const int p = y * P + x;
-      const long long token = (v * P + y) * P + x;
+      const long long token = (v * P + y) * P + x;   // (SMALLSTORE experiment: v was folded above, PE index p is unaffected)
       float mean, rstd;
       {
         float z[64];
@@ -169,6 +183,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
           z[4 * i] = b.x; z[4 * i + 1] = b.y; z[4 * i + 2] = b.z; z[4 * i + 3] = b.w;
         }
         await();  // conv
+        LFT_TL2(1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float t[16];
@@ -188,9 +203,12 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(a_ready);             // z ready
+      LFT_TL2(2);
       if (k + 1 < ntl) stage(k + 1);    // the staging area is free (conv MMAs of this tile are complete)
+      LFT_TL2(3);
       const float mr = mean * rstd;
       await();  // Q
+      LFT_TL2(4);
       {
         float dd[64];
 #pragma unroll
@@ -213,7 +231,9 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
           if (ok) planar_store16(Q, v, 4 * q + c, y, x, P, d);
         }
       }
+      LFT_TL2(5);
       await();  // K
+      LFT_TL2(6);
       {
         float dd[64];
 #pragma unroll
@@ -236,7 +256,9 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
           if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
         }
       }
+      LFT_TL2(7);
       await();  // V
+      LFT_TL2(8);
       {
         float dd[64];
 #pragma unroll
@@ -255,6 +277,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
           if (ok) planar_store16(Vv, v, 4 * q + c, y, x, P, d);
         }
       }
+      LFT_TL2(9);
     }
     tc_fence_before();
   }
