@@ -30,9 +30,7 @@ struct Region {
 };
 
 enum Kind {
-  K_CONV0 = 0,
-  K_CONV64,
-  K_CONV128,
+  K_CONV64 = 0,
   K_ANG,
   K_SPA_QKV,
   K_SPA_ATTN,

@@ -718,6 +718,264 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
   LFT_TL(31);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_spa_ffn, second formulation (round 2; the default, -DLFT_FFN_V1 selects the one above).  Same arithmetic, different residency:
+//   * the FFN is evaluated half by half - FFN1a -> hidden_a -> FFN2a, then FFN1b -> hidden_b -> FFN2b - so that BOTH hidden
+//     halves become tcgen05 TS operands in TMEM columns [128,256) (the first formulation wrote hidden_a to shared memory: 64
+//     st.shared.v4 per thread through the port the MMA operands are read from, 5.6 K of its 33.7 K cycles per tile), and
+//   * Y1 (the residual stream after the attention) is never spilled to global memory: its bf16 hi/lo operand stays in shared
+//     memory from FFN1a to the end (nothing overwrites it any more) and Y2 = (Y1_hi + Y1_lo) + FFN2 reconstructs it - the
+//     pair carries Y1 to 2^-17 relative, the accuracy class of every three-pass product here (in bf16 mode the hi part alone
+//     would be a 2^-9 error on the residual, so that mode keeps the spill).  1 KB / token less HBM traffic.
+//   TMEM: D = [0,128) accumulator, T = [128,256) TS operand (hi [128,192) | lo [192,256)) and, for FFN1b, accumulator.
+//   Row phases / a_ready arrivals (each separated from the next by a wait on an MMA that needed the previous one complete):
+//     O -> T | Y1 -> smem A (+ LN2 statistics) | hidden_a -> T | hidden_b -> T (in place over the FFN1b accumulator) | Y2 -> T
+//   MMA phases / mma_done commits: D = O Wo^T | D = Y1 W1a^T | D = hidden_a W2a^T, T = Y1 W1b^T | D += hidden_b W2b^T | D = Y2 Wlin^T
+//   (FFN1b's accumulator is the region FFN2a reads its operand from: the MMA thread waits for FFN2a's own commit - aux[1] - first.)
+__global__ void __launch_bounds__(kThreads2, 2)
+k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_constant__ Tab512 tab,
+           const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1a, const uint8_t* __restrict__ w1b,
+           const uint8_t* __restrict__ w2a, const uint8_t* __restrict__ w2b, const uint8_t* __restrict__ wlin,
+           float* __restrict__ out, const float* __restrict__ final_res, long long T, int P, int passes, Region fr) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem);
+  const uint32_t A = smem_u32(smem) + kCtlBytes;
+  const uint32_t ring = A + 65536;
+  const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
+  const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
+  const uint32_t f2a_done = smem_u32(&ctl->aux[1]);  // completed by one tcgen05.commit (re-initialised below)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
+  if (tid == 0) {
+    mbar_init(f2a_done, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const uint32_t tmem = ctl->tmem;
+  const GemmPhase g_o{wo, 128, 2}, g_1a{w1a, 128, 2}, g_2a{w2a, 128, 2}, g_1b{w1b, 128, 2}, g_2b{w2b, 128, 2},
+      g_l{wlin, 64, 2};
+  const bool fp32m = passes == 3;
+
+  if (warp == kWarpProducer2) {
+    RingState<kSpaNST> rs;  // consumption order
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_o, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_1a, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2a, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_1b, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2b, passes);
+    ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_l, passes);
+  } else if (warp == kWarpMma2) {
+    RingState<kSpaNST> rs;
+    uint32_t par = 0;
+    auto wait_a = [&]() {
+      mbar_wait(a_ready, par);
+      par ^= 1;
+      tc_fence_after();
+    };
+    auto gemm_ss = [&](const GemmPhase& g, uint32_t dcol) {   // A = Y1 operand in shared memory
+      ring_consume_mma<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g, passes, A, A + 32768, kLbo, 8 * kLbo, NoShift{},
+                                tmem + dcol, true);
+    };
+    auto gemm_ts = [&](const GemmPhase& g, bool fresh) {      // A = TS operand in T, accumulator D
+      ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g, passes, tmem + 128, tmem + 192, tmem + 0, fresh);
+    };
+    auto done = [&]() { umma_commit_elected(mma_done); };
+    wait_a(); gemm_ts(g_o, true); done();            // D = O Wo^T
+    wait_a(); gemm_ss(g_1a, 0); done();              // D = Y1 W'1a^T
+    wait_a(); gemm_ts(g_2a, true);                   // D = hidden_a W2a^T
+    umma_commit_elected(f2a_done);
+    mbar_wait(f2a_done, 0);                          // FFN2a has read its operand: T may become FFN1b's accumulator
+    tc_fence_after();
+    gemm_ss(g_1b, 128); done();                      // T = Y1 W'1b^T   (one commit covers FFN2a as well)
+    wait_a(); gemm_ts(g_2b, false); done();          // D += hidden_b W2b^T
+    wait_a(); gemm_ts(g_l, true); done();            // D[0,64) = Y2 Wlin^T
+  } else {
+    const int m = (warp & 3) * 32 + lane, q = warp >> 2;
+    const long long t = (long long)blockIdx.x * 128 + m;
+    const bool ok = t < T;
+    const unsigned PP = (unsigned)(P * P), RR = (unsigned)(fr.rn * fr.rn);
+    auto locate = [&](unsigned tc, unsigned& vu, int& y, int& x) {
+      vu = tc / RR;
+      const int rem = (int)(tc - vu * RR);
+      const int yy = rem / fr.rn;
+      y = fr.r0 + yy;
+      x = fr.r0 + rem - yy * fr.rn;
+      return vu * PP + (unsigned)(y * P + x);
+    };
+    unsigned vu;
+    int y, x;
+    const unsigned tt = locate(ok ? (unsigned)t : 0u, vu, y, x);
+    const long long v = vu;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* trow_g = tok + t32_off(tt, 16 * q, 32);  // own half of the token row, chunk stride 128 floats
+    uint32_t par = 0;
+    auto await = [&]() {
+      mbar_wait(mma_done, par);
+      par ^= 1;
+      tc_fence_after();
+    };
+    auto publish_tmem = [&]() {  // operand written with tcgen05.st
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // phase 0: T <- O (planar gather of own heads 4q..4q+3)
+    {
+      float4 f[16];
+      const float* ob = O + planar_off(v, 4 * q, y, 0, x, P);
+      const long long hs = (long long)PP * 16, js = (long long)P * 4;  // head / piece strides in floats
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[4 * c + j] = ok ? __ldg(reinterpret_cast<const float4*>(ob + c * hs + j * js)) : zero4;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, reinterpret_cast<const float*>(&f[4 * c]), fp32m);
+    }
+    publish_tmem();
+
+    // phase 1: Y1 = tok + D (own half) -> bf16 hi/lo operand in shared memory (kept until the end); LN2 statistics
+    float mean, rstd;
+    {
+      float4 tk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tk[i] = ok ? __ldg(reinterpret_cast<const float4*>(trow_g + 128 * i)) : zero4;  // in flight
+      await();
+      float yv[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + 64 * q + 16 * c, yv + 16 * c);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        yv[4 * i] += tk[i].x; yv[4 * i + 1] += tk[i].y; yv[4 * i + 2] += tk[i].z; yv[4 * i + 3] += tk[i].w;
+      }
+      if (!fp32m && ok) {  // bf16 mode: the hi part alone cannot carry the residual, keep the fp32 copy in `tok`
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          *reinterpret_cast<float4*>(trow_g + 128 * i) = make_float4(yv[4 * i], yv[4 * i + 1], yv[4 * i + 2], yv[4 * i + 3]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a_store16(A, 8 * q + 2 * c, m, yv + 16 * c, fp32m);
+      pair_ln_stats<64>(yv, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(a_ready);
+    const float mr = mean * rstd;
+    const float4* u1 = reinterpret_cast<const float4*>(tab.v);        // [u_1 256 | c_1 256] (constant bank)
+    const float4* c1 = reinterpret_cast<const float4*>(tab.v + 256);
+
+    {  // speculative L2 prefetch of the O pieces and token row of the tile 2 CTAs x 148 SMs ahead
+      const long long tn = t + 296ll * 128;
+      if (tn < T) {
+        unsigned vn;
+        int yn, xn;
+        const unsigned tnu = locate((unsigned)tn, vn, yn, xn);
+        const float* obn = O + planar_off(vn, 4 * q, yn, 0, xn, P);
+        const long long hs = (long long)PP * 16, js = (long long)P * 4;
+        const float* tgn = tok + t32_off(tnu, 16 * q, 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) prefetch_l2(obn + c * hs + j * js);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) prefetch_l2(tgn + 128 * i);
+      }
+    }
+
+    // phases 2 / 3: hidden half (own 64 columns of the accumulator at column `acc`) -> relu(LN2-folded) -> T
+    auto hidden = [&](uint32_t acc, int tab_off, bool in_place) {
+      float hv[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + acc + 64 * q + 16 * c, hv + 16 * c);
+      tmem_wait_ld();
+      if (in_place) {  // the operand overwrites the accumulator: the partner thread must have read its half first
+        tc_fence_before();
+        pair_bar_sync(warp & 3);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 uv = u1[tab_off + 16 * q + j], cv = c1[tab_off + 16 * q + j];
+        hv[4 * j] = fmaxf(fmaf(rstd, hv[4 * j], fmaf(-mr, uv.x, cv.x)), 0.f);
+        hv[4 * j + 1] = fmaxf(fmaf(rstd, hv[4 * j + 1], fmaf(-mr, uv.y, cv.y)), 0.f);
+        hv[4 * j + 2] = fmaxf(fmaf(rstd, hv[4 * j + 2], fmaf(-mr, uv.z, cv.z)), 0.f);
+        hv[4 * j + 3] = fmaxf(fmaf(rstd, hv[4 * j + 3], fmaf(-mr, uv.w, cv.w)), 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, hv + 16 * c, fp32m);
+    };
+    await();                 // FFN1a
+    hidden(0, 0, false);     // T held the O operand, consumed by the out-projection (complete: FFN1a was issued after it)
+    publish_tmem();
+    await();                 // FFN2a (D) and FFN1b (T)
+    hidden(128, 32, true);
+    publish_tmem();
+
+    // phase 4: Y2 = Y1 + D -> T.  Y1 from its hi/lo operand in shared memory (fp32 mode) or from the spilled row (bf16 mode).
+    {
+      float y1[64];
+      if (fp32m) {
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) {
+          uint4 hi, lo;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(A + (8 * q + kc) * kLbo + m * 16));
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(A + 32768 + (8 * q + kc) * kLbo + m * 16));
+          const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {  // bf16 pair -> two fp32 (a bf16 is the top half of an fp32)
+            y1[8 * kc + 2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
+            y1[8 * kc + 2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 f = ok ? *reinterpret_cast<const float4*>(trow_g + 128 * i) : zero4;
+          y1[4 * i] = f.x; y1[4 * i + 1] = f.y; y1[4 * i + 2] = f.z; y1[4 * i + 3] = f.w;
+        }
+      }
+      await();               // FFN2b
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float d[16];
+        tmem_ld16(trow + 64 * q + 16 * c, d);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) d[j] += y1[16 * c + j];
+        a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, d, fp32m);
+      }
+    }
+    publish_tmem();
+
+    // phase 5: out = D[0,64) (+ global residual), own 32 columns
+    float4 r4[8];
+    if (final_res) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        r4[i] = ok ? __ldg(reinterpret_cast<const float4*>(final_res + t32_off(tt, 8 * q + i, 16))) : zero4;
+    }
+    await();
+    {
+      float d[32];
+      tmem_ld16_nowait(trow + 32 * q, d);
+      tmem_ld16_nowait(trow + 32 * q + 16, d + 16);
+      tmem_wait_ld();
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 o4 = make_float4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+          if (final_res) { o4.x += r4[i].x; o4.y += r4[i].y; o4.z += r4[i].z; o4.w += r4[i].w; }
+          *reinterpret_cast<float4*>(out + t32_off(tt, 8 * q + i, 16)) = o4;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  cta_teardown(ctl, warp, 256, kWarpMma2);
+}
+
 int debug_timeline_ring_embed(long long* out) {  // out[40*3]
 #ifdef LFT_TIMELINE
   CUDA_TRY(cudaMemcpyFromSymbol(out, g_ring_tl, sizeof(long long) * 120));
@@ -752,6 +1010,7 @@ int configure_spa() {
   CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_embed<false>()));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_embed<true>()));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
   return 0;
 }
@@ -801,9 +1060,15 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     memcpy(tf.v, L.s_tab[h->mode()].data() + 512, sizeof(tf.v));  // [u_1 256 | c_1 256]
     const long long T = V * need.rn * need.rn;
     Scope sc(h, K_SPA_FFN, st, T);
+#ifdef LFT_FFN_V1
     k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
                                                                         L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P,
                                                                         h->passes(), need);
+#else
+    k_spa_ffn2<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
+                                                                         L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P,
+                                                                         h->passes(), need);
+#endif
     if ((rc = sc.finish())) return rc;
   }
   return 0;

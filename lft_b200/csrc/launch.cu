@@ -7,8 +7,8 @@
 
 namespace lft {
 
-const char* const kKindNames[K_COUNT] = {"conv0",    "conv3x3_64", "conv3x3_128", "ang_fused", "spa_embed_qkv", "spa_attn",
-                                         "spa_ffn",  "up_gemm",    "up_gather",   "lf_divide", "lf_integrate"};
+const char* const kKindNames[K_COUNT] = {"conv3x3_64", "ang_fused", "spa_embed_qkv", "spa_attn", "spa_ffn",
+                                         "up_gemm",    "up_gather", "lf_divide",     "lf_integrate"};
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: configure every device a handle is created on once
 // (the caller has made `device` current).
