@@ -13,6 +13,7 @@ from __future__ import annotations
 from typing import Iterable, List, Optional, Tuple
 
 import torch
+import torch.utils.data
 
 from .lightfield import LightFieldSR
 
@@ -55,6 +56,49 @@ def ssim_per_view(sr_sai: torch.Tensor, hr_sai: torch.Tensor, angRes: int, data_
             smap = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))
             out[u, v] = smap[pad:H - pad, pad:W - pad].mean()
     return torch.from_numpy(out)
+
+
+class TestSetDataLoader(torch.utils.data.Dataset):
+    """The h5 test-set reader of utils_datasets.py:67-98: every file of `<path_for_test>SR_<A>x<A>_<s>x/<data_name>/` holds
+    `Lr_SAI_y` / `Hr_SAI_y` (written by the MATLAB preparation column-major, hence the transpose at :86-87); items are
+    `([1, A*h0, A*w0], [1, A*h0*s, A*w0*s])` float tensors like `ToTensor()` of a 2-D array gives.  Needs `h5py`, which the
+    authoring image lacks: the import is deferred to the first item and fails loudly there (tests feed a stand-in module)."""
+
+    def __init__(self, args, data_name: str = "ALL"):
+        import os
+        self.dataset_dir = f"{args.path_for_test}SR_{args.angRes}x{args.angRes}_{args.scale_factor}x/"
+        self.file_list = [data_name + "/" + f for f in os.listdir(self.dataset_dir + data_name)]
+        self.item_num = len(self.file_list)
+
+    def __getitem__(self, index):
+        import numpy as np
+        try:
+            import h5py
+        except ImportError as e:   # no fallback format: the reference's test sets are h5 files
+            raise ImportError("lft_b200.evalloop.TestSetDataLoader needs h5py to read the reference's test sets") from e
+        with h5py.File(self.dataset_dir + self.file_list[index], "r") as hf:
+            lr = np.transpose(np.array(hf.get("Lr_SAI_y")), (1, 0))
+            hr = np.transpose(np.array(hf.get("Hr_SAI_y")), (1, 0))
+        return torch.from_numpy(lr.copy()).float()[None], torch.from_numpy(hr.copy()).float()[None]
+
+    def __len__(self):
+        return self.item_num
+
+
+def MultiTestSetDataLoader(args):
+    """utils_datasets.py:40-64: one batch-size-1 loader per test set found under the data directory (every sub-directory,
+    like the reference's `os.listdir`; sorted here so that the order does not depend on the file system)
+    -> (names, loaders, number of scenes)."""
+    import os
+    from torch.utils.data import DataLoader
+    dataset_dir = f"{args.path_for_test}SR_{args.angRes}x{args.angRes}_{args.scale_factor}x/"
+    data_list = sorted(os.listdir(dataset_dir))
+    loaders, n = [], 0
+    for name in data_list:
+        ds = TestSetDataLoader(args, name)
+        n += len(ds)
+        loaders.append(DataLoader(dataset=ds, num_workers=getattr(args, "num_workers", 0), batch_size=1, shuffle=False))
+    return data_list, loaders, n
 
 
 def cal_metrics(angRes: int, label: torch.Tensor, out: torch.Tensor) -> Tuple[float, float]:

@@ -93,9 +93,17 @@ class LightFieldSR:
         return self._src.engine(device)
 
     def close(self) -> None:
-        """Unmap / free the peer buffers (collective: call on every rank)."""
-        for b in self._peer.values():
-            if b is not None:
+        """Unmap / free the peer buffers (collective: call on every rank).  The peers unmap first, a barrier, then the owner
+        frees - a mapping must not outlive the allocation it maps."""
+        bufs = [b for b in self._peer.values() if b is not None]
+        for b in bufs:
+            if not b.owner:
+                b.close()
+        if bufs and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+        for b in bufs:
+            if b.owner:
                 b.close()
         self._peer = {}
 

@@ -298,3 +298,41 @@ def test_light_field_sharding_world2_gloo(patch, stride):
     for p in procs:
         p.join(60)
     assert all(res)
+
+
+def test_h5_test_set_reader_with_stand_in_h5py(tmp_path, monkeypatch):
+    """evalloop.TestSetDataLoader / MultiTestSetDataLoader (utils_datasets.py:40-98): directory layout, the column-major
+    transpose and the item shapes, with a stand-in `h5py` (the real one is absent here) that serves .npz files."""
+    import sys
+    import types as _t
+    from lft_b200 import evalloop as E
+    A, s, h0, w0 = 3, 2, 6, 10
+    root = tmp_path / "data_for_test"
+    for ds, n in (("HCI_new", 2), ("EPFL", 1)):
+        d = root / f"SR_{A}x{A}_{s}x" / ds
+        d.mkdir(parents=True)
+        for i in range(n):
+            lr = np.arange(A * h0 * A * w0, dtype=np.float32).reshape(A * h0, A * w0) + i
+            hr = np.arange(A * h0 * s * A * w0 * s, dtype=np.float32).reshape(A * h0 * s, A * w0 * s) - i
+            np.savez(d / f"scene{i}.h5", Lr_SAI_y=lr.T, Hr_SAI_y=hr.T)           # stored transposed, like MATLAB's h5write
+            (d / f"scene{i}.h5.npz").rename(d / f"scene{i}.h5")
+
+    class _File:
+        def __init__(self, path, mode):
+            self._z = np.load(path)
+        def __enter__(self):
+            return self
+        def __exit__(self, *a):
+            self._z.close()
+        def get(self, k):
+            return self._z[k]
+    fake = _t.ModuleType("h5py")
+    fake.File = _File
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    args = _t.SimpleNamespace(path_for_test=str(root) + "/", angRes=A, scale_factor=s, data_name="ALL", num_workers=0)
+    names, loaders, n = E.MultiTestSetDataLoader(args)
+    assert names == ["EPFL", "HCI_new"] and n == 3 and [len(l) for l in loaders] == [1, 2]
+    lr, hr = next(iter(loaders[1]))
+    assert tuple(lr.shape) == (1, 1, A * h0, A * w0) and tuple(hr.shape) == (1, 1, A * h0 * s, A * w0 * s)
+    assert float(lr[0, 0, 0, 1]) in (1.0, 2.0) and float(lr[0, 0, 1, 0]) in (A * w0, A * w0 + 1.0)   # row-major again
+    assert len(E.TestSetDataLoader(args, "EPFL")) == 1
