@@ -239,7 +239,6 @@ def main():
     if rank == 0:
         sampler.start()
     n0 = eng.launch_count()
-    eng.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     e0.record()
@@ -249,6 +248,17 @@ def main():
     sync()
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count() - n0
+    # per-kernel durations: the same K steps once more with the library's per-launch CUDA events (an event between two
+    # kernels serialises them, so this pass runs without programmatic dependent launch; its step time is reported too)
+    eng.profile_enable(True)
+    p0_, p1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    p0_.record()
+    for i in range(args.steps):
+        step()
+    p1_.record()
+    sync()
+    profiled_ms = max_over_ranks(p0_.elapsed_time(p1_))
     prof = eng.profile_read()
     eng.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -345,6 +355,10 @@ def main():
                     "what": "lightfield.HostPipeline: every rank uploads the LR light field from pinned host memory, rank 0 "
                             "downloads the assembled SR light field into pinned host memory; copies overlap the next step's kernels"},
             "gpu_launches": launches_all, "clocks": clocks, "roofline": roof, "assembly": assembled,
+            "kernel_timing": {"ms_per_step_with_events": profiled_ms / args.steps,
+                              "what": "roofline / kernels come from a second pass of the same K steps with per-launch CUDA events on the "
+                                      "launching stream; `value` / `ms_per_step` from the first pass without them (kernels chained by "
+                                      "programmatic dependent launch)"},
             "patches_per_rank": [b - a for a, b in patch_ranges(PATCHES, world)],
             "whole_step": {"reference_work_tflops": whole_ref, "frac_of_bf16_peak": whole_ref / (pk["tensor"] * world),
                            "executed_tflops_rank0": executed / (total_ms * 1e-3) / 1e12,

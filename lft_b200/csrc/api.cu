@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace lft {
@@ -409,6 +410,10 @@ int lft_create(const lft_config* cfg, lft_handle** out) {
   Handle* h = new Handle();
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
+  {  // programmatic dependent launch: built, measured, off by default (see host.h) - LFT_PDL=1 turns it on
+    const char* e = getenv("LFT_PDL");
+    h->pdl = e && e[0] && e[0] != '0';
+  }
   build_spec(h);
   int rc = configure_kernels(cfg->device);
   if (rc) { delete h; return rc; }

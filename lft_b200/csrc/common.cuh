@@ -84,6 +84,15 @@ LFT_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uin
       : "memory");
 }
 
+// Programmatic dependent launch (launch attribute programmaticStreamSerialization, set by LFT_LAUNCH in host.h): a kernel
+// lets the next kernel of the stream start its CTAs - barrier set-up, TMEM allocation, first weight slabs - while it is still
+// running (pdl_trigger, called by every thread at the top), and every thread of the next kernel calls pdl_wait before its
+// first access to global memory another kernel may have written: the wait returns once the preceding kernel has completed
+// and its writes are visible.  Without the attribute both instructions are no-ops - which is the default: the mechanism is
+// correct (all tests pass with LFT_PDL=1) but measured slower on this workload (host.h, LFT_LAUNCH).
+LFT_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+LFT_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 LFT_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------- TMEM

@@ -104,6 +104,7 @@ struct Handle {
   const uint8_t* w_up3 = nullptr;  // upsampling.3.weight packed as a [16 x 64] bf16 hi/lo B operand (rows 9..15 zero)
   const float* pe_ang = nullptr;
   int pe_P = -1;
+  bool pdl = false;                // programmatic dependent launch between the kernels of a forward (LFT_PDL=1 enables)
   bool profiling = false;
   std::vector<ProfEvent> events;   // event pool: created once, reused by every profiling session
   size_t n_events = 0;             // events of the current session
@@ -116,6 +117,28 @@ struct Handle {
 int upload(Handle* h, const void* src, size_t bytes, void** dst);
 int ensure_spa_pe(Handle* h, int P);
 std::vector<uint16_t> pack_weight(int N, int Npad, int K, const std::function<float(int, int)>& w);
+
+// Kernel launch, optionally with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait in common.cuh).
+// Measured on the benchmark (profiles/r02_pdl_ab.md): all parity / repeatability tests pass with it, but the step gets SLOWER -
+// 2.310 vs 2.273 ms at N = 8 (two runs each, identical to 1e-3), no difference beyond noise at N = 1: the kernels are persistent
+// grids that fill every CTA slot, so a dependent's CTAs only get on an SM when one of the running kernel's CTAs retires early, and
+// then hold TMEM / shared memory and poll while that SM's other CTA finishes; launch gaps were not the cost they looked like
+// (the per-launch profiling events were: 2.40 vs 2.27 ms per step at N = 8 with / without them).  Hence off by default.
+// The attribute is dropped while per-launch profiling events are recorded: an event between two kernels serialises them anyway.
+#define LFT_LAUNCH(h, kernel, grid, block, smem, st, ...)                                             \
+  do {                                                                                                \
+    cudaLaunchConfig_t cfg_ = {};                                                                     \
+    cfg_.gridDim = dim3(grid);                                                                        \
+    cfg_.blockDim = dim3(block);                                                                      \
+    cfg_.dynamicSmemBytes = (smem);                                                                   \
+    cfg_.stream = (st);                                                                               \
+    cudaLaunchAttribute at_[1];                                                                       \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                   \
+    at_[0].val.programmaticStreamSerializationAllowed = 1;                                            \
+    cfg_.attrs = at_;                                                                                 \
+    cfg_.numAttrs = ((h)->pdl && !(h)->profiling) ? 1 : 0;                                            \
+    cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                                   \
+  } while (0)
 
 struct Scope {  // profiling + launch accounting around one kernel launch
   Handle* h;

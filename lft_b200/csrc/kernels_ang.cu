@@ -371,6 +371,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t LBO = 128 * 16;
 
+  pdl_trigger();
   cta_setup<kAngNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
 
@@ -477,6 +478,7 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
     };
     // persistent: the CTA walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ... keeping its TMEM, barriers and the
     // weight ring (which already holds the next tile's first slabs when its phase 0 publishes)
+    pdl_wait();  // `in` is the previous kernel's output
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long tok_or = row_token(tile);
     const bool rowok = tok_or >= 0;
@@ -826,8 +828,11 @@ int run_ang(Handle* h, int layer, const float* in, float* out, int B, int P, Reg
   memcpy(ta.v, L.a_tab[h->mode()].data(), sizeof(ta.v));
   Scope sc(h, K_ANG, st, npix * N);
 #define LFT_ANG_LAUNCH(NV)                                                                                          \
-  k_ang<NV><<<grid, kThreads2, kSmemAng, st>>>(in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, ta, L.a_peqk[h->mode()], \
-                                               h->pe_ang, N, P, npix, h->passes(), (int)ntiles, rg)
+  do {                                                                                                              \
+    auto kern = k_ang<NV>;                                                                                          \
+    LFT_LAUNCH(h, kern, grid, kThreads2, kSmemAng, st, in, out, L.a_wqk, L.a_wv, L.a_wo, L.a_w1, L.a_w2, ta,        \
+               L.a_peqk[h->mode()], h->pe_ang, N, P, npix, h->passes(), (int)ntiles, rg);                           \
+  } while (0)
   if (N == 25) LFT_ANG_LAUNCH(25);
   else if (N == 9) LFT_ANG_LAUNCH(9);
   else if (N == 49) LFT_ANG_LAUNCH(49);

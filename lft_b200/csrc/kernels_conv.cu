@@ -13,6 +13,8 @@ namespace lft {
 // Layout conversion for the stage-level entry points: channels-last [T][C] <-> T32.
 __global__ void __launch_bounds__(256) k_layout(const float* __restrict__ in, float* __restrict__ out, long long T,
                                                int C4, int to_t32) {
+  pdl_trigger();
+  pdl_wait();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4
   if (gid >= T * C4) return;
   long long t;
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(256) k_layout(const float* __restrict__ in, fl
 
 int launch_layout(Handle* h, const float* in, float* out, long long T, int C, int to_t32, cudaStream_t st) {
   const long long n = T * (C / 4);
-  k_layout<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, T, C / 4, to_t32);
+  LFT_LAUNCH(h, k_layout, (unsigned)((n + 255) / 256), 256, 0, st, in, out, T, C / 4, to_t32);
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LFT_ERR_CUDA, "k_layout launch failed: %s", cudaGetErrorString(e));
@@ -154,6 +156,7 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
   const int first = blockIdx.x, step = gridDim.x;
   const int ntl = first < ntiles ? (ntiles - first + step - 1) / step : 0;
 
+  pdl_trigger();
   cta_setup<NST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
   const bool stacked = passes == 3;
@@ -224,6 +227,7 @@ k_conv3x3(const float* __restrict__ in, const uint8_t* __restrict__ wp, float* _
       fence_proxy_async_smem();
       mbar_arrive(a_ready);
     };
+    pdl_wait();  // the input feature map / LR patches are the previous kernel's output (weights are not: the producer runs ahead)
     if (ntl > 0) stage(0);
 
     // ---- epilogue: row m <-> position, column half q
@@ -531,10 +535,13 @@ int launch_conv3x3(Handle* h, int N, const float* in, const uint8_t* wp, const u
   memcpy(w0.w, h->w_conv0_host.data(), sizeof(w0.w));
   Scope sc(h, K_CONV64, st, (long long)V * P * P);
   if (N != 64) return fail(LFT_ERR_ARG, "launch_conv3x3: only the 64 -> 64 conv stack uses this kernel (the 64 -> 128 token embedding is part of k_spa_embed_qkv)");
-  if (P <= ConvGeom<false>::kMaxP)
-    k_conv3x3<64, false><<<grid, kThreads2, smem_conv64<false>(), st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst, (int)ntiles);
-  else
-    k_conv3x3<64, true><<<grid, kThreads2, smem_conv64<true>(), st>>>(in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst, (int)ntiles);
+  if (P <= ConvGeom<false>::kMaxP) {
+    auto kern = k_conv3x3<64, false>;
+    LFT_LAUNCH(h, kern, grid, kThreads2, smem_conv64<false>(), st, in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst, (int)ntiles);
+  } else {
+    auto kern = k_conv3x3<64, true>;
+    LFT_LAUNCH(h, kern, grid, kThreads2, smem_conv64<true>(), st, in, wp, out, res, V, P, h->passes(), epi, lr, w0, h->cfg.ang_res, wst, (int)ntiles);
+  }
   return sc.finish();
 }
 

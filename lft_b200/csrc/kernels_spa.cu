@@ -84,6 +84,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
   const int P1 = e.rn + 1;
   const long long VS = (long long)P1 * P1;
   const long long G = (long long)V * VS;
+  pdl_trigger();
   cta_setup<NST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
   const GemmPhase g_c{wmlp, 128, 9}, g_q{wq, 128, 2}, g_k{wk, 128, 2}, g_v{wv, 128, 2};
@@ -149,6 +150,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       fence_proxy_async_smem();
       mbar_arrive(f_ready);
     };
+    pdl_wait();  // `feat` is the previous kernel's output
     if (ntl > 0) stage(0);
     for (int k = 0; k < ntl; ++k) {
       LFT_TL2(0);
@@ -330,11 +332,13 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
   const uint32_t bar = smem_u32(smem);
   uint8_t* ks = smem + 16;
   uint8_t* vs = ks + (kAttnRB + 4) * rowbytes;
+  pdl_trigger();
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_wait();  // Q / K / V are the previous kernel's output
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar, 2 * nbytes);
     const long long src = planar_off(v, head, ys, 0, 0, P);
@@ -472,6 +476,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
   const uint32_t hb_ready = smem_u32(&ctl->aux[0]);  // 256 arrivals, used once per CTA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   LFT_TL(30);
+  pdl_trigger();
   cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   const uint32_t tmem = ctl->tmem;
   const GemmPhase g_o{wo, 128, 2}, g_1a{w1a, 128, 2}, g_2a{w2a, 128, 2}, g_1b{w1b, 128, 2}, g_2b{w2b, 128, 2},
@@ -560,6 +565,7 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
     const bool fp32m = passes == 3;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     LFT_TL(0);
+    pdl_wait();  // O / tok are the previous kernels' output
 
     // phase 0: A <- O (planar gather of own heads 4q..4q+3)
     {
@@ -745,6 +751,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
   const uint32_t f2a_done = smem_u32(&ctl->aux[1]);  // completed by one tcgen05.commit (re-initialised below)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   if (tid == 0) {
     mbar_init(f2a_done, 1);
@@ -820,6 +827,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
       mbar_arrive(a_ready);
     };
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();  // O / tok are the previous kernels' output
 
     // phase 0: T <- O (planar gather of own heads 4q..4q+3)
     {
@@ -1039,20 +1047,22 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     Scope sc(h, K_SPA_QKV, st, V * kv.rn * kv.rn);
     const unsigned ntiles = (unsigned)((G + 127) / 128);
     const unsigned pg = ntiles < 2u * h->num_sms ? ntiles : 2u * h->num_sms;  // persistent: two CTAs per SM
-    if (P <= ConvGeom<false>::kMaxP)
-      k_spa_embed_qkv<false><<<pg, kThreads2, smem_embed<false>(), st>>>(in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq,
-                                                                         L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P,
-                                                                         h->passes(), (int)ntiles, e, kv);
-    else
-      k_spa_embed_qkv<true><<<pg, kThreads2, smem_embed<true>(), st>>>(in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq,
-                                                                       L.s_wk, L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P,
-                                                                       h->passes(), (int)ntiles, e, kv);
+    if (P <= ConvGeom<false>::kMaxP) {
+      auto kern = k_spa_embed_qkv<false>;
+      LFT_LAUNCH(h, kern, pg, kThreads2, smem_embed<false>(), st, in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq, L.s_wk,
+                 L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes(), (int)ntiles, e, kv);
+    } else {
+      auto kern = k_spa_embed_qkv<true>;
+      LFT_LAUNCH(h, kern, pg, kThreads2, smem_embed<true>(), st, in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq, L.s_wk,
+                 L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes(), (int)ntiles, e, kv);
+    }
     if ((rc = sc.finish())) return rc;
   }
   {
     Scope sc(h, K_SPA_ATTN, st, V * need.rn * need.rn);
     const int nblk = (need.rn + kAttnRB - 1) / kAttnRB;
-    k_spa_attn<<<(unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st>>>(w.q, w.k, w.v, w.o, P, need);
+    LFT_LAUNCH(h, k_spa_attn, (unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
+               (const float*)w.v, w.o, P, need);
     if ((rc = sc.finish())) return rc;
   }
   {
@@ -1061,13 +1071,11 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     const long long T = V * need.rn * need.rn;
     Scope sc(h, K_SPA_FFN, st, T);
 #ifdef LFT_FFN_V1
-    k_spa_ffn<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
-                                                                        L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P,
-                                                                        h->passes(), need);
+    LFT_LAUNCH(h, k_spa_ffn, (unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st, (const float*)w.o, w.tok, tf, L.s_wo, L.s_w1a,
+               L.s_w1b, L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P, h->passes(), need);
 #else
-    k_spa_ffn2<<<(unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st>>>(w.o, w.tok, tf, L.s_wo, L.s_w1a, L.s_w1b,
-                                                                         L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P,
-                                                                         h->passes(), need);
+    LFT_LAUNCH(h, k_spa_ffn2, (unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st, (const float*)w.o, w.tok, tf, L.s_wo, L.s_w1a,
+               L.s_w1b, L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P, h->passes(), need);
 #endif
     if ((rc = sc.finish())) return rc;
   }

@@ -62,6 +62,7 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
   auto d2_free = [=](int b) { return b ? d2e1 : d2e0; };
   static_assert(kUpNST <= 4, "full[4], empty[4..5] double as D2 barriers");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   cta_setup<kUpNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   if (tid == 0) {  // accumulator-full barriers are completed by one tcgen05.commit each
     mbar_init(d1_full0, 1);
@@ -144,6 +145,7 @@ k_up_gemm(const float* __restrict__ feat, const uint8_t* __restrict__ wup, const
     const int H = A * P * s;
     const long long Y0 = (long long)(u * P + y) * s, X0 = (long long)(v * P + x) * s;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    pdl_wait();  // `feat` is the previous kernel's output
     {  // A1 <- feat row (own 32 channels); W3 <- packed tap weights (one 16-byte piece per thread)
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
@@ -250,6 +252,8 @@ LFT_DEVINL void cubic_coeffs(float t, float* c) {
 __global__ void __launch_bounds__(256)
 k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* __restrict__ out, int B, int A, int P,
             int s, int mode, int cs, int c0, int h0, int w0, int numV, int p0) {
+  pdl_trigger();
+  pdl_wait();
   const int H = A * P * s;
   const int Ps = P * s;
   const long long total = (long long)B * A * A * cs * cs;
@@ -328,6 +332,8 @@ k_up_gather(const float* __restrict__ Pp, const float* __restrict__ lr, float* _
 __global__ void __launch_bounds__(256)
 k_lf_divide(const float* __restrict__ lf, float* __restrict__ patches, int A, int h0, int w0, int numV, int p0, int n,
             int P, int S, int bdr) {
+  pdl_trigger();
+  pdl_wait();  // also orders this kernel's writes to the patch buffer after the previous chunk's readers
   const int W = A * P;
   const long long total = (long long)n * W * W;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,6 +357,8 @@ k_lf_divide(const float* __restrict__ lf, float* __restrict__ patches, int A, in
 __global__ void __launch_bounds__(256)
 k_lf_integrate(const float* __restrict__ crops, float* __restrict__ sr, int A, int h0, int w0, int s, int numV, int p0,
                int n, int cs) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * A * A * cs * cs;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
@@ -392,7 +400,7 @@ int run_upsample(Handle* h, const float* feat, const float* lr, float* out, floa
   int rc;
   {
     Scope sc(h, K_UP_GEMM, st, T);
-    k_up_gemm<<<(unsigned)((T + 127) / 128), kThreads2, kSmemUp, st>>>(feat, h->w_up, h->w_up3, pp, T, A, P, s, h->passes(), ur);
+    LFT_LAUNCH(h, k_up_gemm, (unsigned)((T + 127) / 128), kThreads2, kSmemUp, st, feat, h->w_up, h->w_up3, pp, T, A, P, s, h->passes(), ur);
     if ((rc = sc.finish())) return rc;
   }
   {
@@ -400,7 +408,7 @@ int run_upsample(Handle* h, const float* feat, const float* lr, float* out, floa
     const int c0 = t.mode ? ((P - t.crop_stride) * s) / 2 : 0;  // bdr of LFintegrate(pz = P*s, stride = S*s), utils.py:145
     const long long total = (long long)B * A * A * cs * cs;
     Scope sc(h, K_UP_GATHER, st, total);
-    k_up_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pp, lr, out, B, A, P, s, t.mode, cs, c0, t.h0, t.w0, t.numV, t.p0);
+    LFT_LAUNCH(h, k_up_gather, (unsigned)((total + 255) / 256), 256, 0, st, (const float*)pp, lr, out, B, A, P, s, t.mode, cs, c0, t.h0, t.w0, t.numV, t.p0);
     if ((rc = sc.finish())) return rc;
   }
   return 0;
@@ -411,7 +419,7 @@ int launch_divide(Handle* h, const float* lf, float* patches, int h0, int w0, in
   const int A = h->cfg.ang_res;
   const long long total = (long long)n * A * P * A * P;
   Scope sc(h, K_DIVIDE, st, total);
-  k_lf_divide<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lf, patches, A, h0, w0, numV, p0, n, P, S, (P - S) / 2);
+  LFT_LAUNCH(h, k_lf_divide, (unsigned)((total + 255) / 256), 256, 0, st, lf, patches, A, h0, w0, numV, p0, n, P, S, (P - S) / 2);
   return sc.finish();
 }
 
@@ -421,7 +429,7 @@ int launch_integrate(Handle* h, const float* crops, float* sr, int h0, int w0, i
   const int cs = S * s;
   const long long total = (long long)n * A * A * cs * cs;
   Scope sc(h, K_INTEGRATE, st, total);
-  k_lf_integrate<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(crops, sr, A, h0, w0, s, numV, p0, n, cs);
+  LFT_LAUNCH(h, k_lf_integrate, (unsigned)((total + 255) / 256), 256, 0, st, crops, sr, A, h0, w0, s, numV, p0, n, cs);
   return sc.finish();
 }
 
