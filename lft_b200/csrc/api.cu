@@ -410,6 +410,18 @@ int lft_create(const lft_config* cfg, lft_handle** out) {
   Handle* h = new Handle();
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
+  {
+    const char* e = getenv("LFT_STREAMS");
+    h->two_streams = !(e && e[0] == '1' && e[1] == 0);
+    if (h->two_streams) {
+      if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        h->two_streams = false;
+      }
+    }
+  }
   {  // programmatic dependent launch: built, measured, off by default (see host.h) - LFT_PDL=1 turns it on
     const char* e = getenv("LFT_PDL");
     h->pdl = e && e[0] && e[0] != '0';
@@ -427,6 +439,9 @@ int lft_destroy(lft_handle* hh) {
   DeviceGuard dg(h->cfg.device);
   free_weights(h);
   for (auto& e : h->events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return 0;
 }

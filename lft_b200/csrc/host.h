@@ -104,6 +104,13 @@ struct Handle {
   const uint8_t* w_up3 = nullptr;  // upsampling.3.weight packed as a [16 x 64] bf16 hi/lo B operand (rows 9..15 zero)
   const float* pe_ang = nullptr;
   int pe_P = -1;
+  // the light-field path runs the two halves of its patch range on two streams (the caller's and `side`): the kernels are
+  // persistent grids of all 296 CTA slots, so at small batches (8 patches per GPU when a light field is sharded over 8 GPUs = 5.5
+  // waves per kernel) the last, partly filled wave of one half's kernel is filled by the other half's: -6.7 % at 8 patches, -2.7 %
+  // at 16, -1.3 % at 64 (tools/gpu_two_stream_lf.py).  LFT_STREAMS=1 disables.
+  bool two_streams = true;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pdl = false;                // programmatic dependent launch between the kernels of a forward (LFT_PDL=1 enables)
   bool profiling = false;
   std::vector<ProfEvent> events;   // event pool: created once, reused by every profiling session

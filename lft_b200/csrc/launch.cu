@@ -325,25 +325,49 @@ static int forward_lf_impl(lft_handle* hh, const float* lr_lf, int h0, int w0, i
   const int A = h->cfg.ang_res, s = h->cfg.scale;
   if (direct && (long long)A * h0 * s * A * w0 * s >= (1LL << 31))
     return fail(LFT_ERR_ARG, "assembled light field too large for 32-bit pixel indices");
-  long long chunk = (long long)((ws_bytes - 1024) / per);
-  {
-    const long long cap = (1LL << 30) / ((long long)A * P * s * A * P * s);
-    if (chunk > cap) chunk = cap < 1 ? 1 : cap;
-  }
+  const long long cap32 = (1LL << 30) / ((long long)A * P * s * A * P * s);  // 32-bit index spaces per chunk
   const size_t crop_stride = (size_t)A * A * stride * s * stride * s;
-  for (long long q0 = p0; q0 < p1; q0 += chunk) {
-    const int Bc = (int)((p1 - q0) < chunk ? (p1 - q0) : chunk);
-    const long long T = (long long)Bc * A * A * P * P;
-    Workspace w = carve(ws, T, s);
-    if ((rc = launch_divide(h, lr_lf, w.lrp, h0, w0, nv, (int)q0, Bc, P, stride, (cudaStream_t)stream))) return rc;
-    UpTarget up;
-    up.mode = direct ? 2 : 1;
-    up.crop_stride = stride;
-    up.h0 = h0; up.w0 = w0; up.numV = nv; up.p0 = (int)q0;
-    float* out = direct ? dst : dst + (q0 - p0) * crop_stride;
-    if ((rc = run_forward_chunk(h, w.lrp, out, w, Bc, P, up, (cudaStream_t)stream))) return rc;
+  // patches [q_begin, q_end) on stream `st`, chunked to the workspace part [wsp, wsp + cap patches)
+  auto run_range = [&](long long q_begin, long long q_end, void* wsp, long long cap, cudaStream_t st) -> int {
+    long long chunk = cap > cap32 ? (cap32 < 1 ? 1 : cap32) : cap;
+    for (long long q0 = q_begin; q0 < q_end; q0 += chunk) {
+      const int Bc = (int)((q_end - q0) < chunk ? (q_end - q0) : chunk);
+      const long long T = (long long)Bc * A * A * P * P;
+      Workspace w = carve(wsp, T, s);
+      int r = launch_divide(h, lr_lf, w.lrp, h0, w0, nv, (int)q0, Bc, P, stride, st);
+      if (r) return r;
+      UpTarget up;
+      up.mode = direct ? 2 : 1;
+      up.crop_stride = stride;
+      up.h0 = h0; up.w0 = w0; up.numV = nv; up.p0 = (int)q0;
+      float* out = direct ? dst : dst + (q0 - p0) * crop_stride;
+      if ((r = run_forward_chunk(h, w.lrp, out, w, Bc, P, up, st))) return r;
+    }
+    return 0;
+  };
+  const long long cap = (long long)((ws_bytes - 1024) / per);
+  const long long n = p1 - p0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->two_streams && !h->profiling && n >= 2 && cap >= 2) {
+    // two halves of the range on two streams (host.h: Handle::two_streams); the workspace is split in proportion.  Not while
+    // per-launch profiling events are recorded: a kernel queued behind the other stream's grid would be timed with its wait.
+    const long long nA = (n + 1) / 2;
+    long long capA = cap / 2 + (cap & 1), capB = cap - capA;
+    if (capA > nA) { capA = nA; capB = cap - capA; }
+    char* wsB = reinterpret_cast<char*>(ws) + (size_t)capA * per;
+    wsB = reinterpret_cast<char*>(((uintptr_t)wsB + 1023) & ~(uintptr_t)1023);
+    if ((size_t)(wsB - reinterpret_cast<char*>(ws)) + (size_t)capB * per > ws_bytes) capB -= 1;
+    if (capB >= 1) {
+      CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      if ((rc = run_range(p0, p0 + nA, ws, capA, st))) return rc;
+      if ((rc = run_range(p0 + nA, p1, wsB, capB, h->side))) return rc;
+      CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
+      CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
+      return 0;
+    }
   }
-  return 0;
+  return run_range(p0, p1, ws, cap, st);
 }
 
 int lft_forward_lf_ex(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride,
