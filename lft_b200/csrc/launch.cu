@@ -119,6 +119,34 @@ static int tiling(int h0, int w0, int P, int S, int* numU, int* numV) {
 
 using namespace lft;
 
+// Run fn(begin, end, workspace part, its capacity in patches, stream) over the units [0, n): as one range on the caller's
+// stream, or - Handle::two_streams - as two halves on the caller's stream and the handle's side stream, forked and joined by
+// events, each with its share of the workspace (`per` bytes per patch).  Not while per-launch profiling events are recorded: a
+// kernel queued behind the other stream's grid would be timed with its wait.
+template <typename F>
+static int run_split(Handle* h, long long n, void* ws, size_t ws_bytes, size_t per, cudaStream_t st, F&& fn) {
+  const long long cap = (long long)((ws_bytes - 1024) / per);
+  if (h->two_streams && !h->profiling && n >= 2 && cap >= 2) {
+    const long long nA = (n + 1) / 2;
+    long long capA = cap / 2 + (cap & 1), capB = cap - capA;
+    if (capA > nA) { capA = nA; capB = cap - capA; }
+    char* wsB = reinterpret_cast<char*>(ws) + (size_t)capA * per;
+    wsB = reinterpret_cast<char*>(((uintptr_t)wsB + 1023) & ~(uintptr_t)1023);
+    if ((size_t)(wsB - reinterpret_cast<char*>(ws)) + (size_t)capB * per > ws_bytes) capB -= 1;
+    if (capB >= 1) {
+      int rc;
+      CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      if ((rc = fn(0LL, nA, ws, capA, st))) return rc;
+      if ((rc = fn(nA, n, (void*)wsB, capB, h->side))) return rc;
+      CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
+      CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
+      return 0;
+    }
+  }
+  return fn(0LL, n, ws, cap, st);
+}
+
 static int check_ready(Handle* h, int B, int P) {
   if (!h) return fail(LFT_ERR_ARG, "null handle");
   if (!h->finalized) return fail(LFT_ERR_STATE, "weights not finalized (call lft_finalize_weights)");
@@ -236,20 +264,21 @@ int lft_forward(lft_handle* hh, const float* lr, float* sr, int32_t B, int32_t P
   per -= 1024;
   if (ws_bytes < per + 1024) return fail(LFT_ERR_WORKSPACE, "workspace too small for one patch: %zu < %zu", ws_bytes, per + 1024);
   const int A = h->cfg.ang_res, s = h->cfg.scale;
-  long long chunk = (long long)((ws_bytes - 1024) / per);
-  {  // kernels use 32-bit index math: keep B*(A*P*s)^2 (largest per-chunk index space) below 2^30
-    const long long cap = (1LL << 30) / ((long long)A * P * s * A * P * s);
-    if (chunk > cap) chunk = cap < 1 ? 1 : cap;
-  }
+  // kernels use 32-bit index math: keep B*(A*P*s)^2 (largest per-chunk index space) below 2^30
+  const long long cap32 = (1LL << 30) / ((long long)A * P * s * A * P * s);
   const size_t lr_stride = (size_t)A * P * A * P, sr_stride = lr_stride * s * s;
-  for (long long b0 = 0; b0 < B; b0 += chunk) {
-    const int Bc = (int)((B - b0) < chunk ? (B - b0) : chunk);
-    const long long T = (long long)Bc * A * A * P * P;
-    Workspace w = carve(ws, T, s);
-    if ((rc = run_forward_chunk(h, lr + b0 * lr_stride, sr + b0 * sr_stride, w, Bc, P, UpTarget{}, (cudaStream_t)stream)))
-      return rc;
-  }
-  return 0;
+  return run_split(h, B, ws, ws_bytes, per, (cudaStream_t)stream,
+                   [&](long long b_begin, long long b_end, void* wsp, long long cap, cudaStream_t st) -> int {
+                     const long long chunk = cap > cap32 ? (cap32 < 1 ? 1 : cap32) : cap;
+                     for (long long b0 = b_begin; b0 < b_end; b0 += chunk) {
+                       const int Bc = (int)((b_end - b0) < chunk ? (b_end - b0) : chunk);
+                       const long long T = (long long)Bc * A * A * P * P;
+                       Workspace w = carve(wsp, T, s);
+                       int r = run_forward_chunk(h, lr + b0 * lr_stride, sr + b0 * sr_stride, w, Bc, P, UpTarget{}, st);
+                       if (r) return r;
+                     }
+                     return 0;
+                   });
 }
 
 int lft_lf_num_patches_ex(int32_t h0, int32_t w0, int32_t patch, int32_t stride, int32_t* numU, int32_t* numV) {
@@ -345,29 +374,8 @@ static int forward_lf_impl(lft_handle* hh, const float* lr_lf, int h0, int w0, i
     }
     return 0;
   };
-  const long long cap = (long long)((ws_bytes - 1024) / per);
-  const long long n = p1 - p0;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (h->two_streams && !h->profiling && n >= 2 && cap >= 2) {
-    // two halves of the range on two streams (host.h: Handle::two_streams); the workspace is split in proportion.  Not while
-    // per-launch profiling events are recorded: a kernel queued behind the other stream's grid would be timed with its wait.
-    const long long nA = (n + 1) / 2;
-    long long capA = cap / 2 + (cap & 1), capB = cap - capA;
-    if (capA > nA) { capA = nA; capB = cap - capA; }
-    char* wsB = reinterpret_cast<char*>(ws) + (size_t)capA * per;
-    wsB = reinterpret_cast<char*>(((uintptr_t)wsB + 1023) & ~(uintptr_t)1023);
-    if ((size_t)(wsB - reinterpret_cast<char*>(ws)) + (size_t)capB * per > ws_bytes) capB -= 1;
-    if (capB >= 1) {
-      CUDA_TRY(cudaEventRecord(h->ev_fork, st));
-      CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-      if ((rc = run_range(p0, p0 + nA, ws, capA, st))) return rc;
-      if ((rc = run_range(p0 + nA, p1, wsB, capB, h->side))) return rc;
-      CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
-      CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
-      return 0;
-    }
-  }
-  return run_range(p0, p1, ws, cap, st);
+  return run_split(h, p1 - p0, ws, ws_bytes, per, (cudaStream_t)stream,
+                   [&](long long a, long long b, void* wsp, long long cap, cudaStream_t st) { return run_range(p0 + a, p0 + b, wsp, cap, st); });
 }
 
 int lft_forward_lf_ex(lft_handle* hh, const float* lr_lf, int32_t h0, int32_t w0, int32_t patch, int32_t stride,

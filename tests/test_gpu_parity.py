@@ -558,6 +558,11 @@ def test_cuda_graph_replay_bit_identical():
     n0 = eng.launch_count()
     eng.forward_graphed(lr)
     assert eng.launch_count() == n0          # replay: no launches issued by the library itself
+    # a batch: the library forks its second half onto a side stream - the capture must follow it and join again
+    lr3 = torch.from_numpy(synth.synth_lr_mosaic(3, A, 16, 16, 5)).cuda()
+    want3 = eng.forward(lr3).clone()
+    for _ in range(2):
+        assert torch.equal(eng.forward_graphed(lr3), want3)
 
 
 def test_direct_assembly_equals_crops_plus_integrate():
