@@ -238,16 +238,24 @@ LFT_DEVINL void ang_attn_item25(const f32x2* q, const ulonglong2* __restrict__ k
 // (pixel, rel head) over the 8 warps | barrier.  The O operand of the output projection (TS form, TMEM columns [64,128))
 // overlaps K accumulator columns of the other half, so half 0's results stay in shared memory until half 1 has been
 // exported.
-LFT_DEVINL void ang_attention25(uint32_t trow, int warp, int lane, int q, int kvrow, float rstd, float mr,
-                                const float4* __restrict__ pq4, const float4* tab4, uint8_t* planes, bool fp32_mode) {
-  constexpr int N = 25;
+// Generalised to the other odd angular resolutions that fill a 128-row tile with whole pixels: NV = 49 (A = 7, 2 pixels per
+// tile) and NV = 81 (A = 9, 1 pixel per tile).  More than 32 views -> a (pixel, head) item is split into chunks of 32 queries
+// (one per lane); the soft-max is evaluated online in chunks of CH keys (81 scores do not fit in registers).  For A = 9 the
+// paired row-owner attention was bound by shared-memory wavefronts (all 81 rows of a tile read the same 81 keys, but every
+// quarter-warp fetched them separately: ~41 K wavefronts per tile); the uniform loads of this mapping need ~16 K.
+template <int N, int PPT, int CH>
+LFT_DEVINL void ang_attention_items(uint32_t trow, int warp, int lane, int q, int kvrow, float rstd, float mr,
+                                    const float4* __restrict__ pq4, const float4* tab4, uint8_t* planes, bool fp32_mode) {
+  constexpr int QCH = (N + 31) / 32;           // query chunks per (pixel, head)
+  constexpr int NITEMS = 4 * PPT * QCH;        // items per head half
+  const int srow = kvrow >= 0 ? kvrow : 0;     // idle rows (A = 7, 9) stage nothing and convert row 0's values (their output is discarded)
   uint8_t* qo_ptr = planes;           // R1
   uint8_t* ks_ptr = planes + 32768;   // R2
   uint8_t* vs_ptr = ks_ptr + 16384;
   const float scale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e)/sqrt(8), folded into Q (softmax via exp2)
   // results of head half g: shared memory -> bf16 hi/lo TS-form operand; the two threads of a row take two heads each
   auto convert = [&](int g) {
-    const uint8_t* src = qo_ptr + g * 16384 + kvrow * 16;
+    const uint8_t* src = qo_ptr + g * 16384 + srow * 16;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       const int rh = 2 * q + hh;
@@ -277,7 +285,7 @@ LFT_DEVINL void ang_attention25(uint32_t trow, int warp, int lane, int q, int kv
                                        fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y)),
                                        fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z)),
                                        fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w)));
-          *reinterpret_cast<float4*>(ks_ptr + ((2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) = r;
+          if (kvrow >= 0) *reinterpret_cast<float4*>(ks_ptr + ((2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) = r;
         }
       }
     } else {       // V (raw) and Q (corrected, pre-scaled) of the same heads
@@ -286,8 +294,9 @@ LFT_DEVINL void ang_attention25(uint32_t trow, int warp, int lane, int q, int kv
         tmem_ld16(trow + 128 + 32 * g + 16 * c, kv);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(vs_ptr + ((2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) =
-              make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+          if (kvrow >= 0)
+            *reinterpret_cast<float4*>(vs_ptr + ((2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) =
+                make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -301,7 +310,7 @@ LFT_DEVINL void ang_attention25(uint32_t trow, int warp, int lane, int q, int kv
                                        scale * fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y)),
                                        scale * fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z)),
                                        scale * fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w)));
-          *reinterpret_cast<float4*>(qo_ptr + g * 16384 + ((2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) = r;
+          if (kvrow >= 0) *reinterpret_cast<float4*>(qo_ptr + g * 16384 + ((2 * c + (j >> 1)) * 2 + (j & 1)) * 2048 + kvrow * 16) = r;
         }
       }
     }
@@ -313,10 +322,13 @@ LFT_DEVINL void ang_attention25(uint32_t trow, int warp, int lane, int q, int kv
     if (g == 1) convert(0);
     const uint8_t* qo_g = qo_ptr + g * 16384;
 #pragma unroll 1
-    for (int it = warp; it < 20; it += 8) {  // items (rel head, pixel); lane = query view (lanes 25..31 shadow view 24)
-      const int rh = it / 5, p = it - 5 * rh;
-      const int a = lane < N ? lane : N - 1;
-      uint8_t* qrow = const_cast<uint8_t*>(qo_g) + (rh * 2) * 2048 + (a * 5 + p) * 16;
+    for (int it = warp; it < NITEMS; it += 8) {  // items (rel head, pixel, query chunk); lane = query view of the chunk
+      const int rh = it / (PPT * QCH);
+      const int rem = it - rh * (PPT * QCH);
+      const int p = rem / QCH, qc = rem - p * QCH;
+      const int aq = 32 * qc + lane;
+      const int a = aq < N ? aq : N - 1;         // lanes beyond the last view shadow it (no store)
+      uint8_t* qrow = const_cast<uint8_t*>(qo_g) + (rh * 2) * 2048 + (a * PPT + p) * 16;
       f32x2 qq[1][4];
       {
         const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(qrow);
@@ -326,12 +338,16 @@ LFT_DEVINL void ang_attention25(uint32_t trow, int warp, int lane, int q, int kv
       const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(ks_ptr + rh * 4096) + p;
       const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(vs_ptr + rh * 4096) + p;
       float o[1][8];
+      if constexpr (N == 25) {
 #ifdef LFT_ANG_ONLINE
-      ang_attn_head<1, 25, 5, 5>(qq, kb, vb, o);
+        ang_attn_head<1, 25, 5, 5>(qq, kb, vb, o);
 #else
-      ang_attn_item25(qq[0], kb, vb, o[0]);
+        ang_attn_item25(qq[0], kb, vb, o[0]);
 #endif
-      if (lane < N) {  // O overwrites Q in place (only this lane ever read it)
+      } else {
+        ang_attn_head<1, N, PPT, CH>(qq, kb, vb, o);
+      }
+      if (aq < N) {  // O overwrites Q in place (only this lane ever read it)
         *reinterpret_cast<float4*>(qrow) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
         *reinterpret_cast<float4*>(qrow + 2048) = make_float4(o[0][4], o[0][5], o[0][6], o[0][7]);
       }
@@ -525,8 +541,8 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       const float mr = mean * rstd;
       const float4* pq4 = reinterpret_cast<const float4*>(peqk) + aa;  // [chunk 32][N][4]: Q chunks 0..15, K 16..31
       const float4* tab4 = reinterpret_cast<const float4*>(tab.v);    // [u_qk 128 | c_qk 128 | u_1 128 | c_1 128] (constant bank)
-      if constexpr (NV == 25) {
-        ang_attention25(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes, passes == 3);
+      if constexpr (NV == 25 || NV == 49 || NV == 81) {
+        ang_attention_items<NV, kPPT, kCH>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes, passes == 3);
         LFT_TL(4);
         tmem_wait_st();
         tc_fence_before();
