@@ -322,7 +322,11 @@ LFT_DEVINL void ang_attention_items(uint32_t trow, int warp, int lane, int q, in
     if (g == 1) convert(0);
     const uint8_t* qo_g = qo_ptr + g * 16384;
 #pragma unroll 1
+#ifdef LFT_X_ANG_NOATTN   // timing experiment (wrong results): the attention items are skipped
+    for (int it = NITEMS; it < NITEMS; it += 8) {
+#else
     for (int it = warp; it < NITEMS; it += 8) {  // items (rel head, pixel, query chunk); lane = query view of the chunk
+#endif
       const int rh = it / (PPT * QCH);
       const int rem = it - rh * (PPT * QCH);
       const int p = rem / QCH, qc = rem - p * QCH;

@@ -29,6 +29,16 @@ constexpr uint32_t embed_window_bytes() { return BIG ? 2u * ConvGeom<true>::kRow
 template <bool BIG>
 constexpr size_t smem_embed() { return kCtlBytes + embed_window_bytes<BIG>() + ConvGeom<BIG>::kNST * kSpaStage; }
 constexpr uint32_t kLbo = 128 * 16;
+#ifdef LFT_X_FFN_NOLOAD
+constexpr bool kFfnNoLoad = true;   // timing experiment: k_spa_ffn2 reads neither O nor tok
+#else
+constexpr bool kFfnNoLoad = false;
+#endif
+#ifdef LFT_X_NOQKV
+constexpr bool kNoQKV = true;   // timing experiment: no Q / K / V stores
+#else
+constexpr bool kNoQKV = false;
+#endif
 
 LFT_DEVINL long long planar_off(long long v, int head, int y, int j, int x, int P) {
   return ((((v * 8 + head) * P + y) * 4 + j) * (long long)P + x) * 4;
@@ -40,6 +50,30 @@ LFT_DEVINL void planar_store16(float* base, long long v, int head, int y, int x,
   for (int j = 0; j < 4; ++j)
     st_stream_v4(base + planar_off(v, head, y, j, x, P), make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]));
 }
+
+// The window attention runs on warp-level tensor-core MMAs (k_spa_attn_mma), so Q / K / V leave k_spa_embed_qkv as bf16 hi / lo
+// pairs in the SAME planar layout (and the same bytes as fp32): the four 16-byte pieces of a (token, head) are
+//   piece 0: hi of dims 0..7 | piece 1: hi of dims 8..15 | piece 2: lo of dims 0..7 | piece 3: lo of dims 8..15
+// (x = hi + lo to 2^-16, the accuracy class of every three-pass product here).  bf16 mode stores the hi pieces only.
+LFT_DEVINL void st_stream_v4u(float* p, const uint4& v) {
+  st_stream_v4(p, make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)));
+}
+LFT_DEVINL void planar_store16_split(float* base, long long v, int head, int y, int x, int P, const float* d, bool fp32_mode) {
+  uint4 h0, l0, h1, l1;
+  split8(d, h0, l0, fp32_mode);
+  split8(d + 8, h1, l1, fp32_mode);
+  st_stream_v4u(base + planar_off(v, head, y, 0, x, P), h0);
+  st_stream_v4u(base + planar_off(v, head, y, 1, x, P), h1);
+  if (fp32_mode) {
+    st_stream_v4u(base + planar_off(v, head, y, 2, x, P), l0);
+    st_stream_v4u(base + planar_off(v, head, y, 3, x, P), l1);
+  }
+}
+#ifdef LFT_ATTN_V1   // the CUDA-core window attention of rounds 1-2 (fp32 Q / K / V planes)
+constexpr bool kAttnMma = false;
+#else
+constexpr bool kAttnMma = true;
+#endif
 
 // split 16 fp32 values into two k-chunks (kc0, kc0+1) of the K=128 A operand (hi at A, lo at A+32K)
 LFT_DEVINL void a_store16(uint32_t A, int kc0, int m, const float* x, bool fp32_mode) {
@@ -190,23 +224,42 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
         for (int c = 0; c < 4; ++c) {
           float t[16];
           tmem_ld16(trow + 64 * q + 16 * c, t);
+#if !defined(LFT_X_NOTOK) && !defined(LFT_X_ZTOK)
           if (ok) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               st_stream_v4(tok + t32_off(token, 16 * q + 4 * c + i, 32),
                            make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]));
           }
+#endif
 #pragma unroll
           for (int i = 0; i < 16; ++i) z[16 * c + i] += t[i];
           a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, z + 16 * c, passes == 3);
         }
         pair_ln_stats<64>(z, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
+#if defined(LFT_X_ZTOK)   // timing experiment (ffn then reads z instead of tok): the token store leaves the z -> Q critical path
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+#if LFT_X_ZTOK == 2
+        if (k + 1 < ntl) stage(k + 1);
+#endif
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            st_stream_v4(tok + t32_off(token, 16 * q + i, 32), make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]));
+        }
+#endif
       }
+#if !defined(LFT_X_ZTOK)
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(a_ready);             // z ready
+#endif
       LFT_TL2(2);
+#if !defined(LFT_X_ZTOK) || LFT_X_ZTOK != 2
       if (k + 1 < ntl) stage(k + 1);    // the staging area is free (conv MMAs of this tile are complete)
+#endif
       LFT_TL2(3);
       const float mr = mean * rstd;
       await();  // Q
@@ -230,7 +283,10 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
             d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
             d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
           }
-          if (ok) planar_store16(Q, v, 4 * q + c, y, x, P, d);
+          if (ok && !kNoQKV) {
+            if (kAttnMma) planar_store16_split(Q, v, 4 * q + c, y, x, P, d, passes == 3);
+            else planar_store16(Q, v, 4 * q + c, y, x, P, d);
+          }
         }
       }
       LFT_TL2(5);
@@ -255,7 +311,10 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
             d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
             d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
           }
-          if (ok) planar_store16(K, v, 4 * q + c, y, x, P, d);
+          if (ok && !kNoQKV) {
+            if (kAttnMma) planar_store16_split(K, v, 4 * q + c, y, x, P, d, passes == 3);
+            else planar_store16(K, v, 4 * q + c, y, x, P, d);
+          }
         }
       }
       LFT_TL2(7);
@@ -276,7 +335,10 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
             const float4 pv = __ldg(reinterpret_cast<const float4*>(pev) + (long long)(16 * q + 4 * c + j) * PP + p);
             d[4 * j] -= pv.x; d[4 * j + 1] -= pv.y; d[4 * j + 2] -= pv.z; d[4 * j + 3] -= pv.w;
           }
-          if (ok) planar_store16(Vv, v, 4 * q + c, y, x, P, d);
+          if (ok && !kNoQKV) {
+            if (kAttnMma) planar_store16_split(Vv, v, 4 * q + c, y, x, P, d, passes == 3);
+            else planar_store16(Vv, v, 4 * q + c, y, x, P, d);
+          }
         }
       }
       LFT_TL2(9);
@@ -458,6 +520,238 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
   }
   }  // query pairs
   if (!staged) mbar_wait(bar, 0);  // threads without a query still wait for the copies before the CTA may exit
+}
+
+// ------------------------------------------------------------------------------------------------
+// Window attention on tensor cores (round 2, the default): S = Q K^T and O = P V of the 5 x 5 window as warp-level
+// mma.sync.m16n8k16 (bf16 operands, fp32 accumulate) with the three-term hi / lo split of every fp32-grade product.  The
+// window attention is ragged and tiny (<= 25 keys of 16 dims per query), which tcgen05's 128-row tiles cannot hold without
+// ~10x padding; a register-fragment MMA can: a warp takes a 4 x 4 block of queries (one m16 tile) of one head, whose windows lie
+// inside the 8 x 8 block of keys around it = 64 keys = eight n8 tiles (one key row each) for S and four k16 steps for P V.
+// 39 % of the S / P entries are inside a window, the rest is masked to -inf / 0 - still 2.2x fewer issue slots and 3.7x fewer
+// shared-memory wavefronts per query than the FFMA2 formulation above, which was bound by getting every key to its 25 queries
+// through the LSU.  CTA = (view, head, 8 query rows) as before: K / V rows [r0-2, r0+10) arrive by two bulk copies; B fragments
+// come from them by ldmatrix (K) / ldmatrix.trans (V) - the 16-byte pieces of the planar layout ARE the 8 x 8 matrix rows, eight
+// neighbouring keys are 128 contiguous bytes (conflict-free); Q fragments are read straight from global memory (32-bit words).
+// Keys outside a query's window are masked after the MMA; their addresses are clamped to the rows / columns this launch's
+// k_spa_embed_qkv has written (masked keys lie at most 3 pixels outside the K / V region), so no stale workspace bits ever reach a
+// multiplier.  Soft-max in fp32 on the accumulator fragments (row statistics by quad shuffles), P re-split into hi / lo.
+LFT_DEVINL void ldsm4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+LFT_DEVINL void ldsm4t(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+LFT_DEVINL void hmma16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two probabilities -> packed bf16 hi (truncation) and lo (rounded remainder); bf16 mode: hi = rounded, no lo
+LFT_DEVINL void split_pair(float a, float b, bool fp32_mode, uint32_t& hi, uint32_t& lo) {
+  if (!fp32_mode) { hi = pack_bf16(a, b); lo = 0u; return; }
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  hi = __byte_perm(ua, ub, 0x7632);
+  lo = pack_bf16(a - __uint_as_float(ua & 0xffff0000u), b - __uint_as_float(ub & 0xffff0000u));
+}
+
+constexpr int kAttnMmaThreads = 128;  // 4 warps: warp w takes block row w & 1 of the CTA's 8 rows and every second block column
+// Query blocks sit on the ABSOLUTE 4 x 4 grid of the view (not the region's), so a query meets its keys in the same order
+// whatever region a launch computes: the light-field path's sub-region results stay bit-identical to the full forward's.
+LFT_DEVINL int attn_mma_nblk(Region qr) { return ((qr.r0 + qr.rn) - (qr.r0 & ~3) + kAttnRB - 1) / kAttnRB; }
+
+template <bool FP32>
+__global__ void __launch_bounds__(kAttnMmaThreads, 4)
+k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ Vv,
+               float* __restrict__ O, int P, Region qr) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nblk = attn_mma_nblk(qr);
+  const int rb = blockIdx.x % nblk;
+  const int head = (blockIdx.x / nblk) & 7;
+  const long long v = blockIdx.x / (nblk * 8);
+  const int rend = qr.r0 + qr.rn, cend = rend;                     // one past the last query row / column
+  const int rowbase = (qr.r0 & ~3) + rb * kAttnRB;                 // first row of the CTA's blocks (multiple of 4)
+  const int q0 = max(rowbase, qr.r0), q1 = min(rowbase + kAttnRB, rend);     // query rows [q0, q1) of this CTA
+  const int ys = max(q0 - 2, 0), ye = min(q1 + 2, P);              // staged key rows [ys, ye)
+  const int kxlo = max(qr.r0 - 2, 0), kxhi = min(cend + 2, P) - 1; // key columns k_spa_embed_qkv has written
+  const uint32_t rowbytes = (uint32_t)P * 64;                      // one (y) plane: 4 pieces x P x 16 B
+  const uint32_t piecebytes = (uint32_t)P * 16;
+  const uint32_t nbytes = (uint32_t)(ye - ys) * rowbytes;
+  const uint32_t bar = smem_u32(smem);
+  const uint32_t ks = smem_u32(smem) + 16, vs = ks + (kAttnRB + 4) * rowbytes;
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_wait();  // Q / K / V are the previous kernel's output
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, 2 * nbytes);
+    const long long src = planar_off(v, head, ys, 0, 0, P);
+    bulk_g2s(ks, K + src, nbytes, bar);
+    bulk_g2s(vs, Vv + src, nbytes, bar);
+  }
+  constexpr bool fp32m = FP32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;      // accumulator fragment: rows g, g + 8; columns 2c, 2c + 1
+  const int mat = lane >> 3, mr = lane & 7;   // ldmatrix: this lane addresses row mr of matrix mat
+  const long long plane = planar_off(v, head, 0, 0, 0, P);
+  const uint32_t* Qw = reinterpret_cast<const uint32_t*>(Q) + plane;
+  float* Ob = O + plane;
+  constexpr int kBR = kAttnRB / 4;            // block rows per CTA
+  constexpr int kWC = kAttnMmaThreads / 32 / kBR;   // warps per block row = block-column stride of a warp
+  const int bx0 = qr.r0 & ~3;
+  const int ncb = (cend - bx0 + 3) >> 2;
+  const float qs = 0.25f * 1.4426950408889634f;   // log2(e)/sqrt(16): softmax through exp2
+  const float NINF = -INFINITY;
+
+  // ---- per-warp invariants: the block row by, its key rows and row masks.
+  // m16 tile rows: A = g -> query (by + iA, bx + g%4), B = g + 8 -> (by + 2 + iA, .), iA = g / 4; n8 tile j = key row by - 2 + j.
+  const int by = rowbase + 4 * (warp % kBR);
+  const bool row_active = by < q1 && by + 4 > q0;
+  const int iA = g >> 2;
+  uint32_t koff[8], voff[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) koff[j] = (uint32_t)(min(max(by - 2 + j, ys), ye - 1) - ys) * rowbytes + (uint32_t)mat * piecebytes;
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+    voff[t] = (uint32_t)(min(max(by - 2 + 2 * t + (mat & 1), ys), ye - 1) - ys) * rowbytes + (uint32_t)(mat >> 1) * piecebytes;
+  // additive row masks (0 / -inf) as accumulator initial values: row A meets key rows j = iA .. iA + 4 (<= 5), row B
+  // j = iA + 2 .. iA + 6 (>= 2), both only inside the view; the (row half, j) pairs outside those ranges are masked for every lane
+  float rbA[6], rbB[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int kyA = by - 2 + j, kyB = by + j;          // rbB[j] belongs to n8 tile j + 2
+    rbA[j] = (j >= iA && j <= iA + 4 && kyA >= 0 && kyA < P) ? 0.f : NINF;
+    rbB[j] = (j + 2 >= iA + 2 && j + 2 <= iA + 6 && kyB >= 0 && kyB < P) ? 0.f : NINF;
+  }
+  bool dxok[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int dx = 2 * c + e - 2 - (g & 3);
+    dxok[e] = dx >= -2 && dx <= 2;
+  }
+  const int qyA = min(max(by + iA, qr.r0), rend - 1), qyB = min(max(by + 2 + iA, qr.r0), rend - 1);
+  const uint32_t qoffA = (uint32_t)qyA * 16u * P + c, qoffB = (uint32_t)qyB * 16u * P + c;   // 32-bit words inside the plane
+  const int ps = P * 4;                       // words between the pieces of one (y, x)
+  const bool odd = c & 1;
+  const int qyo = by + iA + (odd ? 2 : 0);    // the row this lane stores (even lanes: row A's piece, odd lanes: row B's)
+  const bool okrow = qyo >= qr.r0 && qyo < rend;
+  const uint32_t ooff = (uint32_t)(qyo * 4 + (c >> 1)) * P * 4;
+
+  // Q fragments of block column cb; queries outside the region shadow the nearest valid one (their results are not stored)
+  auto load_q = [&](int cb, uint32_t* qh, uint32_t* ql) {
+    const int qx = min(max(bx0 + 4 * cb + (g & 3), qr.r0), cend - 1);
+    const uint32_t* a = Qw + qoffA + qx * 4;
+    const uint32_t* b = Qw + qoffB + qx * 4;
+    qh[0] = __ldg(a); qh[1] = __ldg(b); qh[2] = __ldg(a + ps); qh[3] = __ldg(b + ps);
+    if (fp32m) { ql[0] = __ldg(a + 2 * ps); ql[1] = __ldg(b + 2 * ps); ql[2] = __ldg(a + 3 * ps); ql[3] = __ldg(b + 3 * ps); }
+  };
+  uint32_t qh[4], ql[4] = {0u, 0u, 0u, 0u};
+  const int cb0 = warp / kBR;
+  if (row_active && cb0 < ncb) load_q(cb0, qh, ql);
+  mbar_wait(bar, 0);   // every thread waits for the copies (also before the CTA may exit)
+  if (!row_active) return;
+#pragma unroll 1
+  for (int cb = cb0; cb < ncb; cb += kWC) {
+    const int bx = bx0 + 4 * cb;
+    uint32_t qnh[4], qnl[4] = {0u, 0u, 0u, 0u};
+    if (cb + kWC < ncb) load_q(cb + kWC, qnh, qnl);   // next block's queries in flight under this block's MMAs
+    // ---- S = Q K^T on top of the masks: n8 tile j = key row by - 2 + j, keys bx - 2 .. bx + 5 (column = 2c + e of the tile)
+    const uint32_t kcol = (uint32_t)min(max(bx - 2 + mr, kxlo), kxhi) * 16;
+    float cb_[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) cb_[e] = (dxok[e] && (unsigned)(bx - 2 + 2 * c + e) < (unsigned)P) ? 0.f : NINF;
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[j][e] = j < 6 ? fminf(rbA[j], cb_[e]) : NINF;
+        s[j][2 + e] = j >= 2 ? fminf(rbB[j - 2], cb_[e]) : NINF;
+      }
+      uint32_t kb[4];
+      ldsm4(ks + koff[j] + kcol, kb);
+      hmma16816(s[j], qh, kb[0], kb[1]);
+      if (fp32m) {
+        hmma16816(s[j], ql, kb[0], kb[1]);
+        hmma16816(s[j], qh, kb[2], kb[3]);
+      }
+    }
+    // ---- soft-max (masked entries are -inf; every query sees itself, so the row maxima are finite)
+    float mA = s[0][0], mB = s[2][2];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      mA = fmaxf(mA, fmaxf(s[j][0], s[j][1]));
+      mB = fmaxf(mB, fmaxf(s[j + 2][2], s[j + 2][3]));
+    }
+    mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
+    mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+    mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+    mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+    const float nA = -mA * qs, nB = -mB * qs;
+    float lA = 0.f, lB = 0.f;
+    uint32_t ph[8][2], pl[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < 6) {
+        const float p0 = fast_exp2(fmaf(s[j][0], qs, nA)), p1 = fast_exp2(fmaf(s[j][1], qs, nA));
+        lA += p0 + p1;
+        split_pair(p0, p1, fp32m, ph[j][0], pl[j][0]);
+      } else {
+        ph[j][0] = pl[j][0] = 0u;
+      }
+      if (j >= 2) {
+        const float p2 = fast_exp2(fmaf(s[j][2], qs, nB)), p3 = fast_exp2(fmaf(s[j][3], qs, nB));
+        lB += p2 + p3;
+        split_pair(p2, p3, fp32m, ph[j][1], pl[j][1]);
+      } else {
+        ph[j][1] = pl[j][1] = 0u;
+      }
+    }
+    lA += __shfl_xor_sync(0xffffffffu, lA, 1);
+    lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+    lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+    lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+    // ---- O = P V: k16 step t = key rows by - 2 + 2t, + 1; n8 tile d = dims 8d .. 8d + 7
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t va = vs + voff[t] + kcol;
+      uint32_t vh[4];
+      ldsm4t(va, vh);   // {keys 0-7, keys 8-15} x {dims 0-7, dims 8-15} of the hi pieces
+      const uint32_t ah[4] = {ph[2 * t][0], ph[2 * t][1], ph[2 * t + 1][0], ph[2 * t + 1][1]};
+      hmma16816(o[0], ah, vh[0], vh[1]);
+      hmma16816(o[1], ah, vh[2], vh[3]);
+      if (fp32m) {
+        const uint32_t al[4] = {pl[2 * t][0], pl[2 * t][1], pl[2 * t + 1][0], pl[2 * t + 1][1]};
+        hmma16816(o[0], al, vh[0], vh[1]);
+        hmma16816(o[1], al, vh[2], vh[3]);
+        uint32_t vl[4];
+        ldsm4t(va + 2 * piecebytes, vl);
+        hmma16816(o[0], ah, vl[0], vl[1]);
+        hmma16816(o[1], ah, vl[2], vl[3]);
+      }
+    }
+    // ---- normalise and store (fp32 planar, as k_spa_ffn reads it): the lanes of a pair (c, c ^ 1) hold the two halves of a
+    // 16-byte piece; the even lane stores row A's piece, the odd lane row B's
+    const float iA_ = 1.f / lA, iB_ = 1.f / lB;
+    const int qx = bx + (g & 3);
+    const bool okq = okrow && qx >= qr.r0 && qx < cend;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const float a0 = o[d][0] * iA_, a1 = o[d][1] * iA_, b0 = o[d][2] * iB_, b1 = o[d][3] * iB_;
+      const float r0_ = __shfl_xor_sync(0xffffffffu, odd ? a0 : b0, 1);
+      const float r1_ = __shfl_xor_sync(0xffffffffu, odd ? a1 : b1, 1);
+      const float4 out = odd ? make_float4(r0_, r1_, b0, b1) : make_float4(a0, a1, r0_, r1_);
+      if (okq) st_stream_v4(Ob + ooff + (uint32_t)(2 * d * P + qx) * 4, out);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { qh[i] = qnh[i]; ql[i] = qnl[i]; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -837,7 +1131,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) f[4 * c + j] = ok ? __ldg(reinterpret_cast<const float4*>(ob + c * hs + j * js)) : zero4;
+        for (int j = 0; j < 4; ++j) f[4 * c + j] = (ok && !kFfnNoLoad) ? __ldg(reinterpret_cast<const float4*>(ob + c * hs + j * js)) : zero4;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, reinterpret_cast<const float*>(&f[4 * c]), fp32m);
@@ -849,7 +1143,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
     {
       float4 tk[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) tk[i] = ok ? __ldg(reinterpret_cast<const float4*>(trow_g + 128 * i)) : zero4;  // in flight
+      for (int i = 0; i < 16; ++i) tk[i] = (ok && !kFfnNoLoad) ? __ldg(reinterpret_cast<const float4*>(trow_g + 128 * i)) : zero4;  // in flight
       await();
       float yv[64];
 #pragma unroll
@@ -1020,6 +1314,8 @@ int configure_spa() {
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
   return 0;
 }
 
@@ -1061,8 +1357,21 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
   {
     Scope sc(h, K_SPA_ATTN, st, V * need.rn * need.rn);
     const int nblk = (need.rn + kAttnRB - 1) / kAttnRB;
-    LFT_LAUNCH(h, k_spa_attn, (unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
-               (const float*)w.v, w.o, P, need);
+    if (kAttnMma) {
+      const int nb = ((need.r0 + need.rn) - (need.r0 & ~3) + kAttnRB - 1) / kAttnRB;  // attn_mma_nblk
+      if (h->passes() == 3) {
+        auto kern = k_spa_attn_mma<true>;
+        LFT_LAUNCH(h, kern, (unsigned)(V * 8 * nb), kAttnMmaThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
+                   (const float*)w.v, w.o, P, need);
+      } else {
+        auto kern = k_spa_attn_mma<false>;
+        LFT_LAUNCH(h, kern, (unsigned)(V * 8 * nb), kAttnMmaThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
+                   (const float*)w.v, w.o, P, need);
+      }
+    } else {
+      LFT_LAUNCH(h, k_spa_attn, (unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
+                 (const float*)w.v, w.o, P, need);
+    }
     if ((rc = sc.finish())) return rc;
   }
   {
