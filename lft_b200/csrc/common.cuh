@@ -531,6 +531,11 @@ LFT_DEVINL float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+LFT_DEVINL float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 LFT_DEVINL float lrelu02(float x) { return fmaxf(x, 0.2f * x); }  // == x >= 0 ? x : 0.2x
 
 }  // namespace lft

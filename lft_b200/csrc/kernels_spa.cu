@@ -557,20 +557,26 @@ LFT_DEVINL void split_pair(float a, float b, bool fp32_mode, uint32_t& hi, uint3
   lo = pack_bf16(a - __uint_as_float(ua & 0xffff0000u), b - __uint_as_float(ub & 0xffff0000u));
 }
 
-constexpr int kAttnMmaThreads = 128;  // 4 warps: warp w takes block row w & 1 of the CTA's 8 rows and every second block column
+#ifndef LFT_ATTN_SKEW
+#define LFT_ATTN_SKEW 500
+#endif
+constexpr int kAttnMmaThreads = 256;  // 8 warps: warp w takes block row w & 1 of the item's 8 rows and every fourth block column
 // Query blocks sit on the ABSOLUTE 4 x 4 grid of the view (not the region's), so a query meets its keys in the same order
 // whatever region a launch computes: the light-field path's sub-region results stay bit-identical to the full forward's.
 LFT_DEVINL int attn_mma_nblk(Region qr) { return ((qr.r0 + qr.rn) - (qr.r0 & ~3) + kAttnRB - 1) / kAttnRB; }
+constexpr size_t smem_attn_mma(int P) { return 32 + 2 * 2 * (size_t)(kAttnRB + 4) * 4 * P * 16; }  // two (K rows | V rows) buffers
 
+// Persistent: a CTA (two per SM) walks over the work items (view, head, block of 8 query rows) i = blockIdx.x + k gridDim.x with
+// two staging buffers - the bulk copies of item k + 1 run under the MMAs of item k (the one-item-per-CTA form spent half of a
+// CTA's life waiting for its 49 KB).  The host makes gridDim.x a multiple of the row blocks per view, so a CTA keeps its row
+// block: key-row offsets and row masks are loop invariants.
 template <bool FP32>
-__global__ void __launch_bounds__(kAttnMmaThreads, 4)
+__global__ void __launch_bounds__(kAttnMmaThreads, 2)
 k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ Vv,
-               float* __restrict__ O, int P, Region qr) {
+               float* __restrict__ O, int P, Region qr, int nitems) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nblk = attn_mma_nblk(qr);
   const int rb = blockIdx.x % nblk;
-  const int head = (blockIdx.x / nblk) & 7;
-  const long long v = blockIdx.x / (nblk * 8);
   const int rend = qr.r0 + qr.rn, cend = rend;                     // one past the last query row / column
   const int rowbase = (qr.r0 & ~3) + rb * kAttnRB;                 // first row of the CTA's blocks (multiple of 4)
   const int q0 = max(rowbase, qr.r0), q1 = min(rowbase + kAttnRB, rend);     // query rows [q0, q1) of this CTA
@@ -579,29 +585,39 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
   const uint32_t rowbytes = (uint32_t)P * 64;                      // one (y) plane: 4 pieces x P x 16 B
   const uint32_t piecebytes = (uint32_t)P * 16;
   const uint32_t nbytes = (uint32_t)(ye - ys) * rowbytes;
-  const uint32_t bar = smem_u32(smem);
-  const uint32_t ks = smem_u32(smem) + 16, vs = ks + (kAttnRB + 4) * rowbytes;
+  const uint32_t bufbytes = 2u * (kAttnRB + 4) * rowbytes;
+  const uint32_t bar0 = smem_u32(smem);
+  const uint32_t buf0 = smem_u32(smem) + 32;
+  unsigned* cnt = reinterpret_cast<unsigned*>(smem + 16);      // warps that have finished with buffer 0 / 1 (monotonic)
+  const long long PP16 = (long long)P * P * 16;                    // floats per (view, head) plane
+  const int nk = (int)blockIdx.x < nitems ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const unsigned vh0 = blockIdx.x / (unsigned)nblk, dvh = gridDim.x / (unsigned)nblk;   // gridDim.x % nblk == 0 (host)
+  auto plane_of = [&](int k) { return (long long)(vh0 + (unsigned)k * dvh) * PP16; };
   pdl_trigger();
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    cnt[0] = cnt[1] = 0u;
     mbar_fence_init();
   }
   __syncthreads();
   pdl_wait();  // Q / K / V are the previous kernel's output
-  if (threadIdx.x == 0) {
+  auto issue = [&](int k) {   // thread 0: stage item k's K / V rows into buffer k & 1
+    const long long src = plane_of(k) + (long long)ys * (rowbytes / 4);
+    const uint32_t bar = bar0 + 8u * (k & 1), dst = buf0 + (uint32_t)(k & 1) * bufbytes;
     mbar_arrive_expect_tx(bar, 2 * nbytes);
-    const long long src = planar_off(v, head, ys, 0, 0, P);
-    bulk_g2s(ks, K + src, nbytes, bar);
-    bulk_g2s(vs, Vv + src, nbytes, bar);
+    bulk_g2s(dst, K + src, nbytes, bar);
+    bulk_g2s(dst + (kAttnRB + 4) * rowbytes, Vv + src, nbytes, bar);
+  };
+  if (threadIdx.x == 0) {
+    if (nk > 0) issue(0);
+    if (nk > 1) issue(1);
   }
   constexpr bool fp32m = FP32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, c = lane & 3;      // accumulator fragment: rows g, g + 8; columns 2c, 2c + 1
   const int mat = lane >> 3, mr = lane & 7;   // ldmatrix: this lane addresses row mr of matrix mat
-  const long long plane = planar_off(v, head, 0, 0, 0, P);
-  const uint32_t* Qw = reinterpret_cast<const uint32_t*>(Q) + plane;
-  float* Ob = O + plane;
-  constexpr int kBR = kAttnRB / 4;            // block rows per CTA
+  constexpr int kBR = kAttnRB / 4;            // block rows per item
   constexpr int kWC = kAttnMmaThreads / 32 / kBR;   // warps per block row = block-column stride of a warp
   const int bx0 = qr.r0 & ~3;
   const int ncb = (cend - bx0 + 3) >> 2;
@@ -642,115 +658,169 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
   const bool okrow = qyo >= qr.r0 && qyo < rend;
   const uint32_t ooff = (uint32_t)(qyo * 4 + (c >> 1)) * P * 4;
 
-  // Q fragments of block column cb; queries outside the region shadow the nearest valid one (their results are not stored)
-  auto load_q = [&](int cb, uint32_t* qh, uint32_t* ql) {
-    const int qx = min(max(bx0 + 4 * cb + (g & 3), qr.r0), cend - 1);
-    const uint32_t* a = Qw + qoffA + qx * 4;
-    const uint32_t* b = Qw + qoffB + qx * 4;
-    qh[0] = __ldg(a); qh[1] = __ldg(b); qh[2] = __ldg(a + ps); qh[3] = __ldg(b + ps);
-    if (fp32m) { ql[0] = __ldg(a + 2 * ps); ql[1] = __ldg(b + 2 * ps); ql[2] = __ldg(a + 3 * ps); ql[3] = __ldg(b + 3 * ps); }
+  // Q fragments of block column cb of the item whose plane starts at Qw; queries outside the region shadow the nearest valid
+  // one (their results are not stored).  Row B and the pieces are fixed 64-bit strides from row A's first piece.
+  const long long dAB = (long long)qoffB - (long long)qoffA, ps1 = ps, ps2 = 2 * ps, ps3 = 3 * ps;
+  auto load_q = [&](const uint32_t* Qw, int cb, uint32_t* qh, uint32_t* ql) {
+    const int qx = min(bx0 + 4 * cb + (g & 3), P - 1);   // (columns left / right of the region: any written or stale data will do)
+    const uint32_t* a = Qw + (qoffA + (uint32_t)qx * 4u);
+    const uint32_t* b = a + dAB;
+    qh[0] = __ldg(a); qh[1] = __ldg(b); qh[2] = __ldg(a + ps1); qh[3] = __ldg(b + ps1);
+    if (fp32m) { ql[0] = __ldg(a + ps2); ql[1] = __ldg(b + ps2); ql[2] = __ldg(a + ps3); ql[3] = __ldg(b + ps3); }
   };
-  uint32_t qh[4], ql[4] = {0u, 0u, 0u, 0u};
+  const uint32_t* Qall = reinterpret_cast<const uint32_t*>(Q);
+  uint32_t qh[4] = {0u, 0u, 0u, 0u}, ql[4] = {0u, 0u, 0u, 0u};
   const int cb0 = warp / kBR;
-  if (row_active && cb0 < ncb) load_q(cb0, qh, ql);
-  mbar_wait(bar, 0);   // every thread waits for the copies (also before the CTA may exit)
-  if (!row_active) return;
+  const bool has_work = row_active && cb0 < ncb;
+  if (has_work && nk > 0) load_q(Qall + plane_of(0), cb0, qh, ql);
+#ifndef LFT_ATTN_NOSKEW
+  if (warp >= 4) {   // the two warps of a scheduler (w, w + 4) start half a block apart
+    const long long t0 = clock64();
+    while (clock64() - t0 < LFT_ATTN_SKEW) {}
+  }
+#endif
 #pragma unroll 1
-  for (int cb = cb0; cb < ncb; cb += kWC) {
-    const int bx = bx0 + 4 * cb;
-    uint32_t qnh[4], qnl[4] = {0u, 0u, 0u, 0u};
-    if (cb + kWC < ncb) load_q(cb + kWC, qnh, qnl);   // next block's queries in flight under this block's MMAs
-    // ---- S = Q K^T on top of the masks: n8 tile j = key row by - 2 + j, keys bx - 2 .. bx + 5 (column = 2c + e of the tile)
-    const uint32_t kcol = (uint32_t)min(max(bx - 2 + mr, kxlo), kxhi) * 16;
-    float cb_[2];
+  for (int k = 0; k < nk; ++k) {
+    const uint32_t ks = buf0 + (uint32_t)(k & 1) * bufbytes, vs = ks + (kAttnRB + 4) * rowbytes;
+    const long long plane = plane_of(k);
+    const uint32_t* Qw = Qall + plane;
+    const uint32_t* Qn = Qall + plane_of(k + 1);
+    float* Ob = O + plane;
+    mbar_wait(bar0 + 8u * (k & 1), (uint32_t)(k >> 1) & 1u);   // item k's rows have landed
+    if (has_work) {
+#pragma unroll 1
+      for (int cb = cb0; cb < ncb; cb += kWC) {
+        const int bx = bx0 + 4 * cb;
+        uint32_t qnh[4] = {0u, 0u, 0u, 0u}, qnl[4] = {0u, 0u, 0u, 0u};
+        // the next block's queries (of this item or of the next one) in flight under this block's MMAs
+        const bool same = cb + kWC < ncb;
+        if (same || k + 1 < nk) load_q(same ? Qw : Qn, same ? cb + kWC : cb0, qnh, qnl);
+        // ---- S = Q K^T on top of the masks: n8 tile j = key row by - 2 + j, keys bx - 2 .. bx + 5 (column = 2c + e of the tile)
+        const uint32_t kcol = (uint32_t)min(max(bx - 2 + mr, kxlo), kxhi) * 16;
+        float cb_[2];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) cb_[e] = (dxok[e] && (unsigned)(bx - 2 + 2 * c + e) < (unsigned)P) ? 0.f : NINF;
-    float s[8][4];
+        for (int e = 0; e < 2; ++e) cb_[e] = (dxok[e] && (unsigned)(bx - 2 + 2 * c + e) < (unsigned)P) ? 0.f : NINF;
+        float s[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8; ++j) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        s[j][e] = j < 6 ? fminf(rbA[j], cb_[e]) : NINF;
-        s[j][2 + e] = j >= 2 ? fminf(rbB[j - 2], cb_[e]) : NINF;
-      }
-      uint32_t kb[4];
-      ldsm4(ks + koff[j] + kcol, kb);
-      hmma16816(s[j], qh, kb[0], kb[1]);
-      if (fp32m) {
-        hmma16816(s[j], ql, kb[0], kb[1]);
-        hmma16816(s[j], qh, kb[2], kb[3]);
+          for (int e = 0; e < 2; ++e) {
+            s[j][e] = j < 6 ? fminf(rbA[j], cb_[e]) : NINF;
+            s[j][2 + e] = j >= 2 ? fminf(rbB[j - 2], cb_[e]) : NINF;
+          }
+          uint32_t kb[4];
+          ldsm4(ks + koff[j] + kcol, kb);
+          hmma16816(s[j], qh, kb[0], kb[1]);
+          if (fp32m) {
+            hmma16816(s[j], ql, kb[0], kb[1]);
+            hmma16816(s[j], qh, kb[2], kb[3]);
+          }
+        }
+        // ---- soft-max (masked entries are -inf; every query sees itself, so the row maxima are finite).  Packed f32x2 math on
+        // the accumulator pairs, two partial sums per row half (short dependency chains: four warps per scheduler is all the
+        // latency hiding there is)
+        float mA0 = fmaxf(s[0][0], s[0][1]), mA1 = fmaxf(s[1][0], s[1][1]);
+        float mB0 = fmaxf(s[2][2], s[2][3]), mB1 = fmaxf(s[3][2], s[3][3]);
+#pragma unroll
+        for (int j = 2; j < 6; j += 2) {
+          mA0 = fmaxf(mA0, fmaxf(s[j][0], s[j][1]));
+          mA1 = fmaxf(mA1, fmaxf(s[j + 1][0], s[j + 1][1]));
+          mB0 = fmaxf(mB0, fmaxf(s[j + 2][2], s[j + 2][3]));
+          mB1 = fmaxf(mB1, fmaxf(s[j + 3][2], s[j + 3][3]));
+        }
+        float mA = fmaxf(mA0, mA1), mB = fmaxf(mB0, mB1);
+        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
+        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+        const f32x2 qs2 = pack2(qs, qs), nA2 = pack2(-mA * qs, -mA * qs), nB2 = pack2(-mB * qs, -mB * qs);
+        const f32x2 neg1 = pack2(-1.f, -1.f);
+        f32x2 lA2[2] = {0ull, 0ull}, lB2[2] = {0ull, 0ull};
+        // P as the A operands of the four k16 steps: pa[t] = {row A tile 2t, row B tile 2t, row A tile 2t+1, row B tile 2t+1}
+        uint32_t pa[4][4], pb[4][4];
+        auto prob = [&](float x0, float x1, f32x2 n2, f32x2& l2, uint32_t& hi, uint32_t& lo) {
+          float e0, e1;
+          unpack2(fma2(pack2(x0, x1), qs2, n2), e0, e1);
+          const float p0 = fast_exp2(e0), p1 = fast_exp2(e1);
+          const f32x2 pp = pack2(p0, p1);
+          l2 = add2(l2, pp);
+          if (fp32m) {
+            const uint32_t u0 = __float_as_uint(p0), u1 = __float_as_uint(p1);
+            hi = __byte_perm(u0, u1, 0x7632);
+            float r0, r1;   // p - trunc_bf16(p), exact
+            unpack2(fma2(pack2(__uint_as_float(u0 & 0xffff0000u), __uint_as_float(u1 & 0xffff0000u)), neg1, pp), r0, r1);
+            lo = pack_bf16(r0, r1);
+          } else {
+            hi = pack_bf16(p0, p1);
+            lo = 0u;
+          }
+        };
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int t = j >> 1, h = (j & 1) * 2;
+          if (j < 6) prob(s[j][0], s[j][1], nA2, lA2[j & 1], pa[t][h], pb[t][h]);
+          else pa[t][h] = pb[t][h] = 0u;
+          if (j >= 2) prob(s[j][2], s[j][3], nB2, lB2[j & 1], pa[t][h + 1], pb[t][h + 1]);
+          else pa[t][h + 1] = pb[t][h + 1] = 0u;
+        }
+        float lA = hsum2(add2(lA2[0], lA2[1])), lB = hsum2(add2(lB2[0], lB2[1]));
+        lA += __shfl_xor_sync(0xffffffffu, lA, 1);
+        lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+        lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+        lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+        // ---- O = P V: k16 step t = key rows by - 2 + 2t, + 1; n8 tile d = dims 8d .. 8d + 7
+        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float o2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // odd k steps: two more independent accumulation chains
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t va = vs + voff[t] + kcol;
+          float (*oo)[4] = (t & 1) ? o2 : o;
+          uint32_t vh[4];
+          ldsm4t(va, vh);   // {keys 0-7, keys 8-15} x {dims 0-7, dims 8-15} of the hi pieces
+          hmma16816(oo[0], pa[t], vh[0], vh[1]);
+          hmma16816(oo[1], pa[t], vh[2], vh[3]);
+          if (fp32m) {
+            hmma16816(oo[0], pb[t], vh[0], vh[1]);
+            hmma16816(oo[1], pb[t], vh[2], vh[3]);
+            uint32_t vl[4];
+            ldsm4t(va + 2 * piecebytes, vl);
+            hmma16816(oo[0], pa[t], vl[0], vl[1]);
+            hmma16816(oo[1], pa[t], vl[2], vl[3]);
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+#pragma unroll
+          for (int i = 0; i < 4; i += 2) {
+            float x0, x1;
+            unpack2(add2(pack2(o[d][i], o[d][i + 1]), pack2(o2[d][i], o2[d][i + 1])), x0, x1);
+            o[d][i] = x0; o[d][i + 1] = x1;
+          }
+        // ---- normalise and store (fp32 planar, as k_spa_ffn reads it): the lanes of a pair (c, c ^ 1) hold the two halves of
+        // a 16-byte piece; the even lane stores row A's piece, the odd lane row B's
+        const float iA_ = fast_rcp(lA), iB_ = fast_rcp(lB);   // l in [1, 25]: rcp.approx is within 1 ulp
+        const int qx = bx + (g & 3);
+        const bool okq = okrow && qx >= qr.r0 && qx < cend;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const float a0 = o[d][0] * iA_, a1 = o[d][1] * iA_, b0 = o[d][2] * iB_, b1 = o[d][3] * iB_;
+          const float r0_ = __shfl_xor_sync(0xffffffffu, odd ? a0 : b0, 1);
+          const float r1_ = __shfl_xor_sync(0xffffffffu, odd ? a1 : b1, 1);
+          const float4 out = odd ? make_float4(r0_, r1_, b0, b1) : make_float4(a0, a1, r0_, r1_);
+          if (okq) st_stream_v4(Ob + ooff + (uint32_t)(2 * d * P + qx) * 4, out);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { qh[i] = qnh[i]; ql[i] = qnl[i]; }
       }
     }
-    // ---- soft-max (masked entries are -inf; every query sees itself, so the row maxima are finite)
-    float mA = s[0][0], mB = s[2][2];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      mA = fmaxf(mA, fmaxf(s[j][0], s[j][1]));
-      mB = fmaxf(mB, fmaxf(s[j + 2][2], s[j + 2][3]));
+    // Buffer release without a CTA-wide barrier (the warps of a scheduler should drift apart: in lockstep they all want the
+    // tensor pipe, then all the ALUs): every warp counts itself off item k; the last one refills the buffer with item k + 2.
+    // A warp's ldmatrix reads have completed when it gets here (their HMMAs have been issued).
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned done = atomicAdd(&cnt[k & 1], 1u) + 1u;
+      if (done == (unsigned)(kAttnMmaThreads / 32) * (unsigned)((k >> 1) + 1) && k + 2 < nk) issue(k + 2);
     }
-    mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
-    mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
-    mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
-    mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
-    const float nA = -mA * qs, nB = -mB * qs;
-    float lA = 0.f, lB = 0.f;
-    uint32_t ph[8][2], pl[8][2];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < 6) {
-        const float p0 = fast_exp2(fmaf(s[j][0], qs, nA)), p1 = fast_exp2(fmaf(s[j][1], qs, nA));
-        lA += p0 + p1;
-        split_pair(p0, p1, fp32m, ph[j][0], pl[j][0]);
-      } else {
-        ph[j][0] = pl[j][0] = 0u;
-      }
-      if (j >= 2) {
-        const float p2 = fast_exp2(fmaf(s[j][2], qs, nB)), p3 = fast_exp2(fmaf(s[j][3], qs, nB));
-        lB += p2 + p3;
-        split_pair(p2, p3, fp32m, ph[j][1], pl[j][1]);
-      } else {
-        ph[j][1] = pl[j][1] = 0u;
-      }
-    }
-    lA += __shfl_xor_sync(0xffffffffu, lA, 1);
-    lA += __shfl_xor_sync(0xffffffffu, lA, 2);
-    lB += __shfl_xor_sync(0xffffffffu, lB, 1);
-    lB += __shfl_xor_sync(0xffffffffu, lB, 2);
-    // ---- O = P V: k16 step t = key rows by - 2 + 2t, + 1; n8 tile d = dims 8d .. 8d + 7
-    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const uint32_t va = vs + voff[t] + kcol;
-      uint32_t vh[4];
-      ldsm4t(va, vh);   // {keys 0-7, keys 8-15} x {dims 0-7, dims 8-15} of the hi pieces
-      const uint32_t ah[4] = {ph[2 * t][0], ph[2 * t][1], ph[2 * t + 1][0], ph[2 * t + 1][1]};
-      hmma16816(o[0], ah, vh[0], vh[1]);
-      hmma16816(o[1], ah, vh[2], vh[3]);
-      if (fp32m) {
-        const uint32_t al[4] = {pl[2 * t][0], pl[2 * t][1], pl[2 * t + 1][0], pl[2 * t + 1][1]};
-        hmma16816(o[0], al, vh[0], vh[1]);
-        hmma16816(o[1], al, vh[2], vh[3]);
-        uint32_t vl[4];
-        ldsm4t(va + 2 * piecebytes, vl);
-        hmma16816(o[0], ah, vl[0], vl[1]);
-        hmma16816(o[1], ah, vl[2], vl[3]);
-      }
-    }
-    // ---- normalise and store (fp32 planar, as k_spa_ffn reads it): the lanes of a pair (c, c ^ 1) hold the two halves of a
-    // 16-byte piece; the even lane stores row A's piece, the odd lane row B's
-    const float iA_ = 1.f / lA, iB_ = 1.f / lB;
-    const int qx = bx + (g & 3);
-    const bool okq = okrow && qx >= qr.r0 && qx < cend;
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const float a0 = o[d][0] * iA_, a1 = o[d][1] * iA_, b0 = o[d][2] * iB_, b1 = o[d][3] * iB_;
-      const float r0_ = __shfl_xor_sync(0xffffffffu, odd ? a0 : b0, 1);
-      const float r1_ = __shfl_xor_sync(0xffffffffu, odd ? a1 : b1, 1);
-      const float4 out = odd ? make_float4(r0_, r1_, b0, b1) : make_float4(a0, a1, r0_, r1_);
-      if (okq) st_stream_v4(Ob + ooff + (uint32_t)(2 * d * P + qx) * 4, out);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { qh[i] = qnh[i]; ql[i] = qnl[i]; }
   }
 }
 
@@ -1314,8 +1384,8 @@ int configure_spa() {
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
-  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
-  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn_mma(64)));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn_mma(64)));
   return 0;
 }
 
@@ -1359,14 +1429,18 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     const int nblk = (need.rn + kAttnRB - 1) / kAttnRB;
     if (kAttnMma) {
       const int nb = ((need.r0 + need.rn) - (need.r0 & ~3) + kAttnRB - 1) / kAttnRB;  // attn_mma_nblk
+      const long long items = V * 8 * nb;
+      if (items >= (1ll << 31)) return fail(LFT_ERR_ARG, "k_spa_attn_mma: too many work items");
+      const long long maxg = 2ll * h->num_sms;   // persistent: two CTAs per SM; a multiple of nb so that a CTA keeps its row block
+      const unsigned pg = (unsigned)(items <= maxg ? items : (maxg / nb) * nb);
       if (h->passes() == 3) {
         auto kern = k_spa_attn_mma<true>;
-        LFT_LAUNCH(h, kern, (unsigned)(V * 8 * nb), kAttnMmaThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
-                   (const float*)w.v, w.o, P, need);
+        LFT_LAUNCH(h, kern, pg, kAttnMmaThreads, smem_attn_mma(P), st, (const float*)w.q, (const float*)w.k, (const float*)w.v,
+                   w.o, P, need, (int)items);
       } else {
         auto kern = k_spa_attn_mma<false>;
-        LFT_LAUNCH(h, kern, (unsigned)(V * 8 * nb), kAttnMmaThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
-                   (const float*)w.v, w.o, P, need);
+        LFT_LAUNCH(h, kern, pg, kAttnMmaThreads, smem_attn_mma(P), st, (const float*)w.q, (const float*)w.k, (const float*)w.v,
+                   w.o, P, need, (int)items);
       }
     } else {
       LFT_LAUNCH(h, k_spa_attn, (unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
