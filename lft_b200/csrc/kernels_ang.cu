@@ -363,6 +363,217 @@ LFT_DEVINL void ang_attention_items(uint32_t trow, int warp, int lane, int q, in
   convert(1);
 }
 
+// A = 5 on tensor cores (round 2, the default for NV = 25; -DLFT_ANG_ITEMS_V1 selects the FFMA2 items above): the same
+// (pixel, head) work items, but S = Q K^T and O = P V are warp-level mma.sync.m16n8k16 (bf16 hi / lo, fp32 accumulate).
+//   queries 25 -> two m16 tiles (views 0..15, 16..31: the rows beyond view 24 shadow it and are not written back)
+//   keys    25 -> four n8 tiles (keys 25..31 are masked: -inf as the accumulator's initial value)
+//   S       : the head dimension is 8, so hi and lo ride side by side along k = 16: A = [Q_hi | Q_lo],
+//             B = [K_hi | K_hi] gives Q_hi K_hi + Q_lo K_hi in ONE instruction, B = [K_lo | 0] adds Q_hi K_lo  (16 HMMA)
+//   O = P V : k = keys (two k16 steps), n = the 8 dims; P_hi V_hi + P_lo V_hi + P_hi V_lo                      (12 HMMA)
+// The planes keep their geometry ([rel head 4][2][kv row 128][16 B], kv row = view * 5 + pixel) but hold bf16: slot 0 = hi of
+// the head's 8 dims, slot 1 = lo - exactly the 8 x 8 b16 matrices ldmatrix wants (rows of one pixel are 80 bytes apart: the
+// eight 16-byte rows of a matrix fall into eight different bank groups).  O (fp32) overwrites the item's own Q rows: dims
+// 0..3 in slot 0, dims 4..7 in slot 1, which is what convert() reads.
+LFT_DEVINL void ang_ldsm4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+LFT_DEVINL void ang_ldsm4t(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+LFT_DEVINL void ang_hmma(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, int kvrow, float rstd, float mr,
+                                    const float4* __restrict__ pq4, const float4* tab4, uint8_t* planes, bool fp32_mode) {
+  constexpr int N = 25, PPT = 5;
+  uint8_t* qo_ptr = planes;           // R1: Q / O of head half 0 (16 KB) | of head half 1 (16 KB)
+  uint8_t* ks_ptr = planes + 32768;   // R2: K 16 KB | V 16 KB
+  uint8_t* vs_ptr = ks_ptr + 16384;
+  const float scale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e)/sqrt(8), folded into Q (softmax via exp2)
+  const int g = lane >> 2, c = lane & 3;      // accumulator fragment: rows g, g + 8; columns 2c, 2c + 1
+  const int mat = lane >> 3, mrow = lane & 7; // ldmatrix: this lane addresses row mrow of matrix mat
+  // 8 values of one head -> the hi and the lo piece of this row
+  auto put = [&](uint8_t* plane, int rh, const float* x) {
+    uint4 hi, lo;
+    split8(x, hi, lo, fp32_mode);
+    *reinterpret_cast<uint4*>(plane + (rh * 2) * 2048 + kvrow * 16) = hi;
+    *reinterpret_cast<uint4*>(plane + (rh * 2 + 1) * 2048 + kvrow * 16) = lo;
+  };
+  // results of head half hg: shared memory (fp32) -> bf16 hi/lo TS-form operand; the two threads of a row take two heads each
+  auto convert = [&](int hg) {
+    const uint8_t* src = qo_ptr + hg * 16384 + kvrow * 16;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int rh = 2 * q + hh;
+      float o[8];
+      *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(src + (rh * 2) * 2048);
+      *reinterpret_cast<float4*>(o + 4) = *reinterpret_cast<const float4*>(src + (rh * 2 + 1) * 2048);
+      uint4 hi, lo;
+      split8(o, hi, lo, fp32_mode);
+      tmem_st4u(trow + 64 + 16 * hg + 4 * rh, hi);
+      if (fp32_mode) tmem_st4u(trow + 96 + 16 * hg + 4 * rh, lo);
+    }
+  };
+  // per-lane ldmatrix row offsets inside a (rel head, pixel) item: view = 8 * matrix-in-group + mrow, rows beyond view 24 shadow it
+  uint32_t aoff[2], koff;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)   // A = [Q_hi rows 0-7, Q_hi rows 8-15, Q_lo rows 0-7, Q_lo rows 8-15] of m16 tile mt
+    aoff[mt] = (uint32_t)(mat >> 1) * 2048u + (uint32_t)min(16 * mt + 8 * (mat & 1) + mrow, N - 1) * (PPT * 16);
+  koff = (uint32_t)min(8 * mat + mrow, N - 1) * (PPT * 16);   // K / V: matrix = keys 8 mat .. 8 mat + 7 (slot 0: hi; + 2048: lo)
+  const float ninf = -INFINITY;
+  const float b3 = c == 0 ? 0.f : ninf;   // n8 tile 3 = keys 24 + 2c + e: only key 24 exists
+#pragma unroll 1
+  for (int hg = 0; hg < 2; ++hg) {
+    float kv[16];
+    LFT_TL(12 + 4 * hg);
+    if (q == 0) {  // K of heads 4hg..4hg+3 (accumulator columns 64 + 32hg ..), corrected
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = 64 + 32 * hg + 16 * cc;
+        tmem_ld16(trow + col, kv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
+          const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
+          kv[4 * j] = fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
+          kv[4 * j + 1] = fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
+          kv[4 * j + 2] = fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
+          kv[4 * j + 3] = fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+        }
+        put(ks_ptr, 2 * cc, kv);
+        put(ks_ptr, 2 * cc + 1, kv + 8);
+      }
+    } else {       // V (raw) and Q (corrected, pre-scaled) of the same heads
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld16(trow + 128 + 32 * hg + 16 * cc, kv);
+        put(vs_ptr, 2 * cc, kv);
+        put(vs_ptr, 2 * cc + 1, kv + 8);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = 32 * hg + 16 * cc;
+        tmem_ld16(trow + col, kv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
+          const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
+          kv[4 * j] = scale * fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
+          kv[4 * j + 1] = scale * fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
+          kv[4 * j + 2] = scale * fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
+          kv[4 * j + 3] = scale * fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+        }
+        put(qo_ptr + hg * 16384, 2 * cc, kv);
+        put(qo_ptr + hg * 16384, 2 * cc + 1, kv + 8);
+      }
+    }
+    LFT_TL(13 + 4 * hg);
+    tc_fence_before();
+    rows_bar_sync256();  // planes of half hg complete; for hg = 1: every Q / K / V accumulator column has been consumed
+    tc_fence_after();
+    LFT_TL(14 + 4 * hg);
+    if (hg == 1) convert(0);
+    const uint32_t qo_u = smem_u32(qo_ptr + hg * 16384), ks_u = smem_u32(ks_ptr), vs_u = smem_u32(vs_ptr);
+#pragma unroll 1
+    for (int it = warp; it < 4 * PPT; it += 8) {  // item = (rel head, pixel)
+      const int rh = it / PPT, p = it - rh * PPT;
+      const uint32_t ioff = (uint32_t)rh * 4096u + (uint32_t)p * 16u;
+      uint32_t a0[4], a1[4], kh[4], kl[4];
+      ang_ldsm4(qo_u + ioff + aoff[0], a0);
+      ang_ldsm4(qo_u + ioff + aoff[1], a1);
+      ang_ldsm4(ks_u + ioff + koff, kh);
+      if (fp32_mode) ang_ldsm4(ks_u + ioff + 2048u + koff, kl);
+      float s[2][4][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          s[mt][n][0] = s[mt][n][2] = n == 3 ? b3 : 0.f;
+          s[mt][n][1] = s[mt][n][3] = n == 3 ? ninf : 0.f;
+        }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        ang_hmma(s[0][n], a0, kh[n], kh[n]);
+        ang_hmma(s[1][n], a1, kh[n], kh[n]);
+        if (fp32_mode) {
+          ang_hmma(s[0][n], a0, kl[n], 0u);
+          ang_hmma(s[1][n], a1, kl[n], 0u);
+        }
+      }
+      // soft-max over the 25 keys of each of the four rows this thread holds a slice of (rows g, g+8 of both m tiles)
+      uint32_t ph[2][2][4], pl_[2][2][4];   // [m tile][k16 step] A operands
+      float linv[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {   // row g (hf 0) / g + 8 (hf 1)
+          float mx = fmaxf(fmaxf(s[mt][0][2 * hf], s[mt][0][2 * hf + 1]), fmaxf(s[mt][1][2 * hf], s[mt][1][2 * hf + 1]));
+          mx = fmaxf(mx, fmaxf(fmaxf(s[mt][2][2 * hf], s[mt][2][2 * hf + 1]), s[mt][3][2 * hf]));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float l = 0.f;
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const float p0 = fast_exp2(s[mt][n][2 * hf] - mx);
+            const float p1 = n == 3 ? 0.f : fast_exp2(s[mt][n][2 * hf + 1] - mx);
+            l += p0 + p1;
+            uint32_t hi, lo;
+            if (fp32_mode) {
+              const uint32_t u0 = __float_as_uint(p0), u1 = __float_as_uint(p1);
+              hi = __byte_perm(u0, u1, 0x7632);
+              lo = pack_bf16(p0 - __uint_as_float(u0 & 0xffff0000u), p1 - __uint_as_float(u1 & 0xffff0000u));
+            } else {
+              hi = pack_bf16(p0, p1);
+              lo = 0u;
+            }
+            ph[mt][n >> 1][2 * (n & 1) + hf] = hi;
+            pl_[mt][n >> 1][2 * (n & 1) + hf] = lo;
+          }
+          l += __shfl_xor_sync(0xffffffffu, l, 1);
+          l += __shfl_xor_sync(0xffffffffu, l, 2);
+          linv[mt][hf] = fast_rcp(l);   // l in [1, 25]
+        }
+      // O = P V
+      uint32_t vh[4], vl[4];
+      ang_ldsm4t(vs_u + ioff + koff, vh);
+      if (fp32_mode) ang_ldsm4t(vs_u + ioff + 2048u + koff, vl);
+      float o[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          ang_hmma(o[mt], ph[mt][t], vh[2 * t], vh[2 * t + 1]);
+          if (fp32_mode) {
+            ang_hmma(o[mt], pl_[mt][t], vh[2 * t], vh[2 * t + 1]);
+            ang_hmma(o[mt], ph[mt][t], vl[2 * t], vl[2 * t + 1]);
+          }
+        }
+      }
+      // write O (fp32) over the item's own Q rows: dims 2c, 2c + 1 -> slot c / 2, bytes 8 (c & 1)
+      uint8_t* obase = qo_ptr + hg * 16384 + rh * 4096 + (c >> 1) * 2048 + p * 16 + (c & 1) * 8;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int view = 16 * mt + 8 * hf + g;
+          if (view < N)
+            *reinterpret_cast<float2*>(obase + view * (PPT * 16)) =
+                make_float2(o[mt][2 * hf] * linv[mt][hf], o[mt][2 * hf + 1] * linv[mt][hf]);
+        }
+    }
+    LFT_TL(15 + 4 * hg);
+    rows_bar_sync256();  // results of half hg complete; K / V planes free for the next half
+  }
+  LFT_TL(20);
+  convert(1);
+}
+
 // NV > 0: compile-time number of views (scores kept in registers, single QK pass); NV == 0: runtime N.
 template <int NV>
 __global__ void __launch_bounds__(kThreads2, 2)
@@ -546,6 +757,11 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       const float4* pq4 = reinterpret_cast<const float4*>(peqk) + aa;  // [chunk 32][N][4]: Q chunks 0..15, K 16..31
       const float4* tab4 = reinterpret_cast<const float4*>(tab.v);    // [u_qk 128 | c_qk 128 | u_1 128 | c_1 128] (constant bank)
       if constexpr (NV == 25 || NV == 49 || NV == 81) {
+#ifndef LFT_ANG_ITEMS_V1
+        if constexpr (NV == 25)
+          ang_attention_mma25(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes, passes == 3);
+        else
+#endif
         ang_attention_items<NV, kPPT, kCH>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes, passes == 3);
         LFT_TL(4);
         tmem_wait_st();

@@ -235,8 +235,10 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
 #pragma unroll
           for (int i = 0; i < 16; ++i) z[16 * c + i] += t[i];
           a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, z + 16 * c, passes == 3);
+          LFT_TL2(22 + c);
         }
         pair_ln_stats<64>(z, trow + 64 * q, trow + 64 * (1 - q), 1 + (warp & 3), mean, rstd);
+        LFT_TL2(26);
 #if defined(LFT_X_ZTOK)   // timing experiment (ffn then reads z instead of tok): the token store leaves the z -> Q critical path
         tmem_wait_st();
         tc_fence_before();
