@@ -74,6 +74,12 @@ constexpr bool kAttnMma = false;
 #else
 constexpr bool kAttnMma = true;
 #endif
+// O between k_spa_attn_mma and k_spa_ffn2: operand tiles (default) or fp32 planar (-DLFT_O_PLANAR, and with the V1 kernels)
+#if defined(LFT_ATTN_V1) || defined(LFT_FFN_V1) || defined(LFT_O_PLANAR)
+constexpr int kOTile = 0;
+#else
+constexpr int kOTile = 1;
+#endif
 
 // split 16 fp32 values into two k-chunks (kc0, kc0+1) of the K=128 A operand (hi at A, lo at A+32K)
 LFT_DEVINL void a_store16(uint32_t A, int kc0, int m, const float* x, bool fp32_mode) {
@@ -575,7 +581,10 @@ constexpr size_t smem_attn_mma(int P) { return 32 + 2 * 2 * (size_t)(kAttnRB + 4
 template <bool FP32>
 __global__ void __launch_bounds__(kAttnMmaThreads, 2)
 k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ Vv,
-               float* __restrict__ O, int P, Region qr, int nitems) {
+               float* __restrict__ O, int P, Region qr, int nitems, int otile) {
+  // otile != 0: O leaves as the bf16 hi / lo A operand of k_spa_ffn2's output projection, tile by tile in the operand's own
+  // shared-memory layout [tile of 128 compacted tokens][hi | lo][k chunk 16][row 128][8 bf16] (64 KB per tile, channel =
+  // head * 16 + dim), which k_spa_ffn2 fetches with two bulk copies; otile == 0: fp32 planar (the layout of Q / K / V).
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nblk = attn_mma_nblk(qr);
   const int rb = blockIdx.x % nblk;
@@ -659,6 +668,10 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
   const int qyo = by + iA + (odd ? 2 : 0);    // the row this lane stores (even lanes: row A's piece, odd lanes: row B's)
   const bool okrow = qyo >= qr.r0 && qyo < rend;
   const uint32_t ooff = (uint32_t)(qyo * 4 + (c >> 1)) * P * 4;
+  // tile-format output: compacted token of (view, y, x) = (view * rn + y - r0) * rn + x - r0
+  const int tyA = by + iA - qr.r0, tyB = tyA + 2;
+  const bool okA = tyA >= 0 && tyA < qr.rn, okB = tyB >= 0 && tyB < qr.rn;
+  uint32_t* Ot = reinterpret_cast<uint32_t*>(O);
 
   // Q fragments of block column cb of the item whose plane starts at Qw; queries outside the region shadow the nearest valid
   // one (their results are not stored).  Row B and the pieces are fixed 64-bit strides from row A's first piece.
@@ -685,6 +698,8 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
   for (int k = 0; k < nk; ++k) {
     const uint32_t ks = buf0 + (uint32_t)(k & 1) * bufbytes, vs = ks + (kAttnRB + 4) * rowbytes;
     const long long plane = plane_of(k);
+    const unsigned vhk = vh0 + (unsigned)k * dvh, vq = vhk >> 3;
+    const int head = (int)(vhk & 7u);
     const uint32_t* Qw = Qall + plane;
     const uint32_t* Qn = Qall + plane_of(k + 1);
     float* Ob = O + plane;
@@ -802,6 +817,28 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
         // a 16-byte piece; the even lane stores row A's piece, the odd lane row B's
         const float iA_ = fast_rcp(lA), iB_ = fast_rcp(lB);   // l in [1, 25]: rcp.approx is within 1 ulp
         const int qx = bx + (g & 3);
+        if (otile) {
+          const int tx = qx - qr.r0;
+          if (tx >= 0 && tx < qr.rn) {
+            const unsigned tv = vq * (unsigned)(qr.rn * qr.rn) + (unsigned)tx;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              if (hf ? okB : okA) {
+                const unsigned t = tv + (unsigned)((hf ? tyB : tyA) * qr.rn);
+                // 32-bit words: tile * 16384 + plane * 8192 + k chunk * 512 + row * 4 + c
+                uint32_t* dst = Ot + (size_t)(t >> 7) * 16384u + (uint32_t)(head * 2) * 512u + (t & 127u) * 4u + c;
+                const float inv = hf ? iB_ : iA_;
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                  uint32_t hi, lo;
+                  split_pair(o[d][2 * hf] * inv, o[d][2 * hf + 1] * inv, fp32m, hi, lo);
+                  dst[d * 512] = hi;
+                  if (fp32m) dst[8192 + d * 512] = lo;
+                }
+              }
+            }
+          }
+        } else {
         const bool okq = okrow && qx >= qr.r0 && qx < cend;
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
@@ -810,6 +847,7 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
           const float r1_ = __shfl_xor_sync(0xffffffffu, odd ? a1 : b1, 1);
           const float4 out = odd ? make_float4(r0_, r1_, b0, b1) : make_float4(a0, a1, r0_, r1_);
           if (okq) st_stream_v4(Ob + ooff + (uint32_t)(2 * d * P + qx) * 4, out);
+        }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) { qh[i] = qnh[i]; ql[i] = qnl[i]; }
@@ -1108,7 +1146,11 @@ __global__ void __launch_bounds__(kThreads2, 2)
 k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_constant__ Tab512 tab,
            const uint8_t* __restrict__ wo, const uint8_t* __restrict__ w1a, const uint8_t* __restrict__ w1b,
            const uint8_t* __restrict__ w2a, const uint8_t* __restrict__ w2b, const uint8_t* __restrict__ wlin,
-           float* __restrict__ out, const float* __restrict__ final_res, long long T, int P, int passes, Region fr) {
+           float* __restrict__ out, const float* __restrict__ final_res, long long T, int P, int passes, Region fr,
+           int otile) {
+  // otile != 0: `O` holds the attention output as ready-made bf16 hi / lo operand tiles (k_spa_attn_mma): the producer warp
+  // fetches this CTA's tile into the operand area with two bulk copies and the output projection runs in SS form - the row
+  // owners have no phase 0 (no gather, no split, no operand stores), so the first GEMM starts as soon as the copy lands.
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   const uint32_t A = smem_u32(smem) + kCtlBytes;
@@ -1116,11 +1158,13 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
   const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t a_ready = smem_u32(&ctl->a_ready), mma_done = smem_u32(&ctl->mma_done);
   const uint32_t f2a_done = smem_u32(&ctl->aux[1]);  // completed by one tcgen05.commit (re-initialised below)
+  const uint32_t o_full = smem_u32(&ctl->aux[2]);    // completed by the O tile's bulk copies (re-initialised below)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_trigger();
   cta_setup<kSpaNST>(ctl, warp, lane, kRowThreads2, 256, kWarpMma2);
   if (tid == 0) {
     mbar_init(f2a_done, 1);
+    mbar_init(o_full, 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -1131,6 +1175,16 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
 
   if (warp == kWarpProducer2) {
     RingState<kSpaNST> rs;  // consumption order
+    if (otile) {
+      pdl_wait();  // the tile is the previous kernel's output
+      if (elect_one()) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(O) + (size_t)blockIdx.x * 65536u;
+        mbar_arrive_expect_tx(o_full, fp32m ? 65536u : 32768u);
+        bulk_g2s(A, src, 32768u, o_full);
+        if (fp32m) bulk_g2s(A + 32768u, src + 32768u, 32768u, o_full);
+      }
+      __syncwarp();
+    }
     ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_o, passes);
     ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_1a, passes);
     ring_produce<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g_2a, passes);
@@ -1153,7 +1207,13 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
       ring_consume_mma_ts<kSpaNST>(rs, ring, kSpaStage, full0, empty0, g, passes, tmem + 128, tmem + 192, tmem + 0, fresh);
     };
     auto done = [&]() { umma_commit_elected(mma_done); };
-    wait_a(); gemm_ts(g_o, true); done();            // D = O Wo^T
+    if (otile) {
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+      gemm_ss(g_o, 0); done();                       // D = O Wo^T, operand tile fetched by the producer
+    } else {
+      wait_a(); gemm_ts(g_o, true); done();          // D = O Wo^T
+    }
     wait_a(); gemm_ss(g_1a, 0); done();              // D = Y1 W'1a^T
     wait_a(); gemm_ts(g_2a, true);                   // D = hidden_a W2a^T
     umma_commit_elected(f2a_done);
@@ -1196,7 +1256,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
     pdl_wait();  // O / tok are the previous kernels' output
 
     // phase 0: T <- O (planar gather of own heads 4q..4q+3)
-    {
+    if (!otile) {
       float4 f[16];
       const float* ob = O + planar_off(v, 4 * q, y, 0, x, P);
       const long long hs = (long long)PP * 16, js = (long long)P * 4;  // head / piece strides in floats
@@ -1207,8 +1267,8 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, reinterpret_cast<const float*>(&f[4 * c]), fp32m);
+      publish_tmem();
     }
-    publish_tmem();
 
     // phase 1: Y1 = tok + D (own half) -> bf16 hi/lo operand in shared memory (kept until the end); LN2 statistics
     float mean, rstd;
@@ -1247,13 +1307,19 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
         unsigned vn;
         int yn, xn;
         const unsigned tnu = locate((unsigned)tn, vn, yn, xn);
-        const float* obn = O + planar_off(vn, 4 * q, yn, 0, xn, P);
-        const long long hs = (long long)PP * 16, js = (long long)P * 4;
         const float* tgn = tok + t32_off(tnu, 16 * q, 32);
+        if (otile) {   // that CTA's operand tile: 512 lines of 128 bytes, two per row-owner thread
+          const uint8_t* on = reinterpret_cast<const uint8_t*>(O) + ((size_t)blockIdx.x + 296u) * 65536u + (size_t)tid * 256u;
+          prefetch_l2(on);
+          prefetch_l2(on + 128);
+        } else {
+          const float* obn = O + planar_off(vn, 4 * q, yn, 0, xn, P);
+          const long long hs = (long long)PP * 16, js = (long long)P * 4;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) prefetch_l2(obn + c * hs + j * js);
+            for (int j = 0; j < 4; ++j) prefetch_l2(obn + c * hs + j * js);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) prefetch_l2(tgn + 128 * i);
       }
@@ -1438,11 +1504,11 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
       if (h->passes() == 3) {
         auto kern = k_spa_attn_mma<true>;
         LFT_LAUNCH(h, kern, pg, kAttnMmaThreads, smem_attn_mma(P), st, (const float*)w.q, (const float*)w.k, (const float*)w.v,
-                   w.o, P, need, (int)items);
+                   w.o, P, need, (int)items, kOTile);
       } else {
         auto kern = k_spa_attn_mma<false>;
         LFT_LAUNCH(h, kern, pg, kAttnMmaThreads, smem_attn_mma(P), st, (const float*)w.q, (const float*)w.k, (const float*)w.v,
-                   w.o, P, need, (int)items);
+                   w.o, P, need, (int)items, kOTile);
       }
     } else {
       LFT_LAUNCH(h, k_spa_attn, (unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
@@ -1460,7 +1526,7 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
                L.s_w1b, L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P, h->passes(), need);
 #else
     LFT_LAUNCH(h, k_spa_ffn2, (unsigned)((T + 127) / 128), kThreads2, kSmemSpa, st, (const float*)w.o, w.tok, tf, L.s_wo, L.s_w1a,
-               L.s_w1b, L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P, h->passes(), need);
+               L.s_w1b, L.s_w2a, L.s_w2b, L.s_wlin, out, final_res, T, P, h->passes(), need, kOTile);
 #endif
     if ((rc = sc.finish())) return rc;
   }

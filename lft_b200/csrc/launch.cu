@@ -29,7 +29,7 @@ int configure_kernels(int device) {
 size_t ws_floats_per_token(int scale) { return 4 * 64 + 5 * 128 + 9 * (size_t)scale * scale + 1; }
 
 Workspace carve(void* ws, long long T, int scale) {
-  T = (T + 31) / 32 * 32;  // T32 layout: whole 32-token blocks
+  T = (T + 127) / 128 * 128;  // T32 layout: whole 32-token blocks; the O operand tiles of k_spa_ffn2: whole 128-token tiles
   Workspace w;
   float* p = reinterpret_cast<float*>(ws);
   w.f0 = p; p += T * 64;
@@ -169,7 +169,7 @@ int lft_workspace_bytes(lft_handle* hh, int32_t B, int32_t P, size_t* bytes) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h || !bytes || B < 1 || P < 1) return fail(LFT_ERR_ARG, "bad argument");
   size_t T = (size_t)B * h->cfg.ang_res * h->cfg.ang_res * P * P;
-  T = (T + 31) / 32 * 32;
+  T = (T + 127) / 128 * 128;
   *bytes = T * ws_floats_per_token(h->cfg.scale) * sizeof(float) + 1024;
   return 0;
 }
