@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--impl", default="lft_b200", choices=["lft_b200", "reference"])
     ap.add_argument("--assemble", default="auto", choices=["auto", "direct", "collective"],
                     help="N > 1: peer stores into rank 0's SR buffer (direct) or NCCL gather + integrate (collective)")
-    ap.add_argument("--cpu-patches", type=int, default=3, help="patches in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-patches", type=int, default=32, help="patches in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling leg at N > 1")
     args = ap.parse_args()

@@ -106,10 +106,11 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
                   const float* __restrict__ pev, const __grid_constant__ Tab512 tab, const uint8_t* __restrict__ wq,
                   const uint8_t* __restrict__ wk, const uint8_t* __restrict__ wv, float* __restrict__ tok,
                   float* __restrict__ Q, float* __restrict__ K, float* __restrict__ Vv, int V, int P, int passes,
-                  int ntiles, Region e, Region o) {
+                  int ntiles, Region e, Region o, Region oq) {
   // e: the pixels the position space covers (conv inputs; zero padding outside it), o: the pixels whose tok / Q / K / V are
   // stored.  Full view: e = o = {0, P}.  On the light-field path e is the region the conv inputs are valid on and o = e
   // shrunk by one pixel wherever e's border is not the view border (there the zero padding is not the true neighbour).
+  // oq (inside o): the query pixels - tok and Q are only ever read there (K / V also serve as the neighbours' keys).
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NST = ConvGeom<BIG>::kNST;
   constexpr int kConvRows = ConvGeom<BIG>::kRows, kConvOff = ConvGeom<BIG>::kOff;
@@ -207,9 +208,10 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
         x = e.r0 + xx;
         ok = yy < e.rn && xx < e.rn && (unsigned)(y - o.r0) < (unsigned)o.rn && (unsigned)(x - o.r0) < (unsigned)o.rn;
       }
+      bool okq = ok && (unsigned)(y - oq.r0) < (unsigned)oq.rn && (unsigned)(x - oq.r0) < (unsigned)oq.rn;
       if (!ok) { v = 0; y = 0; x = 0; }
 #ifdef LFT_EXPERIMENT_NOSTORE
-      ok = false;  // timing experiment: no global stores at all
+      ok = okq = false;  // timing experiment: no global stores at all
 #endif
 #ifdef LFT_EXPERIMENT_SMALLSTORE
       v = v & 7;   // timing experiment (wrong results): every store lands in the first 8 views' planes (L2-resident, 5 MB)
@@ -231,7 +233,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
           float t[16];
           tmem_ld16(trow + 64 * q + 16 * c, t);
 #if !defined(LFT_X_NOTOK) && !defined(LFT_X_ZTOK)
-          if (ok) {
+          if (okq) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               st_stream_v4(tok + t32_off(token, 16 * q + 4 * c + i, 32),
@@ -291,7 +293,7 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
             d[4 * j + 2] = fmaf(rstd, d[4 * j + 2], fmaf(-mr, uv.z, cv.z));
             d[4 * j + 3] = fmaf(rstd, d[4 * j + 3], fmaf(-mr, uv.w, cv.w));
           }
-          if (ok && !kNoQKV) {
+          if (okq && !kNoQKV) {
             if (kAttnMma) planar_store16_split(Q, v, 4 * q + c, y, x, P, d, passes == 3);
             else planar_store16(Q, v, 4 * q + c, y, x, P, d);
           }
@@ -1484,11 +1486,11 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
     if (P <= ConvGeom<false>::kMaxP) {
       auto kern = k_spa_embed_qkv<false>;
       LFT_LAUNCH(h, kern, pg, kThreads2, smem_embed<false>(), st, in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq, L.s_wk,
-                 L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes(), (int)ntiles, e, kv);
+                 L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes(), (int)ntiles, e, kv, need);
     } else {
       auto kern = k_spa_embed_qkv<true>;
       LFT_LAUNCH(h, kern, pg, kThreads2, smem_embed<true>(), st, in, L.s_wmlp, L.s_pe, L.s_pev[h->mode()], tq, L.s_wq, L.s_wk,
-                 L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes(), (int)ntiles, e, kv);
+                 L.s_wv, w.tok, w.q, w.k, w.v, (int)V, P, h->passes(), (int)ntiles, e, kv, need);
     }
     if ((rc = sc.finish())) return rc;
   }
