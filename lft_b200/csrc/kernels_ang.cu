@@ -388,9 +388,119 @@ LFT_DEVINL void ang_hmma(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, int kvrow, float rstd, float mr,
-                                    const float4* __restrict__ pq4, const float4* tab4, uint8_t* planes, bool fp32_mode) {
+// One work item: NMT m16 tiles (views 16 mt0 .. of (rel head, pixel)) against the pixel's 25 keys.
+template <bool FP32, int NMT>
+LFT_DEVINL void ang_mma_item(uint32_t qo_u, uint32_t ks_u, uint32_t vs_u, uint8_t* qo_half, int rh, int p, int mt0,
+                             const uint32_t* aoff, uint32_t koff, float b3, int g, int c) {
   constexpr int N = 25, PPT = 5;
+  const float ninf = -INFINITY;
+  const uint32_t ioff = (uint32_t)rh * 4096u + (uint32_t)p * 16u;
+  uint32_t a[NMT][4], kh[4], kl[4];
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt) ang_ldsm4(qo_u + ioff + aoff[mt0 + mt], a[mt]);
+  ang_ldsm4(ks_u + ioff + koff, kh);
+  if (FP32) ang_ldsm4(ks_u + ioff + 2048u + koff, kl);
+  float s[NMT][4][4];
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      s[mt][n][0] = s[mt][n][2] = n == 3 ? b3 : 0.f;
+      s[mt][n][1] = s[mt][n][3] = n == 3 ? ninf : 0.f;
+    }
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) {
+      ang_hmma(s[mt][n], a[mt], kh[n], kh[n]);
+      if (FP32) ang_hmma(s[mt][n], a[mt], kl[n], 0u);
+    }
+  // soft-max over the 25 keys of each row this thread holds a slice of (rows g, g + 8 of every m tile): all row maxima first,
+  // then all exponentials, then all sums - the shuffles of the 2 NMT rows overlap
+  float mx[NMT][2], l[NMT][2];
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float m = fmaxf(fmaxf(s[mt][0][2 * hf], s[mt][0][2 * hf + 1]), fmaxf(s[mt][1][2 * hf], s[mt][1][2 * hf + 1]));
+      mx[mt][hf] = fmaxf(m, fmaxf(fmaxf(s[mt][2][2 * hf], s[mt][2][2 * hf + 1]), s[mt][3][2 * hf]));
+    }
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) mx[mt][hf] = fmaxf(mx[mt][hf], __shfl_xor_sync(0xffffffffu, mx[mt][hf], 1));
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) mx[mt][hf] = fmaxf(mx[mt][hf], __shfl_xor_sync(0xffffffffu, mx[mt][hf], 2));
+  uint32_t ph[NMT][2][4], pl_[NMT][2][4];   // [m tile][k16 step] A operands
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float ls = 0.f;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const float p0 = fast_exp2(s[mt][n][2 * hf] - mx[mt][hf]);
+        const float p1 = n == 3 ? 0.f : fast_exp2(s[mt][n][2 * hf + 1] - mx[mt][hf]);
+        ls += p0 + p1;
+        uint32_t hi, lo;
+        if (FP32) {
+          const uint32_t u0 = __float_as_uint(p0), u1 = __float_as_uint(p1);
+          hi = __byte_perm(u0, u1, 0x7632);
+          lo = pack_bf16(p0 - __uint_as_float(u0 & 0xffff0000u), p1 - __uint_as_float(u1 & 0xffff0000u));
+        } else {
+          hi = pack_bf16(p0, p1);
+          lo = 0u;
+        }
+        ph[mt][n >> 1][2 * (n & 1) + hf] = hi;
+        pl_[mt][n >> 1][2 * (n & 1) + hf] = lo;
+      }
+      l[mt][hf] = ls;
+    }
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) l[mt][hf] += __shfl_xor_sync(0xffffffffu, l[mt][hf], 1);
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) l[mt][hf] += __shfl_xor_sync(0xffffffffu, l[mt][hf], 2);
+  // O = P V
+  uint32_t vh[4], vl[4];
+  ang_ldsm4t(vs_u + ioff + koff, vh);
+  if (FP32) ang_ldsm4t(vs_u + ioff + 2048u + koff, vl);
+  float o[NMT][4];
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) {
+      ang_hmma(o[mt], ph[mt][t], vh[2 * t], vh[2 * t + 1]);
+      if (FP32) {
+        ang_hmma(o[mt], pl_[mt][t], vh[2 * t], vh[2 * t + 1]);
+        ang_hmma(o[mt], ph[mt][t], vl[2 * t], vl[2 * t + 1]);
+      }
+    }
+  // write O (fp32) over the item's own Q rows: dims 2c, 2c + 1 -> slot c / 2, bytes 8 (c & 1)
+  uint8_t* obase = qo_half + rh * 4096 + (c >> 1) * 2048 + p * 16 + (c & 1) * 8;
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int view = 16 * (mt0 + mt) + 8 * hf + g;
+      const float inv = fast_rcp(l[mt][hf]);   // l in [1, 25]
+      if (view < N)
+        *reinterpret_cast<float2*>(obase + view * (PPT * 16)) = make_float2(o[mt][2 * hf] * inv, o[mt][2 * hf + 1] * inv);
+    }
+}
+
+template <bool FP32>
+LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, int kvrow, float rstd, float mr,
+                                    const float4* __restrict__ pq4, const float4* tab4, uint8_t* planes) {
+  constexpr int N = 25, PPT = 5;
+  constexpr bool fp32_mode = FP32;
   uint8_t* qo_ptr = planes;           // R1: Q / O of head half 0 (16 KB) | of head half 1 (16 KB)
   uint8_t* ks_ptr = planes + 32768;   // R2: K 16 KB | V 16 KB
   uint8_t* vs_ptr = ks_ptr + 16384;
@@ -402,7 +512,23 @@ LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, in
     uint4 hi, lo;
     split8(x, hi, lo, fp32_mode);
     *reinterpret_cast<uint4*>(plane + (rh * 2) * 2048 + kvrow * 16) = hi;
-    *reinterpret_cast<uint4*>(plane + (rh * 2 + 1) * 2048 + kvrow * 16) = lo;
+    *reinterpret_cast<uint4*>(plane + (rh * 2 + 1) * 2048 + kvrow * 16) = lo;   // (bf16 mode: zeros - the Q_lo half of A is always read)
+  };
+  // corrected Q (pre-scaled) / K of accumulator columns col .. col + 15 (two heads) -> planes
+  auto put_qk = [&](uint8_t* plane, int col, int rh0, float sc) {
+    float kv[16];
+    tmem_ld16(trow + col, kv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
+      const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
+      kv[4 * j] = sc * fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
+      kv[4 * j + 1] = sc * fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
+      kv[4 * j + 2] = sc * fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
+      kv[4 * j + 3] = sc * fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+    }
+    put(plane, rh0, kv);
+    put(plane, rh0 + 1, kv + 8);
   };
   // results of head half hg: shared memory (fp32) -> bf16 hi/lo TS-form operand; the two threads of a row take two heads each
   auto convert = [&](int hg) {
@@ -425,52 +551,25 @@ LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, in
   for (int mt = 0; mt < 2; ++mt)   // A = [Q_hi rows 0-7, Q_hi rows 8-15, Q_lo rows 0-7, Q_lo rows 8-15] of m16 tile mt
     aoff[mt] = (uint32_t)(mat >> 1) * 2048u + (uint32_t)min(16 * mt + 8 * (mat & 1) + mrow, N - 1) * (PPT * 16);
   koff = (uint32_t)min(8 * mat + mrow, N - 1) * (PPT * 16);   // K / V: matrix = keys 8 mat .. 8 mat + 7 (slot 0: hi; + 2048: lo)
-  const float ninf = -INFINITY;
-  const float b3 = c == 0 ? 0.f : ninf;   // n8 tile 3 = keys 24 + 2c + e: only key 24 exists
+  const float b3 = c == 0 ? 0.f : -INFINITY;   // n8 tile 3 = keys 24 + 2c + e: only key 24 exists
 #pragma unroll 1
   for (int hg = 0; hg < 2; ++hg) {
-    float kv[16];
     LFT_TL(12 + 4 * hg);
-    if (q == 0) {  // K of heads 4hg..4hg+3 (accumulator columns 64 + 32hg ..), corrected
+    // exports of heads 4hg .. 4hg + 3, three 16-column chunks per thread: thread 0 of a row K (corrected) and the first half of
+    // Q, thread 1 V (raw) and the second half of Q (corrected, pre-scaled)
+    if (q == 0) {
+      put_qk(ks_ptr, 64 + 32 * hg, 0, 1.f);
+      put_qk(ks_ptr, 64 + 32 * hg + 16, 2, 1.f);
+      put_qk(qo_ptr + hg * 16384, 32 * hg, 0, scale);
+    } else {
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        const int col = 64 + 32 * hg + 16 * cc;
-        tmem_ld16(trow + col, kv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
-          const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
-          kv[4 * j] = fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
-          kv[4 * j + 1] = fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
-          kv[4 * j + 2] = fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
-          kv[4 * j + 3] = fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
-        }
-        put(ks_ptr, 2 * cc, kv);
-        put(ks_ptr, 2 * cc + 1, kv + 8);
-      }
-    } else {       // V (raw) and Q (corrected, pre-scaled) of the same heads
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+        float kv[16];
         tmem_ld16(trow + 128 + 32 * hg + 16 * cc, kv);
         put(vs_ptr, 2 * cc, kv);
         put(vs_ptr, 2 * cc + 1, kv + 8);
       }
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col = 32 * hg + 16 * cc;
-        tmem_ld16(trow + col, kv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
-          const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
-          kv[4 * j] = scale * fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
-          kv[4 * j + 1] = scale * fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
-          kv[4 * j + 2] = scale * fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
-          kv[4 * j + 3] = scale * fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
-        }
-        put(qo_ptr + hg * 16384, 2 * cc, kv);
-        put(qo_ptr + hg * 16384, 2 * cc + 1, kv + 8);
-      }
+      put_qk(qo_ptr + hg * 16384, 32 * hg + 16, 2, scale);
     }
     LFT_TL(13 + 4 * hg);
     tc_fence_before();
@@ -478,94 +577,16 @@ LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, in
     tc_fence_after();
     LFT_TL(14 + 4 * hg);
     if (hg == 1) convert(0);
-    const uint32_t qo_u = smem_u32(qo_ptr + hg * 16384), ks_u = smem_u32(ks_ptr), vs_u = smem_u32(vs_ptr);
+    uint8_t* qo_half = qo_ptr + hg * 16384;
+    const uint32_t qo_u = smem_u32(qo_half), ks_u = smem_u32(ks_ptr), vs_u = smem_u32(vs_ptr);
+    // 20 (rel head, pixel) items: two full rounds of whole items over the 8 warps, the last four items as eight half items
+    // (one m16 tile each) - 2.5 item times per warp instead of 3
 #pragma unroll 1
-    for (int it = warp; it < 4 * PPT; it += 8) {  // item = (rel head, pixel)
-      const int rh = it / PPT, p = it - rh * PPT;
-      const uint32_t ioff = (uint32_t)rh * 4096u + (uint32_t)p * 16u;
-      uint32_t a0[4], a1[4], kh[4], kl[4];
-      ang_ldsm4(qo_u + ioff + aoff[0], a0);
-      ang_ldsm4(qo_u + ioff + aoff[1], a1);
-      ang_ldsm4(ks_u + ioff + koff, kh);
-      if (fp32_mode) ang_ldsm4(ks_u + ioff + 2048u + koff, kl);
-      float s[2][4][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          s[mt][n][0] = s[mt][n][2] = n == 3 ? b3 : 0.f;
-          s[mt][n][1] = s[mt][n][3] = n == 3 ? ninf : 0.f;
-        }
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        ang_hmma(s[0][n], a0, kh[n], kh[n]);
-        ang_hmma(s[1][n], a1, kh[n], kh[n]);
-        if (fp32_mode) {
-          ang_hmma(s[0][n], a0, kl[n], 0u);
-          ang_hmma(s[1][n], a1, kl[n], 0u);
-        }
-      }
-      // soft-max over the 25 keys of each of the four rows this thread holds a slice of (rows g, g+8 of both m tiles)
-      uint32_t ph[2][2][4], pl_[2][2][4];   // [m tile][k16 step] A operands
-      float linv[2][2];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {   // row g (hf 0) / g + 8 (hf 1)
-          float mx = fmaxf(fmaxf(s[mt][0][2 * hf], s[mt][0][2 * hf + 1]), fmaxf(s[mt][1][2 * hf], s[mt][1][2 * hf + 1]));
-          mx = fmaxf(mx, fmaxf(fmaxf(s[mt][2][2 * hf], s[mt][2][2 * hf + 1]), s[mt][3][2 * hf]));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-          float l = 0.f;
-#pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            const float p0 = fast_exp2(s[mt][n][2 * hf] - mx);
-            const float p1 = n == 3 ? 0.f : fast_exp2(s[mt][n][2 * hf + 1] - mx);
-            l += p0 + p1;
-            uint32_t hi, lo;
-            if (fp32_mode) {
-              const uint32_t u0 = __float_as_uint(p0), u1 = __float_as_uint(p1);
-              hi = __byte_perm(u0, u1, 0x7632);
-              lo = pack_bf16(p0 - __uint_as_float(u0 & 0xffff0000u), p1 - __uint_as_float(u1 & 0xffff0000u));
-            } else {
-              hi = pack_bf16(p0, p1);
-              lo = 0u;
-            }
-            ph[mt][n >> 1][2 * (n & 1) + hf] = hi;
-            pl_[mt][n >> 1][2 * (n & 1) + hf] = lo;
-          }
-          l += __shfl_xor_sync(0xffffffffu, l, 1);
-          l += __shfl_xor_sync(0xffffffffu, l, 2);
-          linv[mt][hf] = fast_rcp(l);   // l in [1, 25]
-        }
-      // O = P V
-      uint32_t vh[4], vl[4];
-      ang_ldsm4t(vs_u + ioff + koff, vh);
-      if (fp32_mode) ang_ldsm4t(vs_u + ioff + 2048u + koff, vl);
-      float o[2][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          ang_hmma(o[mt], ph[mt][t], vh[2 * t], vh[2 * t + 1]);
-          if (fp32_mode) {
-            ang_hmma(o[mt], pl_[mt][t], vh[2 * t], vh[2 * t + 1]);
-            ang_hmma(o[mt], ph[mt][t], vl[2 * t], vl[2 * t + 1]);
-          }
-        }
-      }
-      // write O (fp32) over the item's own Q rows: dims 2c, 2c + 1 -> slot c / 2, bytes 8 (c & 1)
-      uint8_t* obase = qo_ptr + hg * 16384 + rh * 4096 + (c >> 1) * 2048 + p * 16 + (c & 1) * 8;
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int view = 16 * mt + 8 * hf + g;
-          if (view < N)
-            *reinterpret_cast<float2*>(obase + view * (PPT * 16)) =
-                make_float2(o[mt][2 * hf] * linv[mt][hf], o[mt][2 * hf + 1] * linv[mt][hf]);
-        }
+    for (int it = warp; it < 16; it += 8)
+      ang_mma_item<FP32, 2>(qo_u, ks_u, vs_u, qo_half, it / PPT, it % PPT, 0, aoff, koff, b3, g, c);
+    {
+      const int it = 16 + (warp >> 1);
+      ang_mma_item<FP32, 1>(qo_u, ks_u, vs_u, qo_half, it / PPT, it % PPT, warp & 1, aoff, koff, b3, g, c);
     }
     LFT_TL(15 + 4 * hg);
     rows_bar_sync256();  // results of half hg complete; K / V planes free for the next half
@@ -758,9 +779,10 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       const float4* tab4 = reinterpret_cast<const float4*>(tab.v);    // [u_qk 128 | c_qk 128 | u_1 128 | c_1 128] (constant bank)
       if constexpr (NV == 25 || NV == 49 || NV == 81) {
 #ifndef LFT_ANG_ITEMS_V1
-        if constexpr (NV == 25)
-          ang_attention_mma25(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes, passes == 3);
-        else
+        if constexpr (NV == 25) {
+          if (passes == 3) ang_attention_mma25<true>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes);
+          else ang_attention_mma25<false>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes);
+        } else
 #endif
         ang_attention_items<NV, kPPT, kCH>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes, passes == 3);
         LFT_TL(4);
