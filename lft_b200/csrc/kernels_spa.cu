@@ -192,6 +192,12 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       mbar_arrive(f_ready);
     };
     pdl_wait();  // `feat` is the previous kernel's output
+#ifdef LFT_X_EMBED_STAGGER   // experiment: CTAs start a fraction of a tile apart, so that their store bursts do not coincide chip-wide
+    {
+      const long long t0 = clock64(), wait = (long long)(blockIdx.x % LFT_X_EMBED_STAGGER_N) * LFT_X_EMBED_STAGGER;
+      while (clock64() - t0 < wait) {}
+    }
+#endif
     if (ntl > 0) stage(0);
     for (int k = 0; k < ntl; ++k) {
       LFT_TL2(0);
