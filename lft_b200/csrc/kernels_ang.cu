@@ -517,15 +517,17 @@ LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, in
   // corrected Q (pre-scaled) / K of accumulator columns col .. col + 15 (two heads) -> planes
   auto put_qk = [&](uint8_t* plane, int col, int rh0, float sc) {
     float kv[16];
+    float4 pv[4];   // PE_a W'^T of this view: issued before the accumulator load (whose wait the compiler cannot move loads across)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pv[j] = __ldg(pq4 + (col / 4 + j) * N);
     tmem_ld16(trow + col, kv);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 pv = __ldg(pq4 + (col / 4 + j) * N);
       const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
-      kv[4 * j] = sc * fmaf(rstd, kv[4 * j] + pv.x, fmaf(-mr, uv.x, cv.x));
-      kv[4 * j + 1] = sc * fmaf(rstd, kv[4 * j + 1] + pv.y, fmaf(-mr, uv.y, cv.y));
-      kv[4 * j + 2] = sc * fmaf(rstd, kv[4 * j + 2] + pv.z, fmaf(-mr, uv.z, cv.z));
-      kv[4 * j + 3] = sc * fmaf(rstd, kv[4 * j + 3] + pv.w, fmaf(-mr, uv.w, cv.w));
+      kv[4 * j] = sc * fmaf(rstd, kv[4 * j] + pv[j].x, fmaf(-mr, uv.x, cv.x));
+      kv[4 * j + 1] = sc * fmaf(rstd, kv[4 * j + 1] + pv[j].y, fmaf(-mr, uv.y, cv.y));
+      kv[4 * j + 2] = sc * fmaf(rstd, kv[4 * j + 2] + pv[j].z, fmaf(-mr, uv.z, cv.z));
+      kv[4 * j + 3] = sc * fmaf(rstd, kv[4 * j + 3] + pv[j].w, fmaf(-mr, uv.w, cv.w));
     }
     put(plane, rh0, kv);
     put(plane, rh0 + 1, kv + 8);
@@ -581,6 +583,7 @@ LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, in
     const uint32_t qo_u = smem_u32(qo_half), ks_u = smem_u32(ks_ptr), vs_u = smem_u32(vs_ptr);
     // 20 (rel head, pixel) items: two full rounds of whole items over the 8 warps, the last four items as eight half items
     // (one m16 tile each) - 2.5 item times per warp instead of 3
+#ifndef LFT_X_ANG_NOITEMS   // (defined: timing experiment, wrong results)
 #pragma unroll 1
     for (int it = warp; it < 16; it += 8)
       ang_mma_item<FP32, 2>(qo_u, ks_u, vs_u, qo_half, it / PPT, it % PPT, 0, aoff, koff, b3, g, c);
@@ -588,6 +591,7 @@ LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, in
       const int it = 16 + (warp >> 1);
       ang_mma_item<FP32, 1>(qo_u, ks_u, vs_u, qo_half, it / PPT, it % PPT, warp & 1, aoff, koff, b3, g, c);
     }
+#endif
     LFT_TL(15 + 4 * hg);
     rows_bar_sync256();  // results of half hg complete; K / V planes free for the next half
   }
@@ -744,8 +748,12 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       float x[32];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
+#ifdef LFT_X_ANG_NOLOAD
+        const float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
         const float4 f = rowok ? __ldg(reinterpret_cast<const float4*>(in + t32_off(tok, 8 * q + i, 16)))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
         x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
       }
       tmem_st16(trow + 192 + 32 * q, x);
@@ -780,8 +788,10 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
       if constexpr (NV == 25 || NV == 49 || NV == 81) {
 #ifndef LFT_ANG_ITEMS_V1
         if constexpr (NV == 25) {
+#ifndef LFT_X_ANG_NOATTN2   // (defined: timing experiment - no exports, no items, no convert)
           if (passes == 3) ang_attention_mma25<true>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes);
           else ang_attention_mma25<false>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes);
+#endif
         } else
 #endif
         ang_attention_items<NV, kPPT, kCH>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes, passes == 3);

@@ -1262,6 +1262,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
     };
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     pdl_wait();  // O / tok are the previous kernels' output
+    LFT_TL(0);
 
     // phase 0: T <- O (planar gather of own heads 4q..4q+3)
     if (!otile) {
@@ -1305,6 +1306,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(a_ready);
+    LFT_TL(2);
     const float mr = mean * rstd;
     const float4* u1 = reinterpret_cast<const float4*>(tab.v);        // [u_1 256 | c_1 256] (constant bank)
     const float4* c1 = reinterpret_cast<const float4*>(tab.v + 256);
@@ -1356,11 +1358,15 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
       for (int c = 0; c < 4; ++c) a_tmem_store16(trow + 128, trow + 192, 64 * q + 16 * c, hv + 16 * c, fp32m);
     };
     await();                 // FFN1a
+    LFT_TL(3);
     hidden(0, 0, false);     // T held the O operand, consumed by the out-projection (complete: FFN1a was issued after it)
     publish_tmem();
+    LFT_TL(4);
     await();                 // FFN2a (D) and FFN1b (T)
+    LFT_TL(5);
     hidden(128, 32, true);
     publish_tmem();
+    LFT_TL(6);
 
     // phase 4: Y2 = Y1 + D -> T.  Y1 from its hi/lo operand in shared memory (fp32 mode) or from the spilled row (bf16 mode).
     {
@@ -1386,6 +1392,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
         }
       }
       await();               // FFN2b
+      LFT_TL(7);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float d[16];
@@ -1396,6 +1403,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
       }
     }
     publish_tmem();
+    LFT_TL(8);
 
     // phase 5: out = D[0,64) (+ global residual), own 32 columns
     float4 r4[8];
@@ -1405,6 +1413,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
         r4[i] = ok ? __ldg(reinterpret_cast<const float4*>(final_res + t32_off(tt, 8 * q + i, 16))) : zero4;
     }
     await();
+    LFT_TL(9);
     {
       float d[32];
       tmem_ld16_nowait(trow + 32 * q, d);
@@ -1419,6 +1428,7 @@ k_spa_ffn2(const float* __restrict__ O, float* __restrict__ tok, const __grid_co
         }
       }
     }
+    LFT_TL(10);
     tc_fence_before();
   }
   cta_teardown(ctl, warp, 256, kWarpMma2);

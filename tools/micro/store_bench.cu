@@ -26,6 +26,23 @@ __global__ void __launch_bounds__(256, 2) k(uint8_t* out, size_t bytes_per_cta, 
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         asm volatile("st.global.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(base + off + (size_t)j * 8192 + tid * 32), "f"(acc) : "memory");
+    } else if (MODE >= 3) {   // smem staging + many small bulk stores (MODE 3: 128 x 512 B, MODE 4: 32 x 2 KB) issued by the lanes of warp 0
+      const int piece = MODE == 3 ? 512 : 2048, per_lane = 65536 / piece / 32;
+      if (off) {
+        if (tid < 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) *reinterpret_cast<float4*>(sm + j * 4096 + tid * 16) = make_float4(acc, acc, acc, acc);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid < 32) {
+        for (int j = 0; j < per_lane; ++j) {
+          const int o = (j * 32 + tid) * piece;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + off + o), "r"(smem_u32(sm) + o), "r"(piece) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
     } else {                  // smem staging + one bulk store of 64 KB
       if (off) {
         if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -42,6 +59,7 @@ __global__ void __launch_bounds__(256, 2) k(uint8_t* out, size_t bytes_per_cta, 
     }
   }
   if (MODE == 2 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (MODE >= 3 && tid < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (acc == 12345.678f) out[0] = 1;
 }
 
@@ -54,9 +72,9 @@ void run(const char* name, int work) {
   cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
-  k<MODE><<<grid, 256, MODE == 2 ? 65536 : 0>>>(out, per, work);
+  k<MODE><<<grid, 256, MODE >= 2 ? 65536 : 0>>>(out, per, work);
   cudaEventRecord(a);
-  k<MODE><<<grid, 256, MODE == 2 ? 65536 : 0>>>(out, per, work);
+  k<MODE><<<grid, 256, MODE >= 2 ? 65536 : 0>>>(out, per, work);
   cudaEventRecord(b);
   cudaError_t e = cudaDeviceSynchronize();
   float ms;
@@ -70,6 +88,8 @@ int main() {
     run<0>("st.global.v4 (no_allocate)", work);
     run<1>("st.global.v8", work);
     run<2>("smem + cp.async.bulk store", work);
+    run<3>("smem + 128 x 512 B bulk", work);
+    run<4>("smem + 32 x 2 KB bulk", work);
   }
   return 0;
 }
