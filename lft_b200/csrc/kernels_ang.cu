@@ -599,6 +599,190 @@ LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, in
   convert(1);
 }
 
+// The same formulation for the larger odd angular resolutions that use the item attention (NV = 49: A = 7, two pixels per tile;
+// NV = 81: A = 9, one pixel per tile): an item is ONE m16 tile of queries of a (rel head, pixel) against all NV keys -
+// NT = ceil(NV / 8) n8 tiles (padded to an even count for the k16 steps of P V; padding keys are masked), all scores of the two
+// rows a thread holds stay in registers (<= 48), one soft-max pass.
+template <bool FP32, int NV, int PPT>
+LFT_DEVINL void ang_attention_mma_g(uint32_t trow, int warp, int lane, int q, int kvrow, float rstd, float mr,
+                                    const float4* __restrict__ pq4, const float4* tab4, uint8_t* planes) {
+  constexpr int N = NV;
+  constexpr int NT = (NV + 7) / 8, NTP = (NT + 1) & ~1, KS = NTP / 2, MT = (NV + 15) / 16;
+  constexpr int NITEMS = 4 * PPT * MT;   // per head half
+  uint8_t* qo_ptr = planes;           // R1: Q / O of head half 0 (16 KB) | of head half 1 (16 KB)
+  uint8_t* ks_ptr = planes + 32768;   // R2: K 16 KB | V 16 KB
+  uint8_t* vs_ptr = ks_ptr + 16384;
+  const float scale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e)/sqrt(8), folded into Q (softmax via exp2)
+  const int g = lane >> 2, c = lane & 3;
+  const int mat = lane >> 3, mrow = lane & 7;
+  const int srow = kvrow >= 0 ? kvrow : 0;     // idle rows stage nothing and convert row 0's values (their output is discarded)
+  const float ninf = -INFINITY;
+  auto put = [&](uint8_t* plane, int rh, const float* x) {
+    uint4 hi, lo;
+    split8(x, hi, lo, FP32);
+    if (kvrow >= 0) {
+      *reinterpret_cast<uint4*>(plane + (rh * 2) * 2048 + kvrow * 16) = hi;
+      *reinterpret_cast<uint4*>(plane + (rh * 2 + 1) * 2048 + kvrow * 16) = lo;
+    }
+  };
+  auto put_qk = [&](uint8_t* plane, int col, int rh0, float sc) {
+    float kv[16];
+    float4 pv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pv[j] = __ldg(pq4 + (col / 4 + j) * N);
+    tmem_ld16(trow + col, kv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
+      kv[4 * j] = sc * fmaf(rstd, kv[4 * j] + pv[j].x, fmaf(-mr, uv.x, cv.x));
+      kv[4 * j + 1] = sc * fmaf(rstd, kv[4 * j + 1] + pv[j].y, fmaf(-mr, uv.y, cv.y));
+      kv[4 * j + 2] = sc * fmaf(rstd, kv[4 * j + 2] + pv[j].z, fmaf(-mr, uv.z, cv.z));
+      kv[4 * j + 3] = sc * fmaf(rstd, kv[4 * j + 3] + pv[j].w, fmaf(-mr, uv.w, cv.w));
+    }
+    put(plane, rh0, kv);
+    put(plane, rh0 + 1, kv + 8);
+  };
+  auto convert = [&](int hg) {
+    const uint8_t* src = qo_ptr + hg * 16384 + srow * 16;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int rh = 2 * q + hh;
+      float o[8];
+      *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(src + (rh * 2) * 2048);
+      *reinterpret_cast<float4*>(o + 4) = *reinterpret_cast<const float4*>(src + (rh * 2 + 1) * 2048);
+      uint4 hi, lo;
+      split8(o, hi, lo, FP32);
+      tmem_st4u(trow + 64 + 16 * hg + 4 * rh, hi);
+      if (FP32) tmem_st4u(trow + 96 + 16 * hg + 4 * rh, lo);
+    }
+  };
+#pragma unroll 1
+  for (int hg = 0; hg < 2; ++hg) {
+    if (q == 0) {
+      put_qk(ks_ptr, 64 + 32 * hg, 0, 1.f);
+      put_qk(ks_ptr, 64 + 32 * hg + 16, 2, 1.f);
+      put_qk(qo_ptr + hg * 16384, 32 * hg, 0, scale);
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        float kv[16];
+        tmem_ld16(trow + 128 + 32 * hg + 16 * cc, kv);
+        put(vs_ptr, 2 * cc, kv);
+        put(vs_ptr, 2 * cc + 1, kv + 8);
+      }
+      put_qk(qo_ptr + hg * 16384, 32 * hg + 16, 2, scale);
+    }
+    tc_fence_before();
+    rows_bar_sync256();
+    tc_fence_after();
+    if (hg == 1) convert(0);
+    uint8_t* qo_half = qo_ptr + hg * 16384;
+    const uint32_t qo_u = smem_u32(qo_half), ks_u = smem_u32(ks_ptr), vs_u = smem_u32(vs_ptr);
+#pragma unroll 1
+    for (int it = warp; it < NITEMS; it += 8) {   // item = (rel head, pixel, m16 tile)
+      const int rh = it / (PPT * MT), rem = it - rh * (PPT * MT);
+      const int p = rem / MT, mt = rem - p * MT;
+      const uint32_t ioff = (uint32_t)rh * 4096u + (uint32_t)p * 16u;
+      uint32_t a[4];
+      ang_ldsm4(qo_u + ioff + (uint32_t)(mat >> 1) * 2048u + (uint32_t)min(16 * mt + 8 * (mat & 1) + mrow, N - 1) * (PPT * 16), a);
+      float s[NTP][4];
+#pragma unroll
+      for (int n = 0; n < NTP; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool dead = 8 * n + 6 + e >= N;      // can the column 8n + 2c + e fall beyond the last key for some c?
+          const float b = !dead ? 0.f : (8 * n + 2 * c + e < N ? 0.f : ninf);
+          s[n][e] = s[n][2 + e] = b;
+        }
+#pragma unroll
+      for (int grp = 0; grp < (NT + 3) / 4; ++grp) {   // K fragments of n8 tiles 4 grp .. 4 grp + 3
+        uint32_t kh[4], kl[4];
+        const uint32_t ko = (uint32_t)min(32 * grp + 8 * mat + mrow, N - 1) * (PPT * 16);
+        ang_ldsm4(ks_u + ioff + ko, kh);
+        if (FP32) ang_ldsm4(ks_u + ioff + 2048u + ko, kl);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = 4 * grp + j;
+          if (n < NT) {
+            ang_hmma(s[n], a, kh[j], kh[j]);
+            if (FP32) ang_hmma(s[n], a, kl[j], 0u);
+          }
+        }
+      }
+      uint32_t ph[KS][4], pl_[KS][4];
+      float linv[2];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float m0 = s[0][2 * hf], m1 = s[0][2 * hf + 1];
+#pragma unroll
+        for (int n = 1; n < NT; ++n) {
+          m0 = fmaxf(m0, s[n][2 * hf]);
+          m1 = fmaxf(m1, s[n][2 * hf + 1]);
+        }
+        float mx = fmaxf(m0, m1);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int n = 0; n < NTP; ++n) {
+          float p0 = 0.f, p1 = 0.f;
+          if (n < NT) {
+            p0 = fast_exp2(s[n][2 * hf] - mx);
+            p1 = fast_exp2(s[n][2 * hf + 1] - mx);
+          }
+          l0 += p0;
+          l1 += p1;
+          uint32_t hi, lo;
+          if (FP32) {
+            const uint32_t u0 = __float_as_uint(p0), u1 = __float_as_uint(p1);
+            hi = __byte_perm(u0, u1, 0x7632);
+            lo = pack_bf16(p0 - __uint_as_float(u0 & 0xffff0000u), p1 - __uint_as_float(u1 & 0xffff0000u));
+          } else {
+            hi = pack_bf16(p0, p1);
+            lo = 0u;
+          }
+          ph[n >> 1][2 * (n & 1) + hf] = hi;
+          pl_[n >> 1][2 * (n & 1) + hf] = lo;
+        }
+        float l = l0 + l1;
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        linv[hf] = fast_rcp(l);
+      }
+      float o[4] = {0.f, 0.f, 0.f, 0.f}, o2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int grp = 0; grp < (KS + 1) / 2; ++grp) {   // V fragments of keys 32 grp .. 32 grp + 31 = k16 steps 2 grp, 2 grp + 1
+        uint32_t vh[4], vl[4];
+        const uint32_t ko = (uint32_t)min(32 * grp + 8 * mat + mrow, N - 1) * (PPT * 16);
+        ang_ldsm4t(vs_u + ioff + ko, vh);
+        if (FP32) ang_ldsm4t(vs_u + ioff + 2048u + ko, vl);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int t = 2 * grp + j;
+          if (t < KS) {
+            float* oo = j ? o2 : o;
+            ang_hmma(oo, ph[t], vh[2 * j], vh[2 * j + 1]);
+            if (FP32) {
+              ang_hmma(oo, pl_[t], vh[2 * j], vh[2 * j + 1]);
+              ang_hmma(oo, ph[t], vl[2 * j], vl[2 * j + 1]);
+            }
+          }
+        }
+      }
+      uint8_t* obase = qo_half + rh * 4096 + (c >> 1) * 2048 + p * 16 + (c & 1) * 8;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int view = 16 * mt + 8 * hf + g;
+        if (view < N)
+          *reinterpret_cast<float2*>(obase + view * (PPT * 16)) =
+              make_float2((o[2 * hf] + o2[2 * hf]) * linv[hf], (o[2 * hf + 1] + o2[2 * hf + 1]) * linv[hf]);
+      }
+    }
+    rows_bar_sync256();
+  }
+  convert(1);
+}
+
 // NV > 0: compile-time number of views (scores kept in registers, single QK pass); NV == 0: runtime N.
 template <int NV>
 __global__ void __launch_bounds__(kThreads2, 2)
@@ -792,9 +976,13 @@ k_ang(const float* __restrict__ in, float* __restrict__ out, const uint8_t* __re
           if (passes == 3) ang_attention_mma25<true>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes);
           else ang_attention_mma25<false>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes);
 #endif
-        } else
-#endif
+        } else {
+          if (passes == 3) ang_attention_mma_g<true, NV, kPPT>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes);
+          else ang_attention_mma_g<false, NV, kPPT>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes);
+        }
+#else
         ang_attention_items<NV, kPPT, kCH>(trow, warp, lane, q, kvrow, rstd, mr, pq4, tab4, smem + kCtlBytes, passes == 3);
+#endif
         LFT_TL(4);
         tmem_wait_st();
         tc_fence_before();
