@@ -54,19 +54,24 @@ LFT_DEVINL void planar_store16(float* base, long long v, int head, int y, int x,
 // The window attention runs on warp-level tensor-core MMAs (k_spa_attn_mma), so Q / K / V leave k_spa_embed_qkv as bf16 hi / lo
 // pairs in the SAME planar layout (and the same bytes as fp32): the four 16-byte pieces of a (token, head) are
 //   piece 0: hi of dims 0..7 | piece 1: hi of dims 8..15 | piece 2: lo of dims 0..7 | piece 3: lo of dims 8..15
-// (x = hi + lo to 2^-16, the accuracy class of every three-pass product here).  bf16 mode stores the hi pieces only.
+// (x = hi + lo to 2^-16, the accuracy class of every three-pass product here).  bf16 mode: hi pieces only, two pieces per (y, x).
 LFT_DEVINL void st_stream_v4u(float* p, const uint4& v) {
   st_stream_v4(p, make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)));
+}
+// (bf16 mode keeps no room for the lo pieces: two pieces per (y, x), rows of half the size)
+LFT_DEVINL long long planar_off_np(long long v, int head, int y, int j, int x, int P, int NP) {
+  return ((((v * 8 + head) * P + y) * NP + j) * (long long)P + x) * 4;
 }
 LFT_DEVINL void planar_store16_split(float* base, long long v, int head, int y, int x, int P, const float* d, bool fp32_mode) {
   uint4 h0, l0, h1, l1;
   split8(d, h0, l0, fp32_mode);
   split8(d + 8, h1, l1, fp32_mode);
-  st_stream_v4u(base + planar_off(v, head, y, 0, x, P), h0);
-  st_stream_v4u(base + planar_off(v, head, y, 1, x, P), h1);
+  const int NP = fp32_mode ? 4 : 2;
+  st_stream_v4u(base + planar_off_np(v, head, y, 0, x, P, NP), h0);
+  st_stream_v4u(base + planar_off_np(v, head, y, 1, x, P, NP), h1);
   if (fp32_mode) {
-    st_stream_v4u(base + planar_off(v, head, y, 2, x, P), l0);
-    st_stream_v4u(base + planar_off(v, head, y, 3, x, P), l1);
+    st_stream_v4u(base + planar_off_np(v, head, y, 2, x, P, NP), l0);
+    st_stream_v4u(base + planar_off_np(v, head, y, 3, x, P, NP), l1);
   }
 }
 #ifdef LFT_ATTN_V1   // the CUDA-core window attention of rounds 1-2 (fp32 Q / K / V planes)
@@ -601,14 +606,15 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
   const int q0 = max(rowbase, qr.r0), q1 = min(rowbase + kAttnRB, rend);     // query rows [q0, q1) of this CTA
   const int ys = max(q0 - 2, 0), ye = min(q1 + 2, P);              // staged key rows [ys, ye)
   const int kxlo = max(qr.r0 - 2, 0), kxhi = min(cend + 2, P) - 1; // key columns k_spa_embed_qkv has written
-  const uint32_t rowbytes = (uint32_t)P * 64;                      // one (y) plane: 4 pieces x P x 16 B
+  constexpr int NP = FP32 ? 4 : 2;                                 // 16-byte pieces per (y, x): hi, hi | lo, lo
+  const uint32_t rowbytes = (uint32_t)P * 16 * NP;                 // one (y) plane: NP pieces x P x 16 B
   const uint32_t piecebytes = (uint32_t)P * 16;
   const uint32_t nbytes = (uint32_t)(ye - ys) * rowbytes;
   const uint32_t bufbytes = 2u * (kAttnRB + 4) * rowbytes;
   const uint32_t bar0 = smem_u32(smem);
   const uint32_t buf0 = smem_u32(smem) + 32;
   unsigned* cnt = reinterpret_cast<unsigned*>(smem + 16);      // warps that have finished with buffer 0 / 1 (monotonic)
-  const long long PP16 = (long long)P * P * 16;                    // floats per (view, head) plane
+  const long long PP16 = (long long)P * P * 4 * NP;                // floats per (view, head) plane
   const int nk = (int)blockIdx.x < nitems ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const unsigned vh0 = blockIdx.x / (unsigned)nblk, dvh = gridDim.x / (unsigned)nblk;   // gridDim.x % nblk == 0 (host)
   auto plane_of = [&](int k) { return (long long)(vh0 + (unsigned)k * dvh) * PP16; };
@@ -670,7 +676,7 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
     dxok[e] = dx >= -2 && dx <= 2;
   }
   const int qyA = min(max(by + iA, qr.r0), rend - 1), qyB = min(max(by + 2 + iA, qr.r0), rend - 1);
-  const uint32_t qoffA = (uint32_t)qyA * 16u * P + c, qoffB = (uint32_t)qyB * 16u * P + c;   // 32-bit words inside the plane
+  const uint32_t qoffA = (uint32_t)qyA * (4u * NP) * P + c, qoffB = (uint32_t)qyB * (4u * NP) * P + c;   // 32-bit words inside the plane
   const int ps = P * 4;                       // words between the pieces of one (y, x)
   const bool odd = c & 1;
   const int qyo = by + iA + (odd ? 2 : 0);    // the row this lane stores (even lanes: row A's piece, odd lanes: row B's)
@@ -710,7 +716,7 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
     const int head = (int)(vhk & 7u);
     const uint32_t* Qw = Qall + plane;
     const uint32_t* Qn = Qall + plane_of(k + 1);
-    float* Ob = O + plane;
+    float* Ob = O + (long long)vhk * ((long long)P * P * 16);   // (fp32 planar O: four pieces per (y, x) in both modes)
     mbar_wait(bar0 + 8u * (k & 1), (uint32_t)(k >> 1) & 1u);   // item k's rows have landed
     if (has_work) {
 #pragma unroll 1
