@@ -591,10 +591,11 @@ constexpr size_t smem_attn_mma(int P) { return 32 + 2 * 2 * (size_t)(kAttnRB + 4
 // two staging buffers - the bulk copies of item k + 1 run under the MMAs of item k (the one-item-per-CTA form spent half of a
 // CTA's life waiting for its 49 KB).  The host makes gridDim.x a multiple of the row blocks per view, so a CTA keeps its row
 // block: key-row offsets and row masks are loop invariants.
-template <bool FP32>
+template <bool FP32, bool OTILE>
 __global__ void __launch_bounds__(kAttnMmaThreads, 2)
 k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ Vv,
-               float* __restrict__ O, int P, Region qr, int nitems, int otile) {
+               float* __restrict__ O, int P, Region qr, int nitems) {
+  constexpr bool otile = OTILE;
   // otile != 0: O leaves as the bf16 hi / lo A operand of k_spa_ffn2's output projection, tile by tile in the operand's own
   // shared-memory layout [tile of 128 compacted tokens][hi | lo][k chunk 16][row 128][8 bf16] (64 KB per tile, channel =
   // head * 16 + dim), which k_spa_ffn2 fetches with two bulk copies; otile == 0: fp32 planar (the layout of Q / K / V).
@@ -685,7 +686,9 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
   // tile-format output: compacted token of (view, y, x) = (view * rn + y - r0) * rn + x - r0
   const int tyA = by + iA - qr.r0, tyB = tyA + 2;
   const bool okA = tyA >= 0 && tyA < qr.rn, okB = tyB >= 0 && tyB < qr.rn;
-  uint32_t* Ot = reinterpret_cast<uint32_t*>(O);
+  const unsigned tyrn[2] = {(unsigned)(tyA * qr.rn), (unsigned)(tyB * qr.rn)};
+  const unsigned rn2 = (unsigned)(qr.rn * qr.rn);
+  uint32_t* Ot = reinterpret_cast<uint32_t*>(O) + c;
 
   // Q fragments of block column cb of the item whose plane starts at Qw; queries outside the region shadow the nearest valid
   // one (their results are not stored).  Row B and the pieces are fixed 64-bit strides from row A's first piece.
@@ -712,8 +715,9 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
   for (int k = 0; k < nk; ++k) {
     const uint32_t ks = buf0 + (uint32_t)(k & 1) * bufbytes, vs = ks + (kAttnRB + 4) * rowbytes;
     const long long plane = plane_of(k);
-    const unsigned vhk = vh0 + (unsigned)k * dvh, vq = vhk >> 3;
-    const int head = (int)(vhk & 7u);
+    const unsigned vhk = vh0 + (unsigned)k * dvh;
+    const unsigned tvq = (vhk >> 3) * rn2;                          // first compacted token of the item's view
+    uint32_t* Oh = Ot + (vhk & 7u) * 1024u;                         // + head * 2 k chunks * 512 words
     const uint32_t* Qw = Qall + plane;
     const uint32_t* Qn = Qall + plane_of(k + 1);
     float* Ob = O + (long long)vhk * ((long long)P * P * 16);   // (fp32 planar O: four pieces per (y, x) in both modes)
@@ -832,22 +836,30 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
         const float iA_ = fast_rcp(lA), iB_ = fast_rcp(lB);   // l in [1, 25]: rcp.approx is within 1 ulp
         const int qx = bx + (g & 3);
         if (otile) {
-          const int tx = qx - qr.r0;
-          if (tx >= 0 && tx < qr.rn) {
-            const unsigned tv = vq * (unsigned)(qr.rn * qr.rn) + (unsigned)tx;
+          const unsigned tx = (unsigned)(qx - qr.r0);
+          if (tx < (unsigned)qr.rn) {
+            const unsigned tv = tvq + tx;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               if (hf ? okB : okA) {
-                const unsigned t = tv + (unsigned)((hf ? tyB : tyA) * qr.rn);
+                const unsigned t = tv + tyrn[hf];
                 // 32-bit words: tile * 16384 + plane * 8192 + k chunk * 512 + row * 4 + c
-                uint32_t* dst = Ot + (size_t)(t >> 7) * 16384u + (uint32_t)(head * 2) * 512u + (t & 127u) * 4u + c;
-                const float inv = hf ? iB_ : iA_;
+                uint32_t* dst = Oh + (((t >> 7) << 14) | ((t & 127u) << 2));
+                const f32x2 inv2 = hf ? pack2(iB_, iB_) : pack2(iA_, iA_);
 #pragma unroll
                 for (int d = 0; d < 2; ++d) {
-                  uint32_t hi, lo;
-                  split_pair(o[d][2 * hf] * inv, o[d][2 * hf + 1] * inv, fp32m, hi, lo);
-                  dst[d * 512] = hi;
-                  if (fp32m) dst[8192 + d * 512] = lo;
+                  const f32x2 v2 = mul2(pack2(o[d][2 * hf], o[d][2 * hf + 1]), inv2);
+                  float x0, x1;
+                  unpack2(v2, x0, x1);
+                  if (fp32m) {
+                    const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
+                    float r0_, r1_;
+                    unpack2(fma2(pack2(__uint_as_float(u0 & 0xffff0000u), __uint_as_float(u1 & 0xffff0000u)), neg1, v2), r0_, r1_);
+                    dst[d * 512] = __byte_perm(u0, u1, 0x7632);
+                    dst[8192 + d * 512] = pack_bf16(r0_, r1_);
+                  } else {
+                    dst[d * 512] = pack_bf16(x0, x1);
+                  }
                 }
               }
             }
@@ -1476,8 +1488,8 @@ int configure_spa() {
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
-  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn_mma(64)));
-  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn_mma(64)));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<true, kOTile != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn_mma(64)));
+  CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<false, kOTile != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn_mma(64)));
   return 0;
 }
 
@@ -1525,15 +1537,12 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
       if (items >= (1ll << 31)) return fail(LFT_ERR_ARG, "k_spa_attn_mma: too many work items");
       const long long maxg = 2ll * h->num_sms;   // persistent: two CTAs per SM; a multiple of nb so that a CTA keeps its row block
       const unsigned pg = (unsigned)(items <= maxg ? items : (maxg / nb) * nb);
-      if (h->passes() == 3) {
-        auto kern = k_spa_attn_mma<true>;
+      auto launch = [&](auto kern) {
         LFT_LAUNCH(h, kern, pg, kAttnMmaThreads, smem_attn_mma(P), st, (const float*)w.q, (const float*)w.k, (const float*)w.v,
-                   w.o, P, need, (int)items, kOTile);
-      } else {
-        auto kern = k_spa_attn_mma<false>;
-        LFT_LAUNCH(h, kern, pg, kAttnMmaThreads, smem_attn_mma(P), st, (const float*)w.q, (const float*)w.k, (const float*)w.v,
-                   w.o, P, need, (int)items, kOTile);
-      }
+                   w.o, P, need, (int)items);
+      };
+      if (h->passes() == 3) launch(k_spa_attn_mma<true, kOTile != 0>);
+      else launch(k_spa_attn_mma<false, kOTile != 0>);
     } else {
       LFT_LAUNCH(h, k_spa_attn, (unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
                  (const float*)w.v, w.o, P, need);
