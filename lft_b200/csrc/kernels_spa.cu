@@ -726,10 +726,6 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
 #pragma unroll 1
       for (int cb = cb0; cb < ncb; cb += kWC) {
         const int bx = bx0 + 4 * cb;
-        uint32_t qnh[4] = {0u, 0u, 0u, 0u}, qnl[4] = {0u, 0u, 0u, 0u};
-        // the next block's queries (of this item or of the next one) in flight under this block's MMAs
-        const bool same = cb + kWC < ncb;
-        if (same || k + 1 < nk) load_q(same ? Qw : Qn, same ? cb + kWC : cb0, qnh, qnl);
         // ---- S = Q K^T on top of the masks: n8 tile j = key row by - 2 + j, keys bx - 2 .. bx + 5 (column = 2c + e of the tile)
         const uint32_t kcol = (uint32_t)min(max(bx - 2 + mr, kxlo), kxhi) * 16;
         float cb_[2];
@@ -740,8 +736,8 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
         for (int j = 0; j < 8; ++j) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            s[j][e] = j < 6 ? fminf(rbA[j], cb_[e]) : NINF;
-            s[j][2 + e] = j >= 2 ? fminf(rbB[j - 2], cb_[e]) : NINF;
+                s[j][e] = j < 6 ? fminf(rbA[j], cb_[e]) : 0.f;          // (the row halves no lane's window reaches are never read)
+            s[j][2 + e] = j >= 2 ? fminf(rbB[j - 2], cb_[e]) : 0.f;
           }
           uint32_t kb[4];
           ldsm4(ks + koff[j] + kcol, kb);
@@ -750,6 +746,12 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
             hmma16816(s[j], ql, kb[0], kb[1]);
             hmma16816(s[j], qh, kb[2], kb[3]);
           }
+        }
+        // the Q fragments are dead: the next block's queries (of this item or of the next one) are loaded straight into their
+        // registers and have the soft-max and P V of this block to arrive
+        {
+          const bool same = cb + kWC < ncb;
+          if (same || k + 1 < nk) load_q(same ? Qw : Qn, same ? cb + kWC : cb0, qh, ql);
         }
         // ---- soft-max (masked entries are -inf; every query sees itself, so the row maxima are finite).  Packed f32x2 math on
         // the accumulator pairs, two partial sums per row half (short dependency chains: four warps per scheduler is all the
@@ -875,8 +877,6 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
           if (okq) st_stream_v4(Ob + ooff + (uint32_t)(2 * d * P + qx) * 4, out);
         }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { qh[i] = qnh[i]; ql[i] = qnl[i]; }
       }
     }
     // Buffer release without a CTA-wide barrier (the warps of a scheduler should drift apart: in lockstep they all want the
