@@ -255,7 +255,14 @@ LFT_DEVINL void split8(const float* x, uint4& hi, uint4& lo, bool fp32_mode) {
   for (int i = 0; i < 4; ++i) {
     const uint32_t a = __float_as_uint(x[2 * i]), b = __float_as_uint(x[2 * i + 1]);
     h[i] = __byte_perm(a, b, 0x7632);
-    l[i] = pack_bf16(x[2 * i] - __uint_as_float(a & 0xffff0000u), x[2 * i + 1] - __uint_as_float(b & 0xffff0000u));
+    // x - trunc(x) for the pair in one packed FFMA (exact: the same bits as two subtractions)
+    unsigned long long t2, x2, r2;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "r"(a & 0xffff0000u), "r"(b & 0xffff0000u));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "r"(a), "r"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r2) : "l"(t2), "l"(0xbf800000bf800000ull), "l"(x2));
+    float r0, r1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r2));
+    l[i] = pack_bf16(r0, r1);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
