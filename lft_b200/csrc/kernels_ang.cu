@@ -521,13 +521,16 @@ LFT_DEVINL void ang_attention_mma25(uint32_t trow, int warp, int lane, int q, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) pv[j] = __ldg(pq4 + (col / 4 + j) * N);
     tmem_ld16(trow + col, kv);
+    const f32x2 nmr2 = pack2(-mr, -mr), rstd2 = pack2(rstd, rstd), sc2 = pack2(sc, sc);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 4; ++j) {   // sc * (rstd * (acc + PE W') - mr * u + c), two columns per packed instruction (same roundings)
       const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
-      kv[4 * j] = sc * fmaf(rstd, kv[4 * j] + pv[j].x, fmaf(-mr, uv.x, cv.x));
-      kv[4 * j + 1] = sc * fmaf(rstd, kv[4 * j + 1] + pv[j].y, fmaf(-mr, uv.y, cv.y));
-      kv[4 * j + 2] = sc * fmaf(rstd, kv[4 * j + 2] + pv[j].z, fmaf(-mr, uv.z, cv.z));
-      kv[4 * j + 3] = sc * fmaf(rstd, kv[4 * j + 3] + pv[j].w, fmaf(-mr, uv.w, cv.w));
+      const f32x2 a = mul2(sc2, fma2(rstd2, add2(pack2(kv[4 * j], kv[4 * j + 1]), pack2(pv[j].x, pv[j].y)),
+                                     fma2(nmr2, pack2(uv.x, uv.y), pack2(cv.x, cv.y))));
+      const f32x2 b = mul2(sc2, fma2(rstd2, add2(pack2(kv[4 * j + 2], kv[4 * j + 3]), pack2(pv[j].z, pv[j].w)),
+                                     fma2(nmr2, pack2(uv.z, uv.w), pack2(cv.z, cv.w))));
+      unpack2(a, kv[4 * j], kv[4 * j + 1]);
+      unpack2(b, kv[4 * j + 2], kv[4 * j + 3]);
     }
     put(plane, rh0, kv);
     put(plane, rh0 + 1, kv + 8);
@@ -631,13 +634,16 @@ LFT_DEVINL void ang_attention_mma_g(uint32_t trow, int warp, int lane, int q, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) pv[j] = __ldg(pq4 + (col / 4 + j) * N);
     tmem_ld16(trow + col, kv);
+    const f32x2 nmr2 = pack2(-mr, -mr), rstd2 = pack2(rstd, rstd), sc2 = pack2(sc, sc);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 4; ++j) {   // sc * (rstd * (acc + PE W') - mr * u + c), two columns per packed instruction (same roundings)
       const float4 uv = tab4[col / 4 + j], cv = tab4[32 + col / 4 + j];
-      kv[4 * j] = sc * fmaf(rstd, kv[4 * j] + pv[j].x, fmaf(-mr, uv.x, cv.x));
-      kv[4 * j + 1] = sc * fmaf(rstd, kv[4 * j + 1] + pv[j].y, fmaf(-mr, uv.y, cv.y));
-      kv[4 * j + 2] = sc * fmaf(rstd, kv[4 * j + 2] + pv[j].z, fmaf(-mr, uv.z, cv.z));
-      kv[4 * j + 3] = sc * fmaf(rstd, kv[4 * j + 3] + pv[j].w, fmaf(-mr, uv.w, cv.w));
+      const f32x2 a = mul2(sc2, fma2(rstd2, add2(pack2(kv[4 * j], kv[4 * j + 1]), pack2(pv[j].x, pv[j].y)),
+                                     fma2(nmr2, pack2(uv.x, uv.y), pack2(cv.x, cv.y))));
+      const f32x2 b = mul2(sc2, fma2(rstd2, add2(pack2(kv[4 * j + 2], kv[4 * j + 3]), pack2(pv[j].z, pv[j].w)),
+                                     fma2(nmr2, pack2(uv.z, uv.w), pack2(cv.z, cv.w))));
+      unpack2(a, kv[4 * j], kv[4 * j + 1]);
+      unpack2(b, kv[4 * j + 2], kv[4 * j + 3]);
     }
     put(plane, rh0, kv);
     put(plane, rh0 + 1, kv + 8);
