@@ -884,7 +884,9 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
     // A warp's ldmatrix reads have completed when it gets here (their HMMAs have been issued).
     __syncwarp();
     if (lane == 0) {
+      __threadfence_block();   // release: this warp's reads of the buffer are ordered before the count ...
       const unsigned done = atomicAdd(&cnt[k & 1], 1u) + 1u;
+      __threadfence_block();   // ... acquire: and every counted warp's before the refill issued below
       if (done == (unsigned)(kAttnMmaThreads / 32) * (unsigned)((k >> 1) + 1) && k + 2 < nk) issue(k + 2);
     }
   }
