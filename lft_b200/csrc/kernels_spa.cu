@@ -141,9 +141,11 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
     RingState<NST> rs;
     for (int k = 0; k < ntl; ++k) {
       ring_produce<NST>(rs, ring, kSpaStage, full0, empty0, g_c, passes);
+#ifndef LFT_X_EMBED_ONLY   // (defined: timing experiment - token embedding only, no Q / K / V projections at all)
       ring_produce<NST>(rs, ring, kSpaStage, full0, empty0, g_q, passes);
       ring_produce<NST>(rs, ring, kSpaStage, full0, empty0, g_k, passes);
       ring_produce<NST>(rs, ring, kSpaStage, full0, empty0, g_v, passes);
+#endif
     }
   } else if (warp == kWarpMma2) {
     RingState<NST> rs;
@@ -161,6 +163,9 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
                                 c_lo + kConvOff * 16, kConvRows * 16, 0, shift, tmem, true);
       umma_commit_elected(mma_done);
       LFT_TL2(13);
+#ifdef LFT_X_EMBED_ONLY
+      continue;
+#endif
       mbar_wait(a_ready, rpar); rpar ^= 1;
       tc_fence_after();
       LFT_TL2(14);
@@ -282,6 +287,9 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
       if (k + 1 < ntl) stage(k + 1);    // the staging area is free (conv MMAs of this tile are complete)
 #endif
       LFT_TL2(3);
+#ifdef LFT_X_EMBED_ONLY
+      continue;
+#endif
       const float mr = mean * rstd;
       await();  // Q
       LFT_TL2(4);
