@@ -377,6 +377,11 @@ k_spa_embed_qkv(const float* __restrict__ feat, const uint8_t* __restrict__ wmlp
   cta_teardown(ctl, warp, 256, kWarpMma2);
 }
 
+#ifndef LFT_ATTN_RB
+#define LFT_ATTN_RB 8
+#endif
+constexpr int kAttnRB = LFT_ATTN_RB;       // query rows per CTA (A/B: 16 stages 20 key rows for 16 instead of 12 for 8)
+#ifdef LFT_ATTN_V1   // the CUDA-core window attention of round 1 is only compiled into -DLFT_ATTN_V1 builds (A/B timing)
 // ------------------------------------------------------------------------------------------------
 // Window attention. One thread = one head of TWO vertically adjacent queries (y0, x), (y0+1, x): the
 // 6 x 5 keys their windows cover are read once (30 instead of 50 key reads).
@@ -398,10 +403,6 @@ LFT_DEVINL void axpy16(f32x2* o, float p, const ulonglong2& a, const ulonglong2&
 // CTA = (view, head, block of kAttnRB query rows): the K and V planes of rows [r0-2, r0+RB+2) are contiguous
 // in the planar layout and are staged in shared memory with two bulk copies (TMA engine).  Softmax is
 // evaluated online, one key row at a time (5 scores per query live at once).
-#ifndef LFT_ATTN_RB
-#define LFT_ATTN_RB 8
-#endif
-constexpr int kAttnRB = LFT_ATTN_RB;       // query rows per CTA (A/B: 16 stages 20 key rows for 16 instead of 12 for 8)
 constexpr int kAttnThreads = kAttnRB * 16;  // 32 x-lanes x RB/2 row pairs; wider rows (P > 32) take several passes
 constexpr size_t smem_attn(int P) { return 2 * (size_t)(kAttnRB + 4) * 4 * P * 16 + 16; }  // K and V rows [r0-2, r0+RB+2)
 
@@ -550,6 +551,8 @@ k_spa_attn(const float* __restrict__ Q, const float* __restrict__ K, const float
   }  // query pairs
   if (!staged) mbar_wait(bar, 0);  // threads without a query still wait for the copies before the CTA may exit
 }
+
+#endif  // LFT_ATTN_V1
 
 // ------------------------------------------------------------------------------------------------
 // Window attention on tensor cores (round 2, the default): S = Q K^T and O = P V of the 5 x 5 window as warp-level
@@ -900,6 +903,7 @@ k_spa_attn_mma(const float* __restrict__ Q, const float* __restrict__ K, const f
   }
 }
 
+#ifdef LFT_FFN_V1   // the first formulation of k_spa_ffn is only compiled into -DLFT_FFN_V1 builds (A/B timing)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads2, 2)
 k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_constant__ Tab512 tab,
@@ -1163,6 +1167,8 @@ k_spa_ffn(const float* __restrict__ O, float* __restrict__ tok, const __grid_con
   cta_teardown(ctl, warp, 256, kWarpMma2);
   LFT_TL(31);
 }
+
+#endif  // LFT_FFN_V1
 
 // ------------------------------------------------------------------------------------------------
 // k_spa_ffn, second formulation (round 2; the default, -DLFT_FFN_V1 selects the one above).  Same arithmetic, different residency:
@@ -1495,9 +1501,13 @@ int debug_timeline_spa(long long* out) {
 int configure_spa() {
   CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_embed<false>()));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_embed_qkv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_embed<true>()));
+#ifdef LFT_FFN_V1
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
+#endif
   CUDA_TRY(cudaFuncSetAttribute(k_spa_ffn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSpa));
+#ifdef LFT_ATTN_V1
   CUDA_TRY(cudaFuncSetAttribute(k_spa_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn(64)));
+#endif
   CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<true, kOTile != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn_mma(64)));
   CUDA_TRY(cudaFuncSetAttribute(k_spa_attn_mma<false, kOTile != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn_mma(64)));
   return 0;
@@ -1540,8 +1550,12 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
   }
   {
     Scope sc(h, K_SPA_ATTN, st, V * need.rn * need.rn);
+#ifdef LFT_ATTN_V1
     const int nblk = (need.rn + kAttnRB - 1) / kAttnRB;
-    if (kAttnMma) {
+    LFT_LAUNCH(h, k_spa_attn, (unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
+               (const float*)w.v, w.o, P, need);
+#else
+    {
       const int nb = ((need.r0 + need.rn) - (need.r0 & ~3) + kAttnRB - 1) / kAttnRB;  // attn_mma_nblk
       const long long items = V * 8 * nb;
       if (items >= (1ll << 31)) return fail(LFT_ERR_ARG, "k_spa_attn_mma: too many work items");
@@ -1553,10 +1567,8 @@ int run_spa(Handle* h, int layer, const float* in, float* out, const float* fina
       };
       if (h->passes() == 3) launch(k_spa_attn_mma<true, kOTile != 0>);
       else launch(k_spa_attn_mma<false, kOTile != 0>);
-    } else {
-      LFT_LAUNCH(h, k_spa_attn, (unsigned)(V * 8 * nblk), kAttnThreads, smem_attn(P), st, (const float*)w.q, (const float*)w.k,
-                 (const float*)w.v, w.o, P, need);
     }
+#endif
     if ((rc = sc.finish())) return rc;
   }
   {
